@@ -1,0 +1,516 @@
+// fb_xcorr.cu -- libfeabas_cuda.so: __global__ wrappers, plan / workspace caches and the
+// C ABI declared in include/feabas_cuda.h.  sm_100a only; no CPU fallback.
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/feabas_cuda.h"
+#include "fb_host_plan.h"
+#include "fb_xcorr.cuh"
+
+using namespace fb;
+
+// ---------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------
+static thread_local std::string g_err;
+static std::atomic<long long> g_launches{0};
+
+static int fail(int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) return fail(FB_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------
+template <typename T, typename TI>
+__global__ void __launch_bounds__(512) fbk_rows_forward(const __grid_constant__ XcParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    k1_rows_forward<T, TI>(p, blockIdx.x, threadIdx.x, blockDim.x, smem);
+}
+template <typename T>
+__global__ void __launch_bounds__(512) fbk_columns(const __grid_constant__ XcParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    k2_columns<T>(p, blockIdx.x, threadIdx.x, blockDim.x, smem);
+}
+template <typename T>
+__global__ void __launch_bounds__(512) fbk_rows_inverse(const __grid_constant__ XcParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    k3_rows_inverse<T>(p, blockIdx.x, threadIdx.x, blockDim.x, smem);
+}
+template <typename T>
+__global__ void __launch_bounds__(256) fbk_finalize(const __grid_constant__ XcParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    k4_finalize<T>(p, blockIdx.x, threadIdx.x, blockDim.x, smem);
+}
+template <typename T, typename TI>
+__global__ void __launch_bounds__(512) fbk_fused(const __grid_constant__ XcParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    kf_fused<T, TI>(p, blockIdx.x, threadIdx.x, blockDim.x, smem);
+}
+
+// ---------------------------------------------------------------------------
+// caches
+// ---------------------------------------------------------------------------
+struct DevTables {
+    void* tw = nullptr;
+    int* pos = nullptr;
+    std::vector<int> radix;
+};
+
+struct StreamCtx {
+    int device = 0;
+    void* ws = nullptr;            // staged-pipeline workspace
+    size_t ws_bytes = 0;
+    // host path
+    cudaStream_t copy_stream = nullptr, own_stream = nullptr;
+    void* din[2] = {nullptr, nullptr};
+    size_t din_bytes = 0;
+    void* pin[2] = {nullptr, nullptr};
+    size_t pin_bytes = 0;
+    double* dout = nullptr;
+    size_t dout_bytes = 0;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+};
+
+static std::mutex g_mu;
+static std::map<std::tuple<int, int, int>, DevTables> g_tables;      // (device, n, is_double)
+static std::map<std::pair<int, void*>, StreamCtx> g_ctx;              // (device, stream)
+static std::map<int, bool> g_attr_done;
+static long long g_opt_ws_bytes = 2LL << 30;
+static long long g_opt_host_chunk = 64LL << 20;
+
+template <typename T>
+static int get_tables(int device, int n, Plan1D& out)
+{
+    auto key = std::make_tuple(device, n, (int)(sizeof(T) == 8));
+    auto it = g_tables.find(key);
+    if (it == g_tables.end()) {
+        DevTables t;
+        t.radix = radix_sequence(n);
+        if ((int)t.radix.size() > kMaxPass) return fail(FB_ESIZE, "fft length %d needs too many passes", n);
+        auto pos = digit_positions(n, t.radix);
+        auto tw = twiddle_table<T>(n);
+        CU(cudaMalloc(&t.tw, tw.size() * sizeof(cx<T>)));
+        CU(cudaMalloc((void**)&t.pos, pos.size() * sizeof(int)));
+        CU(cudaMemcpy(t.tw, tw.data(), tw.size() * sizeof(cx<T>), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(t.pos, pos.data(), pos.size() * sizeof(int), cudaMemcpyHostToDevice));
+        it = g_tables.emplace(key, t).first;
+    }
+    const DevTables& t = it->second;
+    out.n = n;
+    out.npass = (int)t.radix.size();
+    for (int i = 0; i < out.npass; ++i) out.radix[i] = t.radix[i];
+    out.tw = t.tw;
+    out.pos = t.pos;
+    return FB_OK;
+}
+
+template <typename F>
+static int raise_smem(F* fn)
+{
+    CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+    return FB_OK;
+}
+
+static int set_attrs(int device)
+{
+    if (g_attr_done[device]) return FB_OK;
+    int rc;
+#define RS(k) if ((rc = raise_smem(k)) != FB_OK) return rc
+    RS((fbk_rows_forward<float, float>));
+    RS((fbk_rows_forward<float, unsigned char>));
+    RS((fbk_rows_forward<double, unsigned char>));
+    RS((fbk_rows_forward<double, double>));
+    RS((fbk_columns<float>));
+    RS((fbk_columns<double>));
+    RS((fbk_rows_inverse<float>));
+    RS((fbk_rows_inverse<double>));
+    RS((fbk_finalize<float>));
+    RS((fbk_finalize<double>));
+    RS((fbk_fused<float, float>));
+    RS((fbk_fused<float, unsigned char>));
+    RS((fbk_fused<double, unsigned char>));
+    RS((fbk_fused<double, double>));
+#undef RS
+    g_attr_done[device] = true;
+    return FB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// geometry / validation
+// ---------------------------------------------------------------------------
+struct Problem {
+    int n, h0, w0, h1, w1, in_dtype, ny, nx, flags;
+    int conf_mode, subpixel;
+    bool f64;       // compute type
+    int isz;        // bytes per input element
+    Geometry g;
+    bool fused;
+    size_t ws_per_pair;
+    int nrt;
+};
+
+static int make_problem(Problem& q, int n, int h0, int w0, int h1, int w1, int in_dtype, int fft_h, int fft_w, int flags)
+{
+    if (n < 0 || h0 < 1 || w0 < 1 || h1 < 1 || w1 < 1) return fail(FB_EINVAL, "bad shape n=%d %dx%d / %dx%d", n, h0, w0, h1, w1);
+    if (in_dtype < FB_F32 || in_dtype > FB_F64) return fail(FB_EINVAL, "bad in_dtype %d", in_dtype);
+    if (fft_h < (h0 > h1 ? h0 : h1) || fft_w < (w0 > w1 ? w0 : w1)) return fail(FB_EINVAL, "fft grid %dx%d smaller than the images", fft_h, fft_w);
+    if (!is_5smooth(fft_h) || !is_5smooth(fft_w)) return fail(FB_ESIZE, "fft grid %dx%d is not 2^a 3^b 5^c", fft_h, fft_w);
+    if ((long long)fft_h * fft_w >= (1LL << 31)) return fail(FB_ESIZE, "fft grid %dx%d too large", fft_h, fft_w);
+    q.n = n; q.h0 = h0; q.w0 = w0; q.h1 = h1; q.w1 = w1; q.in_dtype = in_dtype; q.ny = fft_h; q.nx = fft_w; q.flags = flags;
+    q.conf_mode = (flags >> FB_CONF_SHIFT) & 3;
+    if (q.conf_mode > 2) return fail(FB_EINVAL, "bad conf_mode %d", q.conf_mode);
+    q.subpixel = (flags & FB_FLAG_SUBPIXEL) ? 1 : 0;
+    q.f64 = in_dtype == FB_F64 || (in_dtype == FB_U8 && !(flags & FB_FLAG_U8_AS_F32));
+    q.isz = in_dtype == FB_F32 ? 4 : (in_dtype == FB_U8 ? 1 : 8);
+    Geometry& g = q.g;
+    g = Geometry{};
+    g.h0 = h0; g.w0 = w0; g.h1 = h1; g.w1 = w1; g.ny = fft_h; g.nx = fft_w;
+    g.esize = q.f64 ? 16 : 8;
+    g.mirror = q.conf_mode == CONF_MIRROR;
+    if (!choose_tiles(g)) return fail(FB_ESIZE, "fft grid %dx%d does not fit the kernels' shared-memory tiling", fft_h, fft_w);
+    q.fused = g.fused;
+    if (flags & FB_FLAG_FORCE_STAGED) {
+        if (!g.tl_row || !g.tc_col) return fail(FB_ESIZE, "staged path unavailable for %dx%d", fft_h, fft_w);
+        q.fused = false;
+    }
+    if (flags & FB_FLAG_FORCE_FUSED) {
+        if (!g.fused) return fail(FB_ESIZE, "fused path unavailable for %dx%d", fft_h, fft_w);
+        q.fused = true;
+    }
+    const int rpt = g.mirror ? g.tl_row : 2 * g.tl_row;
+    q.nrt = q.fused ? 0 : (fft_h + rpt - 1) / rpt;
+    q.ws_per_pair = q.fused ? 0
+                            : ((size_t)(h0 + h1) * g.fpitch + (size_t)fft_h * 2 * g.fpitch) * g.esize + (size_t)q.nrt * sizeof(Partial);
+    q.ws_per_pair = (q.ws_per_pair + 255) & ~(size_t)255;
+    return FB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// launch of one chunk (device pointers)
+// ---------------------------------------------------------------------------
+template <typename T, typename TI>
+static int launch_chunk(const Problem& q, StreamCtx& ctx, const void* img0, const void* img1, int nb,
+                        double* dx, double* dy, double* conf, double* peak, double* mir, cudaStream_t st)
+{
+    XcParams p{};
+    int rc;
+    if ((rc = get_tables<T>(ctx.device, q.nx, p.px)) != FB_OK) return rc;
+    if ((rc = get_tables<T>(ctx.device, q.ny, p.py)) != FB_OK) return rc;
+    const Geometry& g = q.g;
+    p.img0 = img0; p.img1 = img1; p.n = nb;
+    p.h0 = q.h0; p.w0 = q.w0; p.h1 = q.h1; p.w1 = q.w1; p.ny = q.ny; p.nx = q.nx; p.kp = g.kp;
+    p.fpitch = g.fpitch; p.dx = dx; p.dy = dy; p.conf = conf; p.peak = peak; p.mir = mir;
+    p.conf_mode = q.conf_mode; p.subpixel = q.subpixel; p.scale = 1.0 / ((double)q.ny * (double)q.nx);
+    if (q.fused) {
+        p.tl = g.tl_fused; p.spitch = g.spitch;
+        int nthr = g.smem_fused > 100 * 1024 ? 512 : 256;
+        fbk_fused<T, TI><<<nb, nthr, g.smem_fused, st>>>(p);
+        g_launches += 1;
+        CU(cudaGetLastError());
+        return FB_OK;
+    }
+    p.tl = g.tl_row; p.tc = g.tc_col; p.nrt = q.nrt;
+    unsigned char* w = reinterpret_cast<unsigned char*>(ctx.ws);
+    size_t f0 = (size_t)nb * q.h0 * g.fpitch * g.esize, f1 = (size_t)nb * q.h1 * g.fpitch * g.esize;
+    size_t gg = (size_t)nb * q.ny * 2 * g.fpitch * g.esize;
+    p.F0 = w; p.F1 = w + f0; p.G = w + f0 + f1; p.part = reinterpret_cast<Partial*>(w + f0 + f1 + gg);
+    const int t0 = row_tiles<T>(q.h0, p.tl), t1 = row_tiles<T>(q.h1, p.tl);
+    const int nct = (g.kp + p.tc - 1) / p.tc;
+    fbk_rows_forward<T, TI><<<nb * (t0 + t1), g.nthreads_row, g.smem_row, st>>>(p);
+    fbk_columns<T><<<nb * nct, g.nthreads_col, g.smem_col, st>>>(p);
+    fbk_rows_inverse<T><<<nb * q.nrt, g.nthreads_row, g.smem_row, st>>>(p);
+    fbk_finalize<T><<<nb, 256, (size_t)q.nx * 4 * sizeof(cx<T>) + 2048, st>>>(p);
+    g_launches += 4;
+    CU(cudaGetLastError());
+    return FB_OK;
+}
+
+static int launch_chunk_any(const Problem& q, StreamCtx& ctx, const void* img0, const void* img1, int nb,
+                            double* dx, double* dy, double* conf, double* peak, double* mir, cudaStream_t st)
+{
+    if (q.in_dtype == FB_F32) return launch_chunk<float, float>(q, ctx, img0, img1, nb, dx, dy, conf, peak, mir, st);
+    if (q.in_dtype == FB_U8) {
+        if (q.f64) return launch_chunk<double, unsigned char>(q, ctx, img0, img1, nb, dx, dy, conf, peak, mir, st);
+        return launch_chunk<float, unsigned char>(q, ctx, img0, img1, nb, dx, dy, conf, peak, mir, st);
+    }
+    return launch_chunk<double, double>(q, ctx, img0, img1, nb, dx, dy, conf, peak, mir, st);
+}
+
+// all pointers device; loops over workspace-sized chunks
+static int run_device(const Problem& q, StreamCtx& ctx, const void* img0, const void* img1, int n,
+                      double* dx, double* dy, double* conf, double* peak, double* mir, cudaStream_t st)
+{
+    int chunk = n;
+    if (!q.fused) {
+        long long fit = g_opt_ws_bytes / (long long)q.ws_per_pair;
+        if (fit < 1) fit = 1;
+        if (chunk > fit) chunk = (int)fit;
+        size_t need = (size_t)chunk * q.ws_per_pair;
+        if (need > ctx.ws_bytes) {
+            if (ctx.ws) { CU(cudaStreamSynchronize(st)); CU(cudaFree(ctx.ws)); ctx.ws = nullptr; ctx.ws_bytes = 0; }
+            if (cudaMalloc(&ctx.ws, need) != cudaSuccess) { cudaGetLastError(); return fail(FB_ENOMEM, "workspace of %zu bytes", need); }
+            ctx.ws_bytes = need;
+        }
+    } else if (chunk > 65535 * 16) {
+        chunk = 65535 * 16;
+    }
+    const size_t b0 = (size_t)q.h0 * q.w0 * q.isz, b1 = (size_t)q.h1 * q.w1 * q.isz;
+    for (int lo = 0; lo < n; lo += chunk) {
+        int nb = n - lo < chunk ? n - lo : chunk;
+        int rc = launch_chunk_any(q, ctx, (const char*)img0 + lo * b0, (const char*)img1 + lo * b1, nb,
+                                  dx + lo, dy + lo, conf + lo, peak ? peak + lo : nullptr, mir ? mir + lo : nullptr, st);
+        if (rc != FB_OK) return rc;
+    }
+    return FB_OK;
+}
+
+static int get_ctx(int device, void* stream, StreamCtx*& out)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(FB_ECUDA, "no CUDA device available (this library has no CPU fallback)");
+    }
+    if (device < 0 || device >= ndev) return fail(FB_EINVAL, "device %d out of range (%d devices)", device, ndev);
+    CU(cudaSetDevice(device));
+    int rc = set_attrs(device);
+    if (rc != FB_OK) return rc;
+    StreamCtx& c = g_ctx[std::make_pair(device, stream)];
+    c.device = device;
+    out = &c;
+    return FB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+extern "C" int fb_xcorr_batch_device(const void* img0, const void* img1, int n, int h0, int w0, int h1, int w1,
+                                     int in_dtype, int fft_h, int fft_w, int flags,
+                                     double* dx, double* dy, double* conf, double* peak, double* mirror,
+                                     int device, void* stream)
+{
+    Problem q;
+    int rc = make_problem(q, n, h0, w0, h1, w1, in_dtype, fft_h, fft_w, flags);
+    if (rc != FB_OK) return rc;
+    if (n == 0) return FB_OK;
+    if (!img0 || !img1 || !dx || !dy || !conf) return fail(FB_EINVAL, "null pointer");
+    std::lock_guard<std::mutex> lk(g_mu);
+    StreamCtx* ctx;
+    if ((rc = get_ctx(device, stream, ctx)) != FB_OK) return rc;
+    return run_device(q, *ctx, img0, img1, n, dx, dy, conf, peak, mirror, (cudaStream_t)stream);
+}
+
+extern "C" int fb_xcorr_batch_host(const void* img0, const void* img1, int n, int h0, int w0, int h1, int w1,
+                                   int in_dtype, int fft_h, int fft_w, int flags,
+                                   double* dx, double* dy, double* conf, double* peak, double* mirror,
+                                   int device, void* stream)
+{
+    Problem q;
+    int rc = make_problem(q, n, h0, w0, h1, w1, in_dtype, fft_h, fft_w, flags);
+    if (rc != FB_OK) return rc;
+    if (n == 0) return FB_OK;
+    if (!img0 || !img1 || !dx || !dy || !conf) return fail(FB_EINVAL, "null pointer");
+    std::lock_guard<std::mutex> lk(g_mu);
+    StreamCtx* cp;
+    if ((rc = get_ctx(device, stream, cp)) != FB_OK) return rc;
+    StreamCtx& c = *cp;
+    if (!c.copy_stream) {
+        CU(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CU(cudaEventCreateWithFlags(&c.ev_copied[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&c.ev_done[i], cudaEventDisableTiming));
+        }
+    }
+    cudaStream_t st = stream ? (cudaStream_t)stream : c.own_stream;
+    const size_t b0 = (size_t)h0 * w0 * q.isz, b1 = (size_t)h1 * w1 * q.isz;
+    long long hc = g_opt_host_chunk / (long long)(b0 + b1);
+    if (hc < 1) hc = 1;
+    if (hc > n) hc = n;
+    // pinned or pageable?
+    cudaPointerAttributes a0{}, a1{};
+    bool pinned = cudaPointerGetAttributes(&a0, img0) == cudaSuccess && cudaPointerGetAttributes(&a1, img1) == cudaSuccess &&
+                  a0.type == cudaMemoryTypeHost && a1.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    const size_t slot_bytes = (size_t)hc * (b0 + b1) + 512;
+    if (slot_bytes > c.din_bytes) {
+        CU(cudaDeviceSynchronize());
+        for (int i = 0; i < 2; ++i) {
+            if (c.din[i]) CU(cudaFree(c.din[i]));
+            c.din[i] = nullptr;
+            if (cudaMalloc(&c.din[i], slot_bytes) != cudaSuccess) { cudaGetLastError(); c.din_bytes = 0; return fail(FB_ENOMEM, "input slot of %zu bytes", slot_bytes); }
+        }
+        c.din_bytes = slot_bytes;
+    }
+    if (!pinned && slot_bytes > c.pin_bytes) {
+        CU(cudaDeviceSynchronize());
+        for (int i = 0; i < 2; ++i) {
+            if (c.pin[i]) CU(cudaFreeHost(c.pin[i]));
+            c.pin[i] = nullptr;
+            if (cudaMallocHost(&c.pin[i], slot_bytes) != cudaSuccess) { cudaGetLastError(); c.pin_bytes = 0; return fail(FB_ENOMEM, "pinned slot of %zu bytes", slot_bytes); }
+        }
+        c.pin_bytes = slot_bytes;
+    }
+    const size_t ob = (size_t)n * 5 * sizeof(double);
+    if (ob > c.dout_bytes) {
+        CU(cudaDeviceSynchronize());
+        if (c.dout) CU(cudaFree(c.dout));
+        c.dout = nullptr;
+        if (cudaMalloc((void**)&c.dout, ob) != cudaSuccess) { cudaGetLastError(); c.dout_bytes = 0; return fail(FB_ENOMEM, "output buffer"); }
+        c.dout_bytes = ob;
+    }
+    double* o = c.dout;
+    const size_t off1 = ((size_t)hc * b0 + 255) & ~(size_t)255;     // img1 offset inside a slot
+    int ci = 0;
+    for (int lo = 0; lo < n; lo += (int)hc, ++ci) {
+        const int nb = n - lo < hc ? n - lo : (int)hc;
+        const int s = ci & 1;
+        char* d = (char*)c.din[s];
+        const char* src0 = (const char*)img0 + (size_t)lo * b0;
+        const char* src1 = (const char*)img1 + (size_t)lo * b1;
+        if (ci >= 2) {
+            if (pinned) CU(cudaStreamWaitEvent(c.copy_stream, c.ev_done[s], 0));
+            else CU(cudaEventSynchronize(c.ev_done[s]));      // also implies the slot's H2D finished
+        }
+        if (!pinned) {
+            memcpy(c.pin[s], src0, (size_t)nb * b0);
+            memcpy((char*)c.pin[s] + off1, src1, (size_t)nb * b1);
+            src0 = (const char*)c.pin[s];
+            src1 = (const char*)c.pin[s] + off1;
+        }
+        CU(cudaMemcpyAsync(d, src0, (size_t)nb * b0, cudaMemcpyHostToDevice, c.copy_stream));
+        CU(cudaMemcpyAsync(d + off1, src1, (size_t)nb * b1, cudaMemcpyHostToDevice, c.copy_stream));
+        CU(cudaEventRecord(c.ev_copied[s], c.copy_stream));
+        CU(cudaStreamWaitEvent(st, c.ev_copied[s], 0));
+        rc = run_device(q, c, d, d + off1, nb, o + lo, o + n + lo, o + 2 * (size_t)n + lo, o + 3 * (size_t)n + lo, o + 4 * (size_t)n + lo, st);
+        if (rc != FB_OK) return rc;
+        CU(cudaEventRecord(c.ev_done[s], st));
+    }
+    CU(cudaMemcpyAsync(dx, o, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(dy, o + n, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(conf, o + 2 * (size_t)n, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (peak) CU(cudaMemcpyAsync(peak, o + 3 * (size_t)n, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (mirror) CU(cudaMemcpyAsync(mirror, o + 4 * (size_t)n, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return FB_OK;
+}
+
+extern "C" int fb_xcorr_batch(const void* img0, const void* img1, int n, int h0, int w0, int h1, int w1,
+                              int in_dtype, int fft_h, int fft_w, int flags,
+                              double* dx, double* dy, double* conf, double* peak, double* mirror,
+                              int device, void* stream)
+{
+    cudaPointerAttributes a{};
+    bool on_device = img0 && cudaPointerGetAttributes(&a, img0) == cudaSuccess &&
+                     (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged);
+    cudaGetLastError();
+    if (on_device)
+        return fb_xcorr_batch_device(img0, img1, n, h0, w0, h1, w1, in_dtype, fft_h, fft_w, flags, dx, dy, conf, peak, mirror, device, stream);
+    return fb_xcorr_batch_host(img0, img1, n, h0, w0, h1, w1, in_dtype, fft_h, fft_w, flags, dx, dy, conf, peak, mirror, device, stream);
+}
+
+extern "C" int fb_next_fast_len(int target)
+{
+    if (target <= 1) return 1;
+    for (int n = target;; ++n)
+        if (is_5smooth(n)) return n;
+}
+
+extern "C" int fb_xcorr_plan_info(int h0, int w0, int h1, int w1, int in_dtype, int fft_h, int fft_w, int flags,
+                                  long long* info)
+{
+    Problem q;
+    int rc = make_problem(q, 1, h0, w0, h1, w1, in_dtype, fft_h, fft_w, flags);
+    if (rc != FB_OK) return rc;
+    if (!info) return fail(FB_EINVAL, "null info");
+    info[0] = q.fused ? 1 : 2;
+    info[1] = (long long)q.ws_per_pair;
+    info[2] = q.g.fused ? (long long)q.g.smem_fused : 0;
+    info[3] = (long long)q.g.smem_row;
+    info[4] = (long long)q.g.smem_col;
+    info[5] = q.fused ? q.g.tl_fused : q.g.tl_row;
+    info[6] = q.g.tc_col;
+    info[7] = q.fused ? 1 : 4;
+    return FB_OK;
+}
+
+extern "C" int fb_set_option(const char* name, long long value)
+{
+    if (!name) return fail(FB_EINVAL, "null option name");
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!strcmp(name, "ws_bytes")) { if (value < (1 << 20)) return fail(FB_EINVAL, "ws_bytes too small"); g_opt_ws_bytes = value; return FB_OK; }
+    if (!strcmp(name, "host_chunk_bytes")) { if (value < 4096) return fail(FB_EINVAL, "host_chunk_bytes too small"); g_opt_host_chunk = value; return FB_OK; }
+    return fail(FB_EINVAL, "unknown option %s", name);
+}
+
+extern "C" long long fb_launch_count(void) { return g_launches.load(); }
+
+extern "C" int fb_release(int device)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (auto it = g_ctx.begin(); it != g_ctx.end();) {
+        StreamCtx& c = it->second;
+        if (device >= 0 && c.device != device) { ++it; continue; }
+        cudaSetDevice(c.device);
+        cudaDeviceSynchronize();
+        if (c.ws) cudaFree(c.ws);
+        for (int i = 0; i < 2; ++i) {
+            if (c.din[i]) cudaFree(c.din[i]);
+            if (c.pin[i]) cudaFreeHost(c.pin[i]);
+            if (c.ev_copied[i]) cudaEventDestroy(c.ev_copied[i]);
+            if (c.ev_done[i]) cudaEventDestroy(c.ev_done[i]);
+        }
+        if (c.dout) cudaFree(c.dout);
+        if (c.copy_stream) cudaStreamDestroy(c.copy_stream);
+        if (c.own_stream) cudaStreamDestroy(c.own_stream);
+        it = g_ctx.erase(it);
+    }
+    for (auto it = g_tables.begin(); it != g_tables.end();) {
+        if (device >= 0 && std::get<0>(it->first) != device) { ++it; continue; }
+        cudaSetDevice(std::get<0>(it->first));
+        cudaFree(it->second.tw);
+        cudaFree(it->second.pos);
+        it = g_tables.erase(it);
+    }
+    cudaGetLastError();
+    return FB_OK;
+}
+
+extern "C" int fb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" const char* fb_last_error(void) { return g_err.c_str(); }
+extern "C" const char* fb_version(void) { return "feabas_cuda 0.1 (sm_100a)"; }

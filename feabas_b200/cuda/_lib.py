@@ -1,0 +1,83 @@
+"""ctypes binding of libfeabas_cuda.so (C ABI: include/feabas_cuda.h).
+
+The library is built in-tree by ``python -m feabas_b200.csrc.build`` (or
+``__graft_entry__.build()``).  There is no CPU fallback: if the shared library
+is missing, or no CUDA device is present when a compute entry point is called,
+the call raises.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), 'csrc', 'libfeabas_cuda.so')
+
+FB_F32, FB_U8, FB_F64 = 0, 1, 2
+FB_FLAG_PAD = 0x1
+FB_FLAG_SUBPIXEL = 0x2
+FB_CONF_SHIFT = 2
+FB_FLAG_FORCE_STAGED = 0x10
+FB_FLAG_FORCE_FUSED = 0x20
+FB_FLAG_U8_AS_F32 = 0x40
+
+_vp, _i, _ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong
+_XCORR_ARGS = [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]
+
+# every symbol include/feabas_cuda.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    'fb_xcorr_batch_device': (_i, _XCORR_ARGS),
+    'fb_xcorr_batch_host': (_i, _XCORR_ARGS),
+    'fb_xcorr_batch': (_i, _XCORR_ARGS),
+    'fb_next_fast_len': (_i, [_i]),
+    'fb_xcorr_plan_info': (_i, [_i, _i, _i, _i, _i, _i, _i, _i, ctypes.POINTER(_ll)]),
+    'fb_set_option': (_i, [ctypes.c_char_p, _ll]),
+    'fb_launch_count': (_ll, []),
+    'fb_release': (_i, [_i]),
+    'fb_device_count': (_i, []),
+    'fb_last_error': (ctypes.c_char_p, []),
+    'fb_version': (ctypes.c_char_p, []),
+}
+
+_lib = None
+
+
+class FeabasCudaError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load (once) and return the ctypes handle; raises if the .so is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FeabasCudaError(
+                f'{LIB_PATH} not found: build it with `python -m feabas_b200.csrc.build` '
+                '(feabas_b200 has no CPU fallback)')
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(handle, name)          # AttributeError if the .so lacks a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise FeabasCudaError(f'libfeabas_cuda error {rc}: {lib().fb_last_error().decode()}')
+
+
+def plan_info(h0, w0, h1, w1, in_dtype, fft_h, fft_w, flags):
+    buf = (_ll * 8)()
+    check(lib().fb_xcorr_plan_info(h0, w0, h1, w1, in_dtype, fft_h, fft_w, flags, buf))
+    keys = ('path', 'ws_bytes_per_pair', 'smem_fused', 'smem_row', 'smem_col', 'row_tile', 'col_tile', 'launches_per_chunk')
+    out = dict(zip(keys, list(buf)))
+    out['path'] = {1: 'fused', 2: 'staged'}[out['path']]
+    return out
+
+
+def launch_count():
+    return int(lib().fb_launch_count())
+
+
+def set_option(name, value):
+    check(lib().fb_set_option(name.encode(), int(value)))
