@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""Benchmark of the xcorr hot path (BASELINE.json metric: xcorr block-matches/sec + HBM GB/s vs
+roofline, next to the host-CPU reference).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+A step = one pass of ``xcorr_fft`` over one batch of synthetic EM-like block pairs.  Default
+workload ``xcorr512``: 512x512 float32 blocks, pad=True (FFT 1024x1024), FFT_CONF_MIRROR,
+subpixel=True -- the block shape of BASELINE.json configs[3]/[4] and of the north-star target.
+N > 1 (torchrun, one process per GPU): every rank processes its own batch (independent pairs,
+no data-path collective; weak scaling); time = max over ranks.
+
+Prints ONE JSON line on rank 0 (see DESIGN.md "Measurement" for every key).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (block h, w, pad, pairs per step per GPU)
+    'xcorr512': dict(h=512, w=512, pad=True, batch=256),
+    'xcorr512_nopad': dict(h=512, w=512, pad=False, batch=512),
+    'xcorr128': dict(h=128, w=128, pad=True, batch=4096),
+    'xcorr256': dict(h=256, w=256, pad=True, batch=1024),
+    'xcorr1024': dict(h=1024, w=1024, pad=True, batch=64),
+    'xcorr2048': dict(h=2048, w=2048, pad=True, batch=16),
+    'stitch_fine': dict(h=74, w=67, pad=True, batch=16384),       # config 1/2 finest level, FFT 150x135
+    'thumb150': dict(h=150, w=150, pad=True, batch=4096),         # config 3, FFT 300x300
+}
+
+
+def algorithmic_bytes(h, w, ny, nx, mirror=True, fused=False):
+    """B_min when the pair is resident on chip, else the 3-stage B_pass."""
+    kp = nx // 2 + 1
+    n_out = 2 if mirror else 1
+    b_min = 2 * h * w * 4 + 20
+    b_pass = 2 * h * w * 4 + 2 * (2 * h * kp * 8) + 2 * (n_out * ny * kp * 8)
+    return (b_min if fused else b_pass), b_min, b_pass
+
+
+def column_kernel_bytes(h, ny, nx, mirror=True):
+    """Algorithmic bytes of the dominant kernel (column stage) per pair: read both row spectra,
+    write the P (and Q) half surfaces."""
+    kp = nx // 2 + 1
+    return 2 * h * kp * 8 + (2 if mirror else 1) * ny * kp * 8
+
+
+def make_pairs(n, h, w, seed, device, max_shift=32):
+    """Seeded synthetic EM-like block pairs with known integer displacement (torch, any device):
+    band-limited texture cut from one canvas per pair at two offsets + independent noise."""
+    import torch
+    import torch.nn.functional as F
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    m = max_shift + 8
+    shifts = torch.randint(-max_shift, max_shift + 1, (n, 2), generator=g, device=device)
+
+    def blur(x, sigma):
+        r = int(4 * sigma + 0.5)
+        t = torch.arange(-r, r + 1, device=device, dtype=torch.float32)
+        k = torch.exp(-0.5 * (t / sigma) ** 2)
+        k = k / k.sum()
+        x = F.conv2d(F.pad(x, (r, r, 0, 0), mode='replicate'), k.view(1, 1, 1, -1))
+        return F.conv2d(F.pad(x, (0, 0, r, r), mode='replicate'), k.view(1, 1, -1, 1))
+
+    a = torch.empty((n, h, w), dtype=torch.float32, device=device)
+    b = torch.empty((n, h, w), dtype=torch.float32, device=device)
+    step = max(1, min(n, (1 << 26) // ((h + 2 * m) * (w + 2 * m))))
+    for lo in range(0, n, step):
+        hi = min(n, lo + step)
+        c = torch.randn((hi - lo, 1, h + 2 * m, w + 2 * m), generator=g, device=device)
+        c = blur(c, 2.0)
+        c = c / c.std()
+        c0 = c + 0.25 * torch.randn(c.shape, generator=g, device=device)
+        c1 = c + 0.25 * torch.randn(c.shape, generator=g, device=device)
+        c0 = blur(c0, 2.5) - blur(blur(c0, 2.5), 2.5)           # DoG-like band-pass, sigma 2.5
+        c1 = blur(c1, 2.5) - blur(blur(c1, 2.5), 2.5)
+        for i in range(lo, hi):
+            dx, dy = int(shifts[i, 0]), int(shifts[i, 1])
+            a[i] = c0[i - lo, 0, m:m + h, m:m + w]
+            b[i] = c1[i - lo, 0, m - dy:m - dy + h, m - dx:m - dx + w]
+    return a, b, shifts
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port of the reference's xcorr_fft on the host cores
+# ----------------------------------------------------------------------------------------------
+_W = {}
+
+
+def _cpu_init(h, w, pad, per_worker, seed):
+    os.environ['OMP_NUM_THREADS'] = '1'                       # reference: config.py:301-310
+    import numpy as np
+    rng = np.random.default_rng(seed + os.getpid())
+    _W['a'] = rng.standard_normal((per_worker, h, w)).astype(np.float32)
+    _W['b'] = np.roll(_W['a'], (3, -5), axis=(1, 2)) + 0.1 * rng.standard_normal((per_worker, h, w)).astype(np.float32)
+    _W['pad'] = pad
+    from oracle import xcorr_oracle as xo
+    _W['f'] = xo.xcorr_oracle
+    _W['f'](_W['a'][:1], _W['b'][:1], subpixel=True, pad=pad)  # warm
+
+
+def _cpu_task(_):
+    t = time.perf_counter()
+    _W['f'](_W['a'], _W['b'], conf_mode=2, subpixel=True, pad=_W['pad'])
+    return time.perf_counter() - t
+
+
+class CpuArm:
+    """Process pool, one single-threaded worker per physical core (the reference's own parallel
+    model: feabas/concurrent.py:59-96), each running the oracle port on its own pairs."""
+
+    def __init__(self, wl, per_worker):
+        import psutil
+        from concurrent.futures import ProcessPoolExecutor
+        import multiprocessing as mp
+        self.cores = psutil.cpu_count(logical=False) or os.cpu_count() or 1
+        self.per_worker = per_worker
+        self.pool = ProcessPoolExecutor(self.cores, mp_context=mp.get_context('spawn'),
+                                        initializer=_cpu_init, initargs=(wl['h'], wl['w'], wl['pad'], per_worker, 1234))
+        list(self.pool.map(_cpu_task, range(self.cores)))      # spawn + warm every worker
+
+    def step(self):
+        """One timed pass: every worker processes its pairs once.  Returns (pairs, seconds)."""
+        t = time.perf_counter()
+        list(self.pool.map(_cpu_task, range(self.cores)))
+        return self.cores * self.per_worker, time.perf_counter() - t
+
+    def close(self):
+        self.pool.shutdown()
+
+
+def cpu_pairs_per_worker(wl, target_cpu_seconds, cores):
+    # ~48 ms per 512^2 padded pair per core; scale by FFT area
+    est = 48e-3 * (wl['h'] * wl['w'] * (4 if wl['pad'] else 1)) / (512 * 512 * 4)
+    return max(1, int(round(target_cpu_seconds / cores / max(est, 1e-5))))
+
+
+# ----------------------------------------------------------------------------------------------
+def clocks_monitor_start(gpu_index):
+    path = tempfile.mktemp(prefix='fb_clocks_', suffix='.csv')
+    q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    try:
+        proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={q}', '--format=csv,noheader,nounits', '-lms', '100', '-i', str(gpu_index)],
+                                stdout=open(path, 'w'), stderr=subprocess.DEVNULL)
+    except OSError:
+        return None, path
+    return proc, path
+
+
+def clocks_monitor_stop(proc, path):
+    out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': []}
+    if proc is None:
+        return out
+    proc.terminate()
+    try:
+        proc.wait(timeout=5)
+    except Exception:
+        proc.kill()
+    sm, mx, reasons = [], [], set()
+    try:
+        for line in open(path):
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        os.unlink(path)
+    except OSError:
+        pass
+    if sm:
+        out = {'sm_mhz': statistics.median(sm), 'sm_max_mhz': max(mx), 'reasons': sorted(reasons), 'samples': len(sm)}
+    return out
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured'
+    except Exception:
+        return 6650.0, 'fallback'
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='xcorr512', choices=sorted(WORKLOADS))
+    ap.add_argument('--batch', type=int, default=0, help='pairs per step per GPU (default: workload table)')
+    ap.add_argument('--ws-gib', type=float, default=6.0, help='HBM workspace budget (GiB)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.batch:
+        wl['batch'] = args.batch
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    warmup = max(args.warmup, 3)
+    h, w, pad, batch = wl['h'], wl['w'], wl['pad'], wl['batch']
+
+    from oracle import xcorr_oracle as xo           # bench may execute oracle/ only for the CPU legs
+    ny, nx = xo.fft_shape((h, w), (h, w), pad)
+    config = {'workload': f'{args.workload}: batched xcorr_fft, {h}x{w} float32 blocks, pad={pad} (FFT {ny}x{nx}), '
+                          f'FFT_CONF_MIRROR, subpixel=True',
+              'pairs_per_step_per_gpu': batch, 'fft': [ny, nx], 'l2': 'inputs larger than L2 (no flush needed)'}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        import psutil
+        cores = psutil.cpu_count(logical=False) or os.cpu_count() or 1
+        per_worker = cpu_pairs_per_worker(wl, 2.0 * cores, cores)      # ~2 s wall per step
+        arm = CpuArm(wl, per_worker)
+        for _ in range(warmup):
+            arm.step()
+        pairs = secs = 0
+        for _ in range(args.steps):
+            p_, s_ = arm.step()
+            pairs += p_; secs += s_
+        arm.close()
+        val = pairs / secs
+        sample = f'{per_worker} pairs per worker x {arm.cores} single-thread workers per step (oracle port of xcorr_fft, scipy pocketfft)'
+        print(json.dumps({
+            'impl': 'reference', 'metric': 'xcorr_block_matches_per_sec', 'value': val, 'unit': 'matches/s',
+            'n_gpus': args.gpus, 'steps': args.steps, 'warmup': warmup, 'ms_per_step': 1e3 * secs / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': config,
+            'cpu_baseline': {'value': val, 'unit': 'matches/s', 'cores': arm.cores, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': val, 'unit': 'matches/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+        return
+
+    # ------------------------------------------------------------------ our arm (GPU)
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    import feabas_b200.cuda as fc
+    L = fc._lib
+    L.set_option('ws_bytes', int(args.ws_gib * (1 << 30)))
+    flags = 0x2 | (2 << 2) | (1 if pad else 0)
+    info = L.plan_info(h, w, h, w, L.FB_F32, ny, nx, flags)
+    fused = info['path'] == 'fused'
+    config['path'] = info['path']
+
+    a, b, shifts = make_pairs(batch, h, w, seed=100 + rank, device=dev)
+    out = torch.empty((5, batch), dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        fc.xcorr_fft_device(a, b, subpixel=True, pad=pad, out=out)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    # correctness inside the bench: the synthetic ground truth must be recovered
+    res = out.cpu().numpy()
+    sh = shifts.cpu().numpy()
+    n_ok = int(np.sum((np.round(res[0]) == sh[:, 0]) & (np.round(res[1]) == sh[:, 1])))
+    assert n_ok == batch, f'only {n_ok}/{batch} ground-truth displacements recovered'
+
+    L.profile_read(local, stream, reset=True) if L.launch_count() else None
+    L.set_option('profile', 1)
+    mon, mon_path = clocks_monitor_start(local) if rank == 0 else (None, None)
+    launches0 = L.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = L.launch_count() - launches0
+    clocks = clocks_monitor_stop(mon, mon_path) if rank == 0 else None
+    L.set_option('profile', 0)
+    prof = L.profile_read(local, stream, reset=True)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * batch * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the public API with HOST buffers (H2D + D2H inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        ah, bh = a.cpu().pin_memory(), b.cpu().pin_memory()
+        an, bn = ah.numpy(), bh.numpy()
+        e_steps = max(3, min(args.steps, 10))
+        for _ in range(2):
+            r = fc.xcorr_fft(an, bn, subpixel=True, pad=pad, device=local)
+        assert np.array_equal(np.round(r[0]), sh[:, 0]) and np.array_equal(np.round(r[1]), sh[:, 1])
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            r = fc.xcorr_fft(an, bn, subpixel=True, pad=pad, device=local)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {'value': world * batch * e_steps / dt, 'unit': 'matches/s',
+               'h2d_bytes_per_step': int(an.nbytes + bn.nbytes), 'd2h_bytes_per_step': int(5 * 8 * batch),
+               'steps': e_steps, 'api': 'feabas_b200.cuda.xcorr_fft(numpy pinned host arrays) -> fb_xcorr_batch_host'}
+        del ah, bh
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel, from the CUDA-event times taken inside the timed region
+    peak, peak_kind = peaks()
+    b_alg, b_min, b_pass = algorithmic_bytes(h, w, ny, nx, True, fused)
+    kern = {k: {'ms_total': v[0], 'launches': v[1], 'ms_per_launch': (v[0] / v[1] if v[1] else None)} for k, v in prof.items() if v[1]}
+    dom = max(kern, key=lambda k: kern[k]['ms_total'])
+    pairs_per_launch = batch * args.steps / kern[dom]['launches']
+    if dom == 'columns':
+        bytes_per_pair = column_kernel_bytes(h, ny, nx, True)
+    elif dom == 'rows_forward':
+        bytes_per_pair = 2 * h * w * 4 + 2 * h * (nx // 2 + 1) * 8
+    elif dom == 'rows_inverse':
+        bytes_per_pair = 2 * ny * (nx // 2 + 1) * 8
+    else:
+        bytes_per_pair = b_min
+    achieved = bytes_per_pair * pairs_per_launch / (kern[dom]['ms_per_launch'] * 1e-3) / 1e9
+    roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                'traffic': None, 'peak_kind': peak_kind, 'algorithmic_bytes_per_pair': bytes_per_pair,
+                'pairs_per_launch': pairs_per_launch, 'ms_per_launch': kern[dom]['ms_per_launch'],
+                'kernel_share_of_step': kern[dom]['ms_total'] / ms if world == 1 else None,
+                'pipeline': {'bytes_per_pair': b_alg, 'b_min': b_min, 'b_pass': b_pass,
+                             'achieved': value / world * b_alg / 1e9, 'frac': value / world * b_alg / 1e9 / peak},
+                'kernels': kern}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        import psutil
+        cores = psutil.cpu_count(logical=False) or os.cpu_count() or 1
+        per_worker = cpu_pairs_per_worker(wl, 20.0, cores)
+        arm = CpuArm(wl, per_worker)
+        p_, s_ = arm.step()
+        arm.close()
+        cpu = {'value': p_ / s_, 'unit': 'matches/s', 'cores': arm.cores, 'kind': 'port',
+               'sample': f'{p_} pairs of the same workload ({per_worker} per single-thread worker, {arm.cores} workers), '
+                         f'oracle port of xcorr_fft (scipy pocketfft), {s_:.1f} s wall'}
+
+    line = {'metric': 'xcorr_block_matches_per_sec', 'value': value, 'unit': 'matches/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config,
+            'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

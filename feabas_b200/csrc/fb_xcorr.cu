@@ -98,6 +98,11 @@ struct StreamCtx {
     double* dout = nullptr;
     size_t dout_bytes = 0;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    // per-kernel timing (option "profile"): (slot, start, stop) triples not yet read back
+    std::vector<std::tuple<int, cudaEvent_t, cudaEvent_t>> prof_pending;
+    std::vector<cudaEvent_t> prof_free;
+    double prof_ms[5] = {0, 0, 0, 0, 0};
+    long long prof_n[5] = {0, 0, 0, 0, 0};
 };
 
 static std::mutex g_mu;
@@ -106,6 +111,7 @@ static std::map<std::pair<int, void*>, StreamCtx> g_ctx;              // (device
 static std::map<int, bool> g_attr_done;
 static long long g_opt_ws_bytes = 2LL << 30;
 static long long g_opt_host_chunk = 64LL << 20;
+static long long g_opt_profile = 0;
 
 template <typename T>
 static int get_tables(int device, int n, Plan1D& out)
@@ -214,6 +220,32 @@ static int make_problem(Problem& q, int n, int h0, int w0, int h1, int w1, int i
     return FB_OK;
 }
 
+
+// ---------------------------------------------------------------------------
+// optional per-kernel CUDA-event timing on the launching stream
+// ---------------------------------------------------------------------------
+enum { SLOT_ROWS_FWD = 0, SLOT_COLUMNS = 1, SLOT_ROWS_INV = 2, SLOT_FINALIZE = 3, SLOT_FUSED = 4 };
+
+static cudaEvent_t prof_event(StreamCtx& c)
+{
+    cudaEvent_t e = nullptr;
+    if (!c.prof_free.empty()) { e = c.prof_free.back(); c.prof_free.pop_back(); return e; }
+    cudaEventCreate(&e);
+    return e;
+}
+
+struct ProfScope {
+    StreamCtx& c; cudaStream_t st; int slot; cudaEvent_t a = nullptr, b = nullptr;
+    ProfScope(StreamCtx& c_, cudaStream_t st_, int slot_) : c(c_), st(st_), slot(slot_)
+    {
+        if (g_opt_profile) { a = prof_event(c); b = prof_event(c); cudaEventRecord(a, st); }
+    }
+    ~ProfScope()
+    {
+        if (a) { cudaEventRecord(b, st); c.prof_pending.emplace_back(slot, a, b); }
+    }
+};
+
 // ---------------------------------------------------------------------------
 // launch of one chunk (device pointers)
 // ---------------------------------------------------------------------------
@@ -233,7 +265,7 @@ static int launch_chunk(const Problem& q, StreamCtx& ctx, const void* img0, cons
     if (q.fused) {
         p.tl = g.tl_fused; p.spitch = g.spitch;
         int nthr = g.smem_fused > 100 * 1024 ? 512 : 256;
-        fbk_fused<T, TI><<<nb, nthr, g.smem_fused, st>>>(p);
+        { ProfScope ps(ctx, st, SLOT_FUSED); fbk_fused<T, TI><<<nb, nthr, g.smem_fused, st>>>(p); }
         g_launches += 1;
         CU(cudaGetLastError());
         return FB_OK;
@@ -245,10 +277,10 @@ static int launch_chunk(const Problem& q, StreamCtx& ctx, const void* img0, cons
     p.F0 = w; p.F1 = w + f0; p.G = w + f0 + f1; p.part = reinterpret_cast<Partial*>(w + f0 + f1 + gg);
     const int t0 = row_tiles<T>(q.h0, p.tl), t1 = row_tiles<T>(q.h1, p.tl);
     const int nct = (g.kp + p.tc - 1) / p.tc;
-    fbk_rows_forward<T, TI><<<nb * (t0 + t1), g.nthreads_row, g.smem_row, st>>>(p);
-    fbk_columns<T><<<nb * nct, g.nthreads_col, g.smem_col, st>>>(p);
-    fbk_rows_inverse<T><<<nb * q.nrt, g.nthreads_row, g.smem_row, st>>>(p);
-    fbk_finalize<T><<<nb, 256, (size_t)q.nx * 4 * sizeof(cx<T>) + 2048, st>>>(p);
+    { ProfScope ps(ctx, st, SLOT_ROWS_FWD); fbk_rows_forward<T, TI><<<nb * (t0 + t1), g.nthreads_row, g.smem_row, st>>>(p); }
+    { ProfScope ps(ctx, st, SLOT_COLUMNS); fbk_columns<T><<<nb * nct, g.nthreads_col, g.smem_col, st>>>(p); }
+    { ProfScope ps(ctx, st, SLOT_ROWS_INV); fbk_rows_inverse<T><<<nb * q.nrt, g.nthreads_row, g.smem_row, st>>>(p); }
+    { ProfScope ps(ctx, st, SLOT_FINALIZE); fbk_finalize<T><<<nb, 256, (size_t)q.nx * 4 * sizeof(cx<T>) + 2048, st>>>(p); }
     g_launches += 4;
     CU(cudaGetLastError());
     return FB_OK;
@@ -468,8 +500,34 @@ extern "C" int fb_set_option(const char* name, long long value)
     if (!name) return fail(FB_EINVAL, "null option name");
     std::lock_guard<std::mutex> lk(g_mu);
     if (!strcmp(name, "ws_bytes")) { if (value < (1 << 20)) return fail(FB_EINVAL, "ws_bytes too small"); g_opt_ws_bytes = value; return FB_OK; }
+    if (!strcmp(name, "profile")) { g_opt_profile = value ? 1 : 0; return FB_OK; }
     if (!strcmp(name, "host_chunk_bytes")) { if (value < 4096) return fail(FB_EINVAL, "host_chunk_bytes too small"); g_opt_host_chunk = value; return FB_OK; }
     return fail(FB_EINVAL, "unknown option %s", name);
+}
+
+extern "C" int fb_profile_read(int device, void* stream, double* ms5, long long* launches5, int reset)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_ctx.find(std::make_pair(device, stream));
+    if (it == g_ctx.end()) return fail(FB_EINVAL, "no context for device %d / stream %p", device, stream);
+    StreamCtx& c = it->second;
+    CU(cudaSetDevice(device));
+    for (auto& t : c.prof_pending) {
+        float ms = 0.f;
+        CU(cudaEventSynchronize(std::get<2>(t)));
+        CU(cudaEventElapsedTime(&ms, std::get<1>(t), std::get<2>(t)));
+        c.prof_ms[std::get<0>(t)] += ms;
+        c.prof_n[std::get<0>(t)] += 1;
+        c.prof_free.push_back(std::get<1>(t));
+        c.prof_free.push_back(std::get<2>(t));
+    }
+    c.prof_pending.clear();
+    for (int i = 0; i < 5; ++i) {
+        if (ms5) ms5[i] = c.prof_ms[i];
+        if (launches5) launches5[i] = c.prof_n[i];
+        if (reset) { c.prof_ms[i] = 0; c.prof_n[i] = 0; }
+    }
+    return FB_OK;
 }
 
 extern "C" long long fb_launch_count(void) { return g_launches.load(); }
@@ -490,6 +548,8 @@ extern "C" int fb_release(int device)
             if (c.ev_done[i]) cudaEventDestroy(c.ev_done[i]);
         }
         if (c.dout) cudaFree(c.dout);
+        for (auto& t : c.prof_pending) { cudaEventDestroy(std::get<1>(t)); cudaEventDestroy(std::get<2>(t)); }
+        for (auto e : c.prof_free) cudaEventDestroy(e);
         if (c.copy_stream) cudaStreamDestroy(c.copy_stream);
         if (c.own_stream) cudaStreamDestroy(c.own_stream);
         it = g_ctx.erase(it);

@@ -30,6 +30,7 @@ SYMBOLS = {
     'fb_next_fast_len': (_i, [_i]),
     'fb_xcorr_plan_info': (_i, [_i, _i, _i, _i, _i, _i, _i, _i, ctypes.POINTER(_ll)]),
     'fb_set_option': (_i, [ctypes.c_char_p, _ll]),
+    'fb_profile_read': (_i, [_i, _vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_ll), _i]),
     'fb_launch_count': (_ll, []),
     'fb_release': (_i, [_i]),
     'fb_device_count': (_i, []),
@@ -81,3 +82,14 @@ def launch_count():
 
 def set_option(name, value):
     check(lib().fb_set_option(name.encode(), int(value)))
+
+
+KERNEL_SLOTS = ('rows_forward', 'columns', 'rows_inverse', 'finalize', 'fused')
+
+
+def profile_read(device, stream, reset=True):
+    """{kernel: (total_ms, launches)} measured with CUDA events while option 'profile' is on."""
+    ms = (ctypes.c_double * 5)()
+    cnt = (_ll * 5)()
+    check(lib().fb_profile_read(int(device), stream, ms, cnt, int(reset)))
+    return {k: (ms[i], int(cnt[i])) for i, k in enumerate(KERNEL_SLOTS)}

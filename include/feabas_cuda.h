@@ -88,8 +88,15 @@ int fb_xcorr_plan_info(int h0, int w0, int h1, int w1, int in_dtype, int fft_h, 
                        long long* info8);
 
 /* Tuning knobs: "ws_bytes" (HBM workspace budget per stream context, default
- * 2 GiB), "host_chunk_bytes" (input bytes per host-path chunk, default 64 MiB). */
+ * 2 GiB), "host_chunk_bytes" (input bytes per host-path chunk, default 64 MiB),
+ * "profile" (0/1: time every kernel with CUDA events, see fb_profile_read).      */
 int fb_set_option(const char* name, long long value);
+
+/* Per-kernel device time, measured with CUDA events on the launching stream while
+ * option "profile" is 1.  Slots: 0 rows-forward, 1 columns, 2 rows-inverse,
+ * 3 finalize, 4 fused.  ms5 / launches5: arrays of 5 (accumulated since the
+ * last reset).  Synchronises the pending events of that (device, stream).     */
+int fb_profile_read(int device, void* stream, double* ms5, long long* launches5, int reset);
 
 /* Number of kernels this library has launched in this process.              */
 long long fb_launch_count(void);

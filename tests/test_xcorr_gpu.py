@@ -1,0 +1,142 @@
+"""GPU tier (-m gpu): the CUDA path, called through the C ABI (ctypes shim in
+feabas_b200.cuda), against the golden vectors of the unmodified reference, against the oracle
+on seeded inputs, and -- at the benchmark's full size -- against the synthetic ground truth."""
+import numpy as np
+import pytest
+
+from conftest import case_kwargs
+from feabas_b200 import synth
+import parity
+
+pytestmark = pytest.mark.gpu
+
+UNSUPPORTED = ('multichannel', 'normalize_masks', 'normalize_default')
+
+
+@pytest.fixture(scope='module')
+def fc():
+    import torch
+    assert torch.cuda.is_available(), 'GPU tests need a CUDA device'
+    import feabas_b200.cuda as fc
+    return fc
+
+
+def _tol(kw):
+    # FFT_CONF_STD raises a float32-rounded base to the power ny*nx (matcher.py:133): one ulp of
+    # the base moves the result by ~ny*nx*6e-8 relative, in the reference itself as well.
+    return dict(conf_rtol=5e-2) if kw.get('conf_mode', 2) == 1 else {}
+
+
+@pytest.mark.parametrize('force', [None, 'staged', 'fused'])
+def test_golden_small(fc, golden_small, force):
+    n = 0
+    for name, rec in golden_small.items():
+        if name in UNSUPPORTED:
+            continue
+        kw = case_kwargs(rec)
+        try:
+            dx, dy, cf = fc.xcorr_fft(rec['img0'], rec['img1'], force=force, **kw)
+        except fc._lib.FeabasCudaError as e:
+            assert force == 'fused' and 'unavailable' in str(e), (name, e)
+            continue
+        parity.compare(dx, dy, cf, rec['dx'], rec['dy'], rec['conf'], rec['img0'], rec['img1'], **_tol(kw), **kw)
+        n += 1
+    assert n >= (14 if force == 'fused' else 20)
+    assert fc._lib.launch_count() > 0
+
+
+def test_golden_seeded(fc, golden_seeded):
+    for name, rec in golden_seeded.items():
+        s0, s1, shifts = synth.block_pairs(int(rec['n']), rec['size'].tolist(), int(rec['seed']), max_shift=int(rec['max_shift']))
+        kw = case_kwargs(rec)
+        dx, dy, cf = fc.xcorr_fft(s0, s1, **kw)
+        parity.compare(dx, dy, cf, rec['dx'], rec['dy'], rec['conf'], s0, s1, **kw)
+        np.testing.assert_array_equal(np.round(dx), shifts[:, 0])
+        np.testing.assert_array_equal(np.round(dy), shifts[:, 1])
+
+
+@pytest.mark.parametrize('shape0,shape1,kw', [
+    ((5, 74, 67), (5, 74, 67), dict(subpixel=True)),
+    ((5, 74, 67), (5, 74, 67), dict(subpixel=True, pad=False)),
+    ((3, 33, 20), (3, 50, 64), dict(subpixel=True, pad=False)),
+    ((3, 50, 64), (3, 33, 20), dict(subpixel=True)),
+    ((4, 150, 150), (4, 150, 150), dict(subpixel=True)),                  # thumbnail 300^2 FFT
+    ((2, 280, 280), (2, 280, 280), dict(subpixel=True, conf_mode=0)),     # alignment 576^2 FFT
+    ((2, 250, 1500), (2, 250, 1500), dict(subpixel=False)),               # coarse strip 500 x 3000
+    ((1, 2000, 200), (1, 2000, 200), dict(subpixel=False)),               # coarse strip 4000 x 400
+    ((3, 256, 256), (3, 256, 256), dict(subpixel=True, conf_mode=1)),
+    ((2, 100, 90), (2, 100, 90), dict(subpixel=True, conf_mode=1, pad=False)),
+])
+def test_random_against_oracle(fc, shape0, shape1, kw):
+    rng = np.random.default_rng(abs(hash((shape0, shape1))) % (2 ** 31))
+    if shape0 == shape1:
+        a, b, _ = synth.block_pairs(shape0[0], shape0[1:], seed=shape0[1], max_shift=min(shape0[1:]) // 8)
+    else:
+        a = rng.standard_normal(shape0).astype(np.float32)
+        b = rng.standard_normal(shape1).astype(np.float32)
+    got = fc.xcorr_fft(a, b, **kw)
+    parity.check_against_oracle(got, a, b, **_tol(kw), **kw)
+
+
+@pytest.mark.parametrize('dtype', [np.uint8, np.float64])
+def test_float64_pipeline(fc, dtype):
+    a, b, _ = synth.block_pairs(3, 96, seed=5, max_shift=10, band_pass=False)
+    a, b = a.clip(0, 255).astype(dtype), b.clip(0, 255).astype(dtype)
+    for kw in (dict(subpixel=True), dict(subpixel=True, pad=False), dict(subpixel=True, conf_mode=1)):
+        got = fc.xcorr_fft(a, b, **kw)
+        parity.check_against_oracle(got, a, b, conf_rtol=1e-6 if kw.get('conf_mode', 2) != 1 else 5e-2, **kw)
+
+
+def test_device_tensors_and_host_arrays_agree(fc):
+    import torch
+    a, b, _ = synth.block_pairs(6, 128, seed=3, max_shift=16)
+    host = fc.xcorr_fft(a, b, subpixel=True)
+    dev = fc.xcorr_fft(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(), subpixel=True)
+    pinned = fc.xcorr_fft(torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory(), subpixel=True)
+    for x, y, z in zip(host, dev, pinned):
+        np.testing.assert_array_equal(x, y)
+        np.testing.assert_array_equal(x, z)
+
+
+def test_empty_batch(fc):
+    a = np.zeros((0, 16, 16), np.float32)
+    dx, dy, cf = fc.xcorr_fft(a, a)
+    assert dx.shape == dy.shape == cf.shape == (0,)
+
+
+def test_host_path_chunking(fc):
+    """Chunked, double-buffered host path must not depend on the chunk size."""
+    a, b, _ = synth.block_pairs(37, 64, seed=8, max_shift=8)
+    ref = fc.xcorr_fft(a, b, subpixel=True)
+    fc._lib.set_option('host_chunk_bytes', 5 * 2 * 64 * 64 * 4)     # 5 pairs per chunk
+    fc._lib.set_option('ws_bytes', 1 << 20)
+    try:
+        for force in (None, 'staged'):
+            got = fc.xcorr_fft(a, b, subpixel=True, force=force)
+            for x, y in zip(ref, got):
+                np.testing.assert_allclose(x, y, rtol=0, atol=1e-4)
+    finally:
+        fc._lib.set_option('host_chunk_bytes', 64 << 20)
+        fc._lib.set_option('ws_bytes', 2 << 30)
+
+
+def test_full_size_ground_truth(fc):
+    """Benchmark-sized work (512^2 blocks, FFT 1024^2): size-independent properties.
+    (1) the synthetic ground-truth shift is recovered for every pair; (2) swapping the two
+    stacks negates the displacement; (3) results do not depend on batch composition."""
+    import torch
+    n = 24
+    a, b, shifts = synth.block_pairs(n, 512, seed=4, max_shift=32)
+    ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    out = fc.xcorr_fft_device(ta, tb, subpixel=True).cpu().numpy()
+    np.testing.assert_array_equal(np.round(out[0]), shifts[:, 0])
+    np.testing.assert_array_equal(np.round(out[1]), shifts[:, 1])
+    assert np.all(out[2] > 0.5)
+    swapped = fc.xcorr_fft_device(tb, ta, subpixel=True).cpu().numpy()
+    np.testing.assert_allclose(swapped[0], -out[0], atol=0.02)
+    np.testing.assert_allclose(swapped[1], -out[1], atol=0.02)
+    np.testing.assert_allclose(swapped[2], out[2], rtol=1e-4, atol=1e-6)
+    part = fc.xcorr_fft_device(ta[5:9].contiguous(), tb[5:9].contiguous(), subpixel=True).cpu().numpy()
+    np.testing.assert_array_equal(part, out[:, 5:9])
+    # and the first two pairs against the oracle
+    parity.check_against_oracle((out[0, :2], out[1, :2], out[2, :2].astype(np.float32)), a[:2], b[:2], subpixel=True)
