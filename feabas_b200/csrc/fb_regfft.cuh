@@ -1,0 +1,96 @@
+// fb_regfft.cuh -- register-resident FFTs of 8 / 16 / 32 complex points per thread.
+//
+// Radix-2 decimation-in-frequency, fully unrolled, twiddles as compile-time
+// constants with the trivial ones (1, -i, exp(-i pi/4)) special-cased.  The
+// transform is in place on v[0..N) and leaves X[k] in v[bitrev(k)]; callers
+// index the result through brev<N>(k), which folds away at compile time.
+#pragma once
+#include "fb_fft.cuh"
+
+namespace fb {
+
+template <int N> FB_HD constexpr int brev(int k)
+{
+    int r = 0;
+    for (int b = 1; b < N; b <<= 1) { r = (r << 1) | (k & 1); k >>= 1; }
+    return r;
+}
+
+// cos / sin of 2 pi j / 32 for j = 0..8 (first octant + one), double precision literals
+FB_HD constexpr double cos32(int j)
+{
+    constexpr double c[9] = {1.0, 0.98078528040323044913, 0.92387953251128675613, 0.83146961230254523708,
+                             0.70710678118654752440, 0.55557023301960222474, 0.38268343236508977173,
+                             0.19509032201612826785, 0.0};
+    // reduce j (mod 32) to the first quadrant
+    j &= 31;
+    int q = j >> 3, r = j & 7;
+    double cs = c[r], sn = c[8 - r];
+    return q == 0 ? cs : (q == 1 ? -sn : (q == 2 ? -cs : sn));
+}
+FB_HD constexpr double sin32(int j) { return cos32(j - 8); }
+
+// v *= exp(-/+ 2 pi i j / n), n in {4, 8, 16, 32}
+template <typename T, int N, int J, bool INV> FB_HD cx<T> twiddle_const(cx<T> v)
+{
+    constexpr int j32 = (J * (32 / N)) & 31;
+    if constexpr (j32 == 0) {
+        return v;
+    } else if constexpr (j32 == 8) {
+        return rot<T, INV>(v);
+    } else if constexpr (j32 == 16) {
+        return mk<T>(-v.x, -v.y);
+    } else if constexpr (j32 == 24) {
+        return rot<T, !INV>(v);
+    } else if constexpr (j32 == 4) {
+        constexpr T h = T(0.70710678118654752440);
+        return INV ? mk<T>(h * (v.x - v.y), h * (v.x + v.y)) : mk<T>(h * (v.x + v.y), h * (v.y - v.x));
+    } else if constexpr (j32 == 12) {
+        constexpr T h = T(0.70710678118654752440);
+        return INV ? mk<T>(-h * (v.x + v.y), h * (v.x - v.y)) : mk<T>(h * (v.y - v.x), -h * (v.x + v.y));
+    } else {
+        constexpr T c = T(cos32(j32));
+        constexpr T s = T(INV ? sin32(j32) : -sin32(j32));
+        return mk<T>(v.x * c - v.y * s, v.x * s + v.y * c);
+    }
+}
+
+template <typename T, int N, bool INV, int J = 0> struct DifLevel {
+    static FB_HD void run(cx<T>* v)
+    {
+        cx<T> a = v[J], b = v[J + N / 2];
+        v[J] = a + b;
+        v[J + N / 2] = twiddle_const<T, N, J, INV>(a - b);
+        if constexpr (J + 1 < N / 2) DifLevel<T, N, INV, J + 1>::run(v);
+    }
+};
+
+// first level when v[N/2..N) is known to be zero (zero padded input)
+template <typename T, int N, bool INV, int J = 0> struct DifLevelPruned {
+    static FB_HD void run(cx<T>* v)
+    {
+        v[J + N / 2] = twiddle_const<T, N, J, INV>(v[J]);
+        if constexpr (J + 1 < N / 2) DifLevelPruned<T, N, INV, J + 1>::run(v);
+    }
+};
+
+template <typename T, int N, bool INV> struct RegFFT {
+    static FB_HD void run(cx<T>* v)
+    {
+        DifLevel<T, N, INV>::run(v);
+        RegFFT<T, N / 2, INV>::run(v);
+        RegFFT<T, N / 2, INV>::run(v + N / 2);
+    }
+    // upper half of the input is zero
+    static FB_HD void run_pruned(cx<T>* v)
+    {
+        DifLevelPruned<T, N, INV>::run(v);
+        RegFFT<T, N / 2, INV>::run(v);
+        RegFFT<T, N / 2, INV>::run(v + N / 2);
+    }
+};
+template <typename T, bool INV> struct RegFFT<T, 1, INV> {
+    static FB_HD void run(cx<T>*) {}
+};
+
+}  // namespace fb

@@ -11,11 +11,13 @@
 #include <mutex>
 #include <string>
 #include <tuple>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/feabas_cuda.h"
 #include "fb_host_plan.h"
 #include "fb_xcorr.cuh"
+#include "fb_xcorr_fast.cuh"
 
 using namespace fb;
 
@@ -74,6 +76,27 @@ __global__ void __launch_bounds__(512) fbk_fused(const __grid_constant__ XcParam
 {
     extern __shared__ __align__(16) unsigned char smem[];
     kf_fused<T, TI>(p, blockIdx.x, threadIdx.x, blockDim.x, smem);
+}
+
+
+// ---- register-resident fast path (power-of-two grids, float32 compute) ----
+template <int E, int T, typename TI, bool PRUNED>
+__global__ void __launch_bounds__(256, 2) fbk_fast_rows_forward(const __grid_constant__ FastParams fp)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    kfast_rows_forward<E, T, TI, PRUNED>(fp, smem);
+}
+template <int E, int T, bool PRUNED>
+__global__ void __launch_bounds__(256, 2) fbk_fast_columns(const __grid_constant__ FastParams fp)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    kfast_columns<E, T, PRUNED, PRUNED>(fp, smem);
+}
+template <int E, int T>
+__global__ void __launch_bounds__(256, 2) fbk_fast_rows_inverse(const __grid_constant__ FastParams fp)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    kfast_rows_inverse<E, T>(fp, smem);
 }
 
 // ---------------------------------------------------------------------------
@@ -139,6 +162,30 @@ static int get_tables(int device, int n, Plan1D& out)
     return FB_OK;
 }
 
+static std::map<std::tuple<int, int, int>, void*> g_wtables;           // (device, n, T) -> cx<float>[E][T]
+
+static int get_warp_table(int device, int n, int T, const cx<float>*& out)
+{
+    auto key = std::make_tuple(device, n, T);
+    auto it = g_wtables.find(key);
+    if (it == g_wtables.end()) {
+        const int E = n / T;
+        std::vector<cx<float>> tw((size_t)n);
+        for (int k1 = 0; k1 < E; ++k1)
+            for (int t = 0; t < T; ++t) {
+                long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)((k1 * t) % n) / (long double)n;
+                tw[(size_t)k1 * T + t].x = (float)std::cos(a);
+                tw[(size_t)k1 * T + t].y = (float)std::sin(a);
+            }
+        void* d = nullptr;
+        CU(cudaMalloc(&d, tw.size() * sizeof(cx<float>)));
+        CU(cudaMemcpy(d, tw.data(), tw.size() * sizeof(cx<float>), cudaMemcpyHostToDevice));
+        it = g_wtables.emplace(key, d).first;
+    }
+    out = reinterpret_cast<const cx<float>*>(it->second);
+    return FB_OK;
+}
+
 template <typename F>
 static int raise_smem(F* fn)
 {
@@ -165,6 +212,18 @@ static int set_attrs(int device)
     RS((fbk_fused<float, unsigned char>));
     RS((fbk_fused<double, unsigned char>));
     RS((fbk_fused<double, double>));
+#define RSF(E, T)                                            \
+    RS((fbk_fast_rows_forward<E, T, float, true>));          \
+    RS((fbk_fast_rows_forward<E, T, float, false>));         \
+    RS((fbk_fast_rows_forward<E, T, unsigned char, true>));  \
+    RS((fbk_fast_rows_forward<E, T, unsigned char, false>)); \
+    RS((fbk_fast_columns<E, T, true>));                      \
+    RS((fbk_fast_columns<E, T, false>));                     \
+    RS((fbk_fast_rows_inverse<E, T>))
+    RSF(16, 16);
+    RSF(32, 16);
+    RSF(32, 32);
+#undef RSF
 #undef RS
     g_attr_done[device] = true;
     return FB_OK;
@@ -180,9 +239,13 @@ struct Problem {
     int isz;        // bytes per input element
     Geometry g;
     bool fused;
+    bool fast;      // register-resident power-of-two pipeline
+    int hp0, hp1;   // fast: padded heights of the transposed row spectra
     size_t ws_per_pair;
     int nrt;
 };
+
+static bool fast_size(int n) { return n == 256 || n == 512 || n == 1024; }
 
 static int make_problem(Problem& q, int n, int h0, int w0, int h1, int w1, int in_dtype, int fft_h, int fft_w, int flags)
 {
@@ -216,6 +279,12 @@ static int make_problem(Problem& q, int n, int h0, int w0, int h1, int w1, int i
     q.nrt = q.fused ? 0 : (fft_h + rpt - 1) / rpt;
     q.ws_per_pair = q.fused ? 0
                             : ((size_t)(h0 + h1) * g.fpitch + (size_t)fft_h * 2 * g.fpitch) * g.esize + (size_t)q.nrt * sizeof(Partial);
+    q.fast = !q.fused && !q.f64 && fast_size(fft_h) && fast_size(fft_w) && !(flags & FB_FLAG_FORCE_GENERIC);
+    if (q.fast) {
+        q.hp0 = (h0 + 31) & ~31; q.hp1 = (h1 + 31) & ~31;
+        q.nrt = g.mirror ? fft_h : (fft_h + 1) / 2;
+        q.ws_per_pair = ((size_t)g.kp * (q.hp0 + q.hp1) + (size_t)2 * g.kp * fft_h) * 8 + (size_t)q.nrt * sizeof(Partial);
+    }
     q.ws_per_pair = (q.ws_per_pair + 255) & ~(size_t)255;
     return FB_OK;
 }
@@ -246,6 +315,96 @@ struct ProfScope {
     }
 };
 
+
+// ---------------------------------------------------------------------------
+// fast path launch
+// ---------------------------------------------------------------------------
+template <int E, int T, typename TI>
+static void launch_fast_k1(const FastParams& fp, bool pruned, int grid, size_t smem, cudaStream_t st)
+{
+    if (pruned) fbk_fast_rows_forward<E, T, TI, true><<<grid, 256, smem, st>>>(fp);
+    else fbk_fast_rows_forward<E, T, TI, false><<<grid, 256, smem, st>>>(fp);
+}
+template <int E, int T>
+static void launch_fast_k2(const FastParams& fp, bool pruned, int grid, size_t smem, cudaStream_t st)
+{
+    if (pruned) fbk_fast_columns<E, T, true><<<grid, 256, smem, st>>>(fp);
+    else fbk_fast_columns<E, T, false><<<grid, 256, smem, st>>>(fp);
+}
+static void fast_et(int n, int& E, int& T)
+{
+    if (n == 256) { E = 16; T = 16; } else if (n == 512) { E = 32; T = 16; } else { E = 32; T = 32; }
+}
+static size_t fast_smem(int n)
+{
+    int E, T; fast_et(n, E, T);
+    return ((size_t)kFastWarps * (32 / T) * (n + E + 1) + n) * sizeof(cx<float>);
+}
+
+static int g_num_sms = 0;
+
+template <typename TI>
+static int launch_fast(const Problem& q, StreamCtx& ctx, XcParams& p, int nb, cudaStream_t st)
+{
+    FastParams fp{};
+    int rc;
+    int EX, TX, EY, TY;
+    fast_et(q.nx, EX, TX); fast_et(q.ny, EY, TY);
+    if ((rc = get_warp_table(ctx.device, q.nx, TX, fp.twx)) != FB_OK) return rc;
+    if ((rc = get_warp_table(ctx.device, q.ny, TY, fp.twy)) != FB_OK) return rc;
+    if (!g_num_sms) { cudaDeviceProp pr; CU(cudaGetDeviceProperties(&pr, ctx.device)); g_num_sms = pr.multiProcessorCount; }
+    const Geometry& g = q.g;
+    unsigned char* w = reinterpret_cast<unsigned char*>(ctx.ws);
+    const size_t f0 = (size_t)nb * g.kp * q.hp0 * 8, f1 = (size_t)nb * g.kp * q.hp1 * 8, gg = (size_t)nb * 2 * g.kp * q.ny * 8;
+    fp.FT0 = reinterpret_cast<cx<float>*>(w);
+    fp.FT1 = reinterpret_cast<cx<float>*>(w + f0);
+    fp.GT = reinterpret_cast<cx<float>*>(w + f0 + f1);
+    p.part = reinterpret_cast<Partial*>(w + f0 + f1 + gg);
+    p.G = fp.GT; p.gt_layout = 1; p.nrt = q.nrt;
+    fp.hp0 = q.hp0; fp.hp1 = q.hp1;
+    fp.x = p;
+    const int cap = g_num_sms * 2;
+    // K1
+    {
+        const int lpw = 32 / TX, TR = 2 * lpw * kFastWarps;
+        const int work = nb * (q.hp0 / TR + q.hp1 / TR);
+        const int grid = work < cap ? work : cap;
+        const bool pruned = q.w0 <= q.nx / 2 && q.w1 <= q.nx / 2;
+        ProfScope ps(ctx, st, SLOT_ROWS_FWD);
+        if (q.nx == 256) launch_fast_k1<16, 16, TI>(fp, pruned, grid, fast_smem(256), st);
+        else if (q.nx == 512) launch_fast_k1<32, 16, TI>(fp, pruned, grid, fast_smem(512), st);
+        else launch_fast_k1<32, 32, TI>(fp, pruned, grid, fast_smem(1024), st);
+    }
+    // K2
+    {
+        const int cpg = (32 / TY) * (kFastWarps / 2);
+        const int work = nb * ((g.kp + cpg - 1) / cpg);
+        const int grid = work < cap ? work : cap;
+        const bool pruned = q.hp0 <= q.ny / 2 && q.hp1 <= q.ny / 2;
+        ProfScope ps(ctx, st, SLOT_COLUMNS);
+        if (q.ny == 256) launch_fast_k2<16, 16>(fp, pruned, grid, fast_smem(256), st);
+        else if (q.ny == 512) launch_fast_k2<32, 16>(fp, pruned, grid, fast_smem(512), st);
+        else launch_fast_k2<32, 32>(fp, pruned, grid, fast_smem(1024), st);
+    }
+    // K3
+    {
+        const int lpc = (32 / TX) * kFastWarps;
+        const int work = nb * ((q.nrt + lpc - 1) / lpc);
+        const int grid = work < cap ? work : cap;
+        ProfScope ps(ctx, st, SLOT_ROWS_INV);
+        if (q.nx == 256) fbk_fast_rows_inverse<16, 16><<<grid, 256, fast_smem(256), st>>>(fp);
+        else if (q.nx == 512) fbk_fast_rows_inverse<32, 16><<<grid, 256, fast_smem(512), st>>>(fp);
+        else fbk_fast_rows_inverse<32, 32><<<grid, 256, fast_smem(1024), st>>>(fp);
+    }
+    {
+        ProfScope ps(ctx, st, SLOT_FINALIZE);
+        fbk_finalize<float><<<nb, 256, (size_t)q.nx * 4 * sizeof(cx<float>) + 2048, st>>>(fp.x);
+    }
+    g_launches += 4;
+    CU(cudaGetLastError());
+    return FB_OK;
+}
+
 // ---------------------------------------------------------------------------
 // launch of one chunk (device pointers)
 // ---------------------------------------------------------------------------
@@ -271,6 +430,9 @@ static int launch_chunk(const Problem& q, StreamCtx& ctx, const void* img0, cons
         return FB_OK;
     }
     p.tl = g.tl_row; p.tc = g.tc_col; p.nrt = q.nrt;
+    if (q.fast) {
+        if constexpr (std::is_same<T, float>::value) return launch_fast<TI>(q, ctx, p, nb, st);
+    }
     unsigned char* w = reinterpret_cast<unsigned char*>(ctx.ws);
     size_t f0 = (size_t)nb * q.h0 * g.fpitch * g.esize, f1 = (size_t)nb * q.h1 * g.fpitch * g.esize;
     size_t gg = (size_t)nb * q.ny * 2 * g.fpitch * g.esize;
@@ -484,7 +646,7 @@ extern "C" int fb_xcorr_plan_info(int h0, int w0, int h1, int w1, int in_dtype, 
     int rc = make_problem(q, 1, h0, w0, h1, w1, in_dtype, fft_h, fft_w, flags);
     if (rc != FB_OK) return rc;
     if (!info) return fail(FB_EINVAL, "null info");
-    info[0] = q.fused ? 1 : 2;
+    info[0] = q.fused ? 1 : (q.fast ? 3 : 2);
     info[1] = (long long)q.ws_per_pair;
     info[2] = q.g.fused ? (long long)q.g.smem_fused : 0;
     info[3] = (long long)q.g.smem_row;
@@ -560,6 +722,12 @@ extern "C" int fb_release(int device)
         cudaFree(it->second.tw);
         cudaFree(it->second.pos);
         it = g_tables.erase(it);
+    }
+    for (auto it = g_wtables.begin(); it != g_wtables.end();) {
+        if (device >= 0 && std::get<0>(it->first) != device) { ++it; continue; }
+        cudaSetDevice(std::get<0>(it->first));
+        cudaFree(it->second);
+        it = g_wtables.erase(it);
     }
     cudaGetLastError();
     return FB_OK;

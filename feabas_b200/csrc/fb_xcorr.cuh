@@ -61,6 +61,7 @@ struct XcParams {
     int tl;               // lines per row tile
     int tc;               // columns per image per column tile
     int spitch;           // fused: row pitch of the resident spectra
+    int gt_layout;        // K4: G holds the fast path's transposed surfaces
 };
 
 template <typename T> struct Acc {
@@ -221,13 +222,13 @@ FB_DEV void cols_stage(const XcParams& p, cx<T>* S, int pitch, int half, bool mi
 // ----------------------------------------------------------------------------
 template <typename T>
 FB_DEV void rows_inverse_fill(const XcParams& p, const cx<T>* X, const cx<T>* Y, cx<T>* s, int pitch, int l,
-                              int tid_in_line, int stride)
+                              int tid_in_line, int stride, size_t ks = 1)
 {
     const int nx = p.nx, kp = p.kp;
     const int* pos = p.px.pos;
     for (int k = tid_in_line; k < kp; k += stride) {
-        cx<T> a = X[k];
-        cx<T> b = Y ? Y[k] : mk<T>(T(0), T(0));
+        cx<T> a = X[k * ks];
+        cx<T> b = Y ? Y[k * ks] : mk<T>(T(0), T(0));
         if (k == 0 || 2 * k == nx) {
             s[(size_t)FB_LDG(pos + k) * pitch + l] = mk<T>(a.x, b.x);
         } else {
@@ -288,7 +289,7 @@ FB_DEV void rows_inverse_tile(const XcParams& p, const cx<T>* Pb, const cx<T>* Q
 // ----------------------------------------------------------------------------
 template <typename T>
 FB_DEV void finalize_pair(const XcParams& p, int pair, const Acc<T>& best, const cx<T>* Pb, const cx<T>* Qb,
-                          int rpitch, bool mirror, cx<T>* s, int tid, int nthr)
+                          int rpitch, bool mirror, cx<T>* s, int tid, int nthr, size_t ks = 1)
 {
     const int nx = p.nx, ny = p.ny, kp = p.kp;
     const int py = best.idx / nx, px = best.idx - py * nx;
@@ -299,7 +300,7 @@ FB_DEV void finalize_pair(const XcParams& p, int pair, const Acc<T>& best, const
             int y = py - 1 + l;
             y = y < 0 ? y + ny : (y >= ny ? y - ny : y);
             rows_inverse_fill<T>(p, Pb + (size_t)y * rpitch, mirror ? Qb + (size_t)y * rpitch : nullptr,
-                                 s, pitch, l, k, kp);
+                                 s, pitch, l, k, kp, ks);
         }
         FB_SYNC();
         fft_lines<T, true>(p.px, s, pitch, 3, tid, nthr);
@@ -449,6 +450,12 @@ FB_DEV void k4_finalize(const XcParams& p, int bid, int tid, int nthr, unsigned 
         acc_merge(acc, b);
     }
     Acc<T> best = block_reduce<T>(acc, red, tid, nthr);
+    if (p.gt_layout) {
+        // fast path: G^T[pair][P|Q][kx][y]
+        const cx<T>* Pb = reinterpret_cast<const cx<T>*>(p.G) + (size_t)bid * 2 * p.kp * p.ny;
+        finalize_pair<T>(p, bid, best, Pb, Pb + (size_t)p.kp * p.ny, 1, mirror, s, tid, nthr, (size_t)p.ny);
+        return;
+    }
     const cx<T>* Pb = reinterpret_cast<const cx<T>*>(p.G) + (size_t)bid * p.ny * 2 * p.fpitch;
     finalize_pair<T>(p, bid, best, Pb, Pb + p.fpitch, 2 * p.fpitch, mirror, s, tid, nthr);
 }

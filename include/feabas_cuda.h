@@ -43,6 +43,7 @@ extern "C" {
 #define FB_FLAG_FORCE_STAGED 0x10 /* testing: always use the HBM-staged 4-kernel pipeline    */
 #define FB_FLAG_FORCE_FUSED 0x20  /* testing: always use the single-CTA fused kernel         */
 #define FB_FLAG_U8_AS_F32 0x40    /* opt-in: compute uint8 input in float32 (not reference-exact) */
+#define FB_FLAG_FORCE_GENERIC 0x80 /* testing: staged pipeline with the generic mixed-radix kernels */
 
 /* xcorr_fft (feabas/matcher.py:22-135) on a stack of n image pairs, sigma == 0,
  * single channel, no mask normalisation.
@@ -79,7 +80,8 @@ int fb_xcorr_batch(const void* img0, const void* img1, int n, int h0, int w0, in
  * feabas/matcher.py:60,62.  Pure host arithmetic.                          */
 int fb_next_fast_len(int target);
 
-/* How a problem class will be executed.  info[0] = 1 fused / 2 staged,
+/* How a problem class will be executed.  info[0] = 1 fused / 2 staged (generic
+ * mixed-radix kernels) / 3 staged (register-resident power-of-two kernels),
  * info[1] = bytes of HBM workspace per pair, info[2..4] = shared memory per
  * CTA of the fused / row / column kernels, info[5] = row tile lines,
  * info[6] = column tile width, info[7] = kernel launches per chunk.

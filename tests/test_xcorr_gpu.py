@@ -140,3 +140,41 @@ def test_full_size_ground_truth(fc):
     np.testing.assert_array_equal(part, out[:, 5:9])
     # and the first two pairs against the oracle
     parity.check_against_oracle((out[0, :2], out[1, :2], out[2, :2].astype(np.float32)), a[:2], b[:2], subpixel=True)
+
+
+FAST_CASES = [
+    # (n, shape0, shape1, kwargs) -- every FFT grid here is a power of two in {256, 512, 1024}
+    (5, (128, 128), (128, 128), dict(subpixel=True)),                          # 256 x 256
+    (3, (127, 127), (127, 127), dict(subpixel=True)),                          # 256 x 256, ragged rows
+    (3, (110, 120), (147, 137), dict(subpixel=True)),                          # 256 x 256, different shapes
+    (3, (256, 256), (256, 256), dict(subpixel=True)),                          # 512 x 512
+    (3, (256, 256), (256, 256), dict(subpixel=True, pad=False)),               # 256 x 256, no pruning
+    (2, (512, 512), (512, 512), dict(subpixel=True)),                          # 1024 x 1024
+    (2, (512, 512), (512, 512), dict(subpixel=True, pad=False)),               # 512 x 512 circular
+    (2, (1000, 250), (1000, 250), dict(subpixel=True, pad=False)),             # 1024 x 256
+    (2, (128, 512), (128, 512), dict(subpixel=False)),                         # 256 x 1024
+    (3, (256, 128), (256, 128), dict(subpixel=True, conf_mode=0)),             # 512 x 256, NONE
+    (3, (256, 256), (256, 256), dict(subpixel=True, conf_mode=1)),             # STD
+    (3, (255, 255), (255, 255), dict(subpixel=True, conf_mode=0, pad=False)),  # 256^2 odd rows, NONE pairs rows
+    (2, (501, 480), (501, 480), dict(subpixel=True, conf_mode=1, pad=False)),  # 512 x 512 (ny odd rows)
+]
+
+
+@pytest.mark.parametrize('n,shape0,shape1,kw', FAST_CASES)
+def test_fast_path_against_oracle(fc, n, shape0, shape1, kw):
+    from feabas_b200.cuda import _lib
+    ny, nx = fc.fft_shape(shape0, shape1, kw.get('pad', True))
+    info = _lib.plan_info(*shape0, *shape1, _lib.FB_F32, ny, nx, 0)
+    assert info['path'] == 'staged-fast', (ny, nx, info)
+    if shape0 == shape1:
+        a, b, _ = synth.block_pairs(n, shape0, seed=shape0[0] + shape0[1], max_shift=min(shape0) // 8)
+    else:
+        rng = np.random.default_rng(shape0[0])
+        b = rng.standard_normal((n,) + shape1).astype(np.float32)
+        a = b[:, 20:20 + shape0[0], 10:10 + shape0[1]] + 0.1 * rng.standard_normal((n,) + shape0).astype(np.float32)
+        a = np.ascontiguousarray(a)
+    got = fc.xcorr_fft(a, b, **kw)
+    parity.check_against_oracle(got, a, b, **_tol(kw), **kw)
+    gen = fc.xcorr_fft(a, b, force='generic', **kw)
+    np.testing.assert_allclose(got[0], gen[0], atol=2e-3)
+    np.testing.assert_allclose(got[1], gen[1], atol=2e-3)
