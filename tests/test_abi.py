@@ -48,7 +48,7 @@ def test_plan_info(lib):
     assert fft_shape((74, 67), (74, 67), True) == (150, 135)
     assert fft_shape((74, 67), (74, 67), False) == (75, 72)
     big = lib.plan_info(512, 512, 512, 512, lib.FB_F32, 1024, 1024, 0x2 | (2 << 2))
-    assert big['path'] == 'staged' and big['launches_per_chunk'] == 4
+    assert big['path'] == 'staged-fast' and big['launches_per_chunk'] == 4
     # F0 + F1 + G(P,Q) ~ 12.6 MB per 512^2 pair
     assert 12.5e6 < big['ws_bytes_per_pair'] < 13.0e6
     small = lib.plan_info(74, 67, 74, 67, lib.FB_F32, 150, 135, 0x2 | (2 << 2))
