@@ -90,7 +90,7 @@ template <int E, int T, bool PRUNED>
 __global__ void __launch_bounds__(256, 2) fbk_fast_columns(const __grid_constant__ FastParams fp)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    kfast_columns<E, T, PRUNED, PRUNED>(fp, smem);
+    kfast_columns<E, T, PRUNED>(fp, smem);
 }
 template <int E, int T>
 __global__ void __launch_bounds__(256, 2) fbk_fast_rows_inverse(const __grid_constant__ FastParams fp)

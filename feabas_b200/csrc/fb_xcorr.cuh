@@ -61,7 +61,8 @@ struct XcParams {
     int tl;               // lines per row tile
     int tc;               // columns per image per column tile
     int spitch;           // fused: row pitch of the resident spectra
-    int gt_layout;        // K4: G holds the fast path's transposed surfaces
+    int gt_layout;        // K4: G holds the fast path's transposed, conjugated surfaces and the
+                          //     partial's idx only identifies the ROW of the maximum
 };
 
 template <typename T> struct Acc {
@@ -229,6 +230,7 @@ FB_DEV void rows_inverse_fill(const XcParams& p, const cx<T>* X, const cx<T>* Y,
     for (int k = tid_in_line; k < kp; k += stride) {
         cx<T> a = X[k * ks];
         cx<T> b = Y ? Y[k * ks] : mk<T>(T(0), T(0));
+        if (p.gt_layout) { a.y = -a.y; b.y = -b.y; }
         if (k == 0 || 2 * k == nx) {
             s[(size_t)FB_LDG(pos + k) * pitch + l] = mk<T>(a.x, b.x);
         } else {
@@ -292,9 +294,10 @@ FB_DEV void finalize_pair(const XcParams& p, int pair, const Acc<T>& best, const
                           int rpitch, bool mirror, cx<T>* s, int tid, int nthr, size_t ks = 1)
 {
     const int nx = p.nx, ny = p.ny, kp = p.kp;
-    const int py = best.idx / nx, px = best.idx - py * nx;
+    const int py = best.idx / nx;
+    int px = best.idx - py * nx;
     const int pitch = 4;
-    if (p.subpixel) {
+    if (p.subpixel || p.gt_layout) {
         for (int idx = tid; idx < kp * 3; idx += nthr) {
             int l = idx / kp, k = idx - l * kp;
             int y = py - 1 + l;
@@ -304,6 +307,14 @@ FB_DEV void finalize_pair(const XcParams& p, int pair, const Acc<T>& best, const
         }
         FB_SYNC();
         fft_lines<T, true>(p.px, s, pitch, 3, tid, nthr);
+    }
+    if (p.gt_layout) {
+        // locate the maximum inside row py (np.argmax: first occurrence)
+        Acc<T> a; acc_init(a);
+        for (int x = tid; x < nx; x += nthr) acc_take(a, s[(size_t)x * pitch + 1].x, x);
+        Acc<T>* red = reinterpret_cast<Acc<T>*>(s + (size_t)nx * pitch);
+        a = block_reduce<T>(a, red, tid, nthr);
+        px = a.idx;
     }
     if (tid == 0) {
         float ox = 0.f, oy = 0.f;

@@ -34,18 +34,18 @@ template <int E, int T> struct WarpFFT {
     // register that holds output j (j-th in increasing k for this lane)
     static constexpr __host__ __device__ int out_reg(int j) { return (j % M) * T + brev<T>(j / M); }
 
-    // v: E registers; in: v[n1] = x[n1 T + t]; out: X[out_k(t, j)] = v[out_reg(j)]
-    template <bool INV, bool PRUNED>
+    // v: E registers; in: v[n1] = x[n1 T + t]; out: X[out_k(t, j)] = v[out_reg(j)].
+    // Forward transform only: inverse transforms are taken as conj(fft(conj(.))) with the
+    // conjugations folded into the neighbouring point-wise steps, so that every kernel
+    // runs ONE butterfly body (instruction-cache footprint).
+    template <bool PRUNED>
     static __device__ __forceinline__ void run(cx<float>* v, cx<float>* region, const cx<float>* tw, int t)
     {
-        if (PRUNED) RegFFT<float, E, INV>::run_pruned(v); else RegFFT<float, E, INV>::run(v);
+        if (PRUNED) RegFFT<float, E, false>::run_pruned(v); else RegFFT<float, E, false>::run(v);
 #pragma unroll
         for (int k1 = 0; k1 < E; ++k1) {
             cx<float> a = v[brev<E>(k1)];
-            if (k1) {
-                cx<float> w = tw[k1 * T + t];
-                a = INV ? cmulc(a, w) : cmul(a, w);
-            }
+            if (k1) a = cmul(a, tw[k1 * T + t]);
             region[k1 * (T + 1) + t] = a;
         }
         __syncwarp();
@@ -56,7 +56,7 @@ template <int E, int T> struct WarpFFT {
         }
         __syncwarp();
 #pragma unroll
-        for (int m = 0; m < M; ++m) RegFFT<float, T, INV>::run(v + m * T);
+        for (int m = 0; m < M; ++m) RegFFT<float, T, false>::run(v + m * T);
     }
 };
 
@@ -125,18 +125,23 @@ __device__ void kfast_rows_forward(const FastParams& fp, unsigned char* smem)
 #pragma unroll
             for (int n1 = 0; n1 < E; ++n1) v[n1] = mk<float>(0.f, 0.f);
         }
-        W::template run<false, PRUNED>(v, region, tw, t);
+        W::template run<PRUNED>(v, region, tw, t);
 #pragma unroll
         for (int j = 0; j < E; ++j) region[W::out_k(t, j)] = v[W::out_reg(j)];
         __syncthreads();
-        // separation + transposed store: thread -> (row r minor, k major)
-        for (int idx = tid; idx < kp * TR; idx += blockDim.x) {
-            const int r = idx % TR, k = idx / TR;
+        // separation + transposed store: thread -> (row r minor, k major); r is fixed per thread
+        {
+            constexpr int KSTEP = 256 / TR;
+            const int r = tid % TR;
             const cx<float>* reg = regions + (r >> 1) * RS;
-            const cx<float> zk = reg[k], zm = reg[k ? N - k : 0];
-            cx<float> o = (r & 1) ? mk<float>(0.5f * (zk.y + zm.y), 0.5f * (zm.x - zk.x))
-                                  : mk<float>(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
-            FT[(size_t)k * hp + row0 + r] = o;
+            const bool odd = r & 1;
+            cx<float>* dst = FT + row0 + r;
+            for (int k = tid / TR; k < kp; k += KSTEP) {
+                const cx<float> zk = reg[k], zm = reg[k ? N - k : 0];
+                const cx<float> o = odd ? mk<float>(0.5f * (zk.y + zm.y), 0.5f * (zm.x - zk.x))
+                                        : mk<float>(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+                dst[(size_t)k * hp] = o;
+            }
         }
         __syncthreads();
     }
@@ -147,7 +152,7 @@ __device__ void kfast_rows_forward(const FastParams& fp, unsigned char* smem)
 // they swap spectra through shared memory, form P = conj(F0) F1 and Q = F0 F1, inverse
 // transform and store the P / Q columns contiguously.  grid-stride over (pair, column group).
 // ---------------------------------------------------------------------------------------------
-template <int E, int T, bool PRUNED0, bool PRUNED1>
+template <int E, int T, bool PRUNED0>
 __device__ void kfast_columns(const FastParams& fp, unsigned char* smem)
 {
     using W = WarpFFT<E, T>;
@@ -176,44 +181,48 @@ __device__ void kfast_columns(const FastParams& fp, unsigned char* smem)
 #pragma unroll
         for (int n1 = 0; n1 < E; ++n1) {
             const int y = n1 * T + t;
-            const bool pruned = roleB ? PRUNED1 : PRUNED0;
             cx<float> a = mk<float>(0.f, 0.f);
-            if ((!pruned || n1 < E / 2) && y < hp) a = ldg(src + y);
+            if ((!PRUNED0 || n1 < E / 2) && y < hp) a = ldg(src + y);
             v[n1] = a;
         }
-        if (roleB) W::template run<false, PRUNED1>(v, mine, tw, t); else W::template run<false, PRUNED0>(v, mine, tw, t);
+        W::template run<PRUNED0>(v, mine, tw, t);
 #pragma unroll
         for (int j = 0; j < E; ++j) mine[W::out_k(t, j)] = v[W::out_reg(j)];
         asm volatile("bar.sync %0, 64;" ::"r"(pw + 1) : "memory");
+        // role A: m = F0, o = F1: conj(P) = F0 conj(F1); role B: m = F1, o = F0: conj(Q) = conj(F1) conj(F0).
+        // The forward transform of conj(P) is conj(ifft-surface); consumers undo the conjugation.
+        const float sgn = roleB ? -sc : sc;
 #pragma unroll
         for (int j = 0; j < E; ++j) {
             const cx<float> o = other[W::out_k(t, j)], m = v[W::out_reg(j)];
-            // role A: m = F0, o = F1 -> conj(F0) F1 ; role B: m = F1, o = F0 -> F0 F1
-            v[W::out_reg(j)] = cscale(roleB ? cmul(o, m) : cmulc(o, m), sc);
+            v[W::out_reg(j)] = cmulc(mk<float>(m.x * sc, m.y * sgn), o);
         }
         asm volatile("bar.sync %0, 64;" ::"r"(pw + 1) : "memory");
         if (!roleB || mirror) {
             // natural order in -> registers n1: value at y-frequency k = n1 T + t
-            cx<float> u[E];
 #pragma unroll
             for (int j = 0; j < E; ++j) mine[W::out_k(t, j)] = v[W::out_reg(j)];
             __syncwarp();
 #pragma unroll
-            for (int n1 = 0; n1 < E; ++n1) u[n1] = mine[n1 * T + t];
+            for (int n1 = 0; n1 < E; ++n1) v[n1] = mine[n1 * T + t];
             __syncwarp();
-            W::template run<true, false>(u, mine, tw, t);
+            W::template run<false>(v, mine, tw, t);
             if (live) {
                 cx<float>* dst = fp.GT + (((size_t)pair * 2 + (roleB ? 1 : 0)) * kp + col) * N;
 #pragma unroll
-                for (int j = 0; j < E; ++j) dst[W::out_k(t, j)] = u[W::out_reg(j)];
+                for (int j = 0; j < E; ++j) dst[W::out_k(t, j)] = v[W::out_reg(j)];
             }
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3: inverse row transforms + per-line arg-max partials.  A line is (P row y, Q row y) with the
-// mirror term, else (P row y, P row y+1).  grid-stride over (pair, tile of 8*LPW lines).
+// K3: inverse row transforms + per-line maxima.  A line is (P row y, Q row y) with the mirror
+// term, else (P row y, P row y+1).  GT holds the CONJUGATE of the column-stage output (see K2),
+// so the Hermitian extension below builds conj(Z) and the forward transform returns
+// conj(surface): C = Re, mirror = -Im (only |.| is used), second row = -Im.
+// Only the per-line maxima are reduced here; the finalize kernel locates x inside the winning
+// row (np.argmax order: lowest row, then lowest x).  grid-stride over (pair, tile of lines).
 // ---------------------------------------------------------------------------------------------
 template <int E, int T>
 __device__ void kfast_rows_inverse(const FastParams& fp, unsigned char* smem)
@@ -238,17 +247,19 @@ __device__ void kfast_rows_inverse(const FastParams& fp, unsigned char* smem)
         const cx<float>* GP = fp.GT + (size_t)pair * 2 * kp * ny;
         __syncthreads();                                       // previous tile fully consumed (and tw visible)
         if (mirror) {
-            // slots [0,kp): P^T[kx][y], slots [kp,2kp): Q^T[kx][y]
-            for (int idx = tid; idx < 2 * kp * LPC; idx += blockDim.x) {
-                const int r = idx % LPC, c = idx / LPC;        // c in [0, 2kp)
-                const int y = line0 + r;
-                if (y < ny) cp_async8(regions + r * RS + c, GP + (size_t)c * ny + y);
+            // slots [0,kp): P^T[kx][y], slots [kp,2kp): Q^T[kx][y]; thread -> fixed line r, c strided
+            const int r = tid % LPC, y = line0 + r;
+            if (y < ny) {
+                const cx<float>* src = GP + y;
+                cx<float>* dst = regions + r * RS;
+                for (int c = tid / LPC; c < 2 * kp; c += 256 / LPC) cp_async8(dst + c, src + (size_t)c * ny);
             }
         } else {
-            for (int idx = tid; idx < 2 * kp * LPC; idx += blockDim.x) {
-                const int r2 = idx % (2 * LPC), kx = idx / (2 * LPC);
-                const int y = 2 * line0 + r2;
-                if (y < ny) cp_async8(regions + (r2 >> 1) * RS + (r2 & 1) * kp + kx, GP + (size_t)kx * ny + y);
+            const int r2 = tid % (2 * LPC), y = 2 * line0 + r2;
+            if (y < ny) {
+                const cx<float>* src = GP + y;
+                cx<float>* dst = regions + (r2 >> 1) * RS + (r2 & 1) * kp;
+                for (int kx = tid / (2 * LPC); kx < kp; kx += 256 / (2 * LPC)) cp_async8(dst + kx, src + (size_t)kx * ny);
             }
         }
         cp_async_wait_all();
@@ -256,69 +267,61 @@ __device__ void kfast_rows_inverse(const FastParams& fp, unsigned char* smem)
         const int gl = line0 + line;                           // global line index
         const bool live = gl < lines_pp;
         const bool have2 = mirror || (2 * gl + 1 < ny);        // second half of the line present
+        const float h2 = have2 ? 1.f : 0.f;
         cx<float> v[E];
 #pragma unroll
         for (int n1 = 0; n1 < E; ++n1) {
             const int k = n1 * T + t;
             cx<float> z;
             if (n1 < E / 2 || (n1 == E / 2 && t == 0)) {
-                cx<float> a = region[k];
-                cx<float> b = have2 ? region[kp + k] : mk<float>(0.f, 0.f);
-                z = (k == 0 || 2 * k == N) ? mk<float>(a.x, b.x) : mk<float>(a.x - b.y, a.y + b.x);
+                const cx<float> a = region[k];
+                cx<float> b = region[kp + k];
+                b = mk<float>(b.x * h2, b.y * h2);
+                // conj(P + iQ) with stored a = conj(P), b = conj(Q):  a - i b
+                z = (k == 0 || 2 * k == N) ? mk<float>(a.x, -b.x) : mk<float>(a.x + b.y, a.y - b.x);
             } else {
-                cx<float> a = region[N - k];
-                cx<float> b = have2 ? region[kp + N - k] : mk<float>(0.f, 0.f);
-                z = mk<float>(a.x + b.y, b.x - a.y);
+                const cx<float> a = region[N - k];
+                cx<float> b = region[kp + N - k];
+                b = mk<float>(b.x * h2, b.y * h2);
+                // conj(conj(P) + i conj(Q)) = P - i Q = conj(a) - i conj(b)
+                z = mk<float>(a.x - b.y, -a.y - b.x);
             }
             v[n1] = live ? z : mk<float>(0.f, 0.f);
         }
         __syncwarp();
-        W::template run<true, false>(v, region, tw, t);
-        // lane-local scan in increasing x
-        float best = 0.f, mir = 0.f, best2 = 0.f;
-        int bx = 0, bx2 = 0;
+        W::template run<false>(v, region, tw, t);
+        // out = conj(surface line): Re -> first row, -Im -> mirror surface / second row
+        float best = v[0].x, second = mirror ? fabsf(v[0].y) : -v[0].y;
         double sum = 0.0, sumsq = 0.0;
 #pragma unroll
-        for (int j = 0; j < E; ++j) {
-            const cx<float> c = v[W::out_reg(j)];
-            const int x = W::out_k(t, j);
-            if (j == 0 || c.x > best) { best = c.x; bx = x; }
-            if (mirror) {
-                mir = fmaxf(mir, fabsf(c.y));
-            } else {
-                if (j == 0 || c.y > best2) { best2 = c.y; bx2 = x; }
-            }
-            if (want_std) {
-                sum += (double)c.x; sumsq += (double)c.x * (double)c.x;
-                if (have2) { sum += (double)c.y; sumsq += (double)c.y * (double)c.y; }
+        for (int j = 1; j < E; ++j) {
+            best = fmaxf(best, v[j].x);
+            second = fmaxf(second, mirror ? fabsf(v[j].y) : -v[j].y);
+        }
+        if (want_std) {
+#pragma unroll
+            for (int j = 0; j < E; ++j) {
+                sum += (double)v[j].x; sumsq += (double)v[j].x * (double)v[j].x;
+                if (have2 && !mirror) { sum -= (double)v[j].y; sumsq += (double)v[j].y * (double)v[j].y; }
             }
         }
-        int idx1, idx2 = 0x7fffffff;
-        if (mirror) {
-            idx1 = gl * N + bx;
-        } else {
-            idx1 = 2 * gl * N + bx;
-            if (have2) {
-                idx2 = (2 * gl + 1) * N + bx2;
-                if (best2 > best) { best = best2; idx1 = idx2; }     // row y+1 has the larger flat index
-            }
-        }
-        // reduce across the T lanes of the line
 #pragma unroll
         for (int off = T / 2; off > 0; off >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, best, off);
-            const int oi = __shfl_xor_sync(0xffffffffu, idx1, off);
-            const float om = __shfl_xor_sync(0xffffffffu, mir, off);
-            if (ov > best || (ov == best && oi < idx1)) { best = ov; idx1 = oi; }
-            mir = fmaxf(mir, om);
+            best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, off));
+            second = fmaxf(second, __shfl_xor_sync(0xffffffffu, second, off));
             if (want_std) {
                 sum += __shfl_xor_sync(0xffffffffu, sum, off);
                 sumsq += __shfl_xor_sync(0xffffffffu, sumsq, off);
             }
         }
         if (t == 0 && live) {
+            // idx = first flat index of the row that holds the maximum; x is resolved by the finalize kernel
+            int row = mirror ? gl : 2 * gl;
+            float mir = 0.f;
+            if (mirror) mir = second;
+            else if (have2 && second > best) { best = second; row += 1; }
             Partial& o = p.part[(size_t)pair * p.nrt + gl];
-            o.val = (double)best; o.mir = (double)mir; o.sum = sum; o.sumsq = sumsq; o.idx = idx1; o.pad = 0;
+            o.val = (double)best; o.mir = (double)mir; o.sum = sum; o.sumsq = sumsq; o.idx = row * N; o.pad = 0;
         }
     }
 }

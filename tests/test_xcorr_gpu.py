@@ -151,7 +151,7 @@ FAST_CASES = [
     (3, (256, 256), (256, 256), dict(subpixel=True, pad=False)),               # 256 x 256, no pruning
     (2, (512, 512), (512, 512), dict(subpixel=True)),                          # 1024 x 1024
     (2, (512, 512), (512, 512), dict(subpixel=True, pad=False)),               # 512 x 512 circular
-    (2, (1024, 250), (1024, 250), dict(subpixel=True, pad=False)),             # 1024 x 256
+    (2, (1024, 256), (1024, 256), dict(subpixel=True, pad=False)),             # 1024 x 256
     (2, (128, 512), (128, 512), dict(subpixel=False)),                         # 256 x 1024
     (3, (256, 128), (256, 128), dict(subpixel=True, conf_mode=0)),             # 512 x 256, NONE
     (3, (256, 256), (256, 256), dict(subpixel=True, conf_mode=1)),             # STD
