@@ -80,23 +80,24 @@ __global__ void __launch_bounds__(512) fbk_fused(const __grid_constant__ XcParam
 
 
 // ---- register-resident fast path (power-of-two grids, float32 compute) ----
+constexpr int kNW1 = 4, kNW2 = 8, kNW3 = 4;          // warps per CTA of K1 / K2 / K3
 template <int E, int T, typename TI, bool PRUNED>
-__global__ void __launch_bounds__(256, 2) fbk_fast_rows_forward(const __grid_constant__ FastParams fp)
+__global__ void __launch_bounds__(32 * kNW1, 16 / kNW1) fbk_fast_rows_forward(const __grid_constant__ FastParams fp)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    kfast_rows_forward<E, T, TI, PRUNED>(fp, smem);
+    kfast_rows_forward<E, T, kNW1, TI, PRUNED>(fp, smem);
 }
 template <int E, int T, bool PRUNED>
-__global__ void __launch_bounds__(256, 2) fbk_fast_columns(const __grid_constant__ FastParams fp)
+__global__ void __launch_bounds__(32 * kNW2, 16 / kNW2) fbk_fast_columns(const __grid_constant__ FastParams fp)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    kfast_columns<E, T, PRUNED>(fp, smem);
+    kfast_columns<E, T, kNW2, PRUNED>(fp, smem);
 }
 template <int E, int T>
-__global__ void __launch_bounds__(256, 2) fbk_fast_rows_inverse(const __grid_constant__ FastParams fp)
+__global__ void __launch_bounds__(32 * kNW3, 16 / kNW3) fbk_fast_rows_inverse(const __grid_constant__ FastParams fp)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    kfast_rows_inverse<E, T>(fp, smem);
+    kfast_rows_inverse<E, T, kNW3>(fp, smem);
 }
 
 // ---------------------------------------------------------------------------
@@ -322,23 +323,23 @@ struct ProfScope {
 template <int E, int T, typename TI>
 static void launch_fast_k1(const FastParams& fp, bool pruned, int grid, size_t smem, cudaStream_t st)
 {
-    if (pruned) fbk_fast_rows_forward<E, T, TI, true><<<grid, 256, smem, st>>>(fp);
-    else fbk_fast_rows_forward<E, T, TI, false><<<grid, 256, smem, st>>>(fp);
+    if (pruned) fbk_fast_rows_forward<E, T, TI, true><<<grid, 32 * kNW1, smem, st>>>(fp);
+    else fbk_fast_rows_forward<E, T, TI, false><<<grid, 32 * kNW1, smem, st>>>(fp);
 }
 template <int E, int T>
 static void launch_fast_k2(const FastParams& fp, bool pruned, int grid, size_t smem, cudaStream_t st)
 {
-    if (pruned) fbk_fast_columns<E, T, true><<<grid, 256, smem, st>>>(fp);
-    else fbk_fast_columns<E, T, false><<<grid, 256, smem, st>>>(fp);
+    if (pruned) fbk_fast_columns<E, T, true><<<grid, 32 * kNW2, smem, st>>>(fp);
+    else fbk_fast_columns<E, T, false><<<grid, 32 * kNW2, smem, st>>>(fp);
 }
 static void fast_et(int n, int& E, int& T)
 {
     if (n == 256) { E = 16; T = 16; } else if (n == 512) { E = 32; T = 16; } else { E = 32; T = 32; }
 }
-static size_t fast_smem(int n)
+static size_t fast_smem(int n, int nw)
 {
     int E, T; fast_et(n, E, T);
-    return ((size_t)kFastWarps * (32 / T) * (n + E + 1) + n) * sizeof(cx<float>);
+    return ((size_t)nw * (32 / T) * (n + E + 1) + n) * sizeof(cx<float>);
 }
 
 static int g_num_sms = 0;
@@ -363,38 +364,40 @@ static int launch_fast(const Problem& q, StreamCtx& ctx, XcParams& p, int nb, cu
     p.G = fp.GT; p.gt_layout = 1; p.nrt = q.nrt;
     fp.hp0 = q.hp0; fp.hp1 = q.hp1;
     fp.x = p;
-    const int cap = g_num_sms * 2;
     // K1
     {
-        const int lpw = 32 / TX, TR = 2 * lpw * kFastWarps;
+        const int lpw = 32 / TX, TR = 2 * lpw * kNW1;
         const int work = nb * (q.hp0 / TR + q.hp1 / TR);
+        const int cap = g_num_sms * (16 / kNW1);
         const int grid = work < cap ? work : cap;
         const bool pruned = q.w0 <= q.nx / 2 && q.w1 <= q.nx / 2;
         ProfScope ps(ctx, st, SLOT_ROWS_FWD);
-        if (q.nx == 256) launch_fast_k1<16, 16, TI>(fp, pruned, grid, fast_smem(256), st);
-        else if (q.nx == 512) launch_fast_k1<32, 16, TI>(fp, pruned, grid, fast_smem(512), st);
-        else launch_fast_k1<32, 32, TI>(fp, pruned, grid, fast_smem(1024), st);
+        if (q.nx == 256) launch_fast_k1<16, 16, TI>(fp, pruned, grid, fast_smem(256, kNW1), st);
+        else if (q.nx == 512) launch_fast_k1<32, 16, TI>(fp, pruned, grid, fast_smem(512, kNW1), st);
+        else launch_fast_k1<32, 32, TI>(fp, pruned, grid, fast_smem(1024, kNW1), st);
     }
     // K2
     {
-        const int cpg = (32 / TY) * (kFastWarps / 2);
+        const int cpg = (32 / TY) * (kNW2 / 2);
         const int work = nb * ((g.kp + cpg - 1) / cpg);
+        const int cap = g_num_sms * (16 / kNW2);
         const int grid = work < cap ? work : cap;
         const bool pruned = q.hp0 <= q.ny / 2 && q.hp1 <= q.ny / 2;
         ProfScope ps(ctx, st, SLOT_COLUMNS);
-        if (q.ny == 256) launch_fast_k2<16, 16>(fp, pruned, grid, fast_smem(256), st);
-        else if (q.ny == 512) launch_fast_k2<32, 16>(fp, pruned, grid, fast_smem(512), st);
-        else launch_fast_k2<32, 32>(fp, pruned, grid, fast_smem(1024), st);
+        if (q.ny == 256) launch_fast_k2<16, 16>(fp, pruned, grid, fast_smem(256, kNW2), st);
+        else if (q.ny == 512) launch_fast_k2<32, 16>(fp, pruned, grid, fast_smem(512, kNW2), st);
+        else launch_fast_k2<32, 32>(fp, pruned, grid, fast_smem(1024, kNW2), st);
     }
     // K3
     {
-        const int lpc = (32 / TX) * kFastWarps;
+        const int lpc = (32 / TX) * kNW3;
         const int work = nb * ((q.nrt + lpc - 1) / lpc);
+        const int cap = g_num_sms * (16 / kNW3);
         const int grid = work < cap ? work : cap;
         ProfScope ps(ctx, st, SLOT_ROWS_INV);
-        if (q.nx == 256) fbk_fast_rows_inverse<16, 16><<<grid, 256, fast_smem(256), st>>>(fp);
-        else if (q.nx == 512) fbk_fast_rows_inverse<32, 16><<<grid, 256, fast_smem(512), st>>>(fp);
-        else fbk_fast_rows_inverse<32, 32><<<grid, 256, fast_smem(1024), st>>>(fp);
+        if (q.nx == 256) fbk_fast_rows_inverse<16, 16><<<grid, 32 * kNW3, fast_smem(256, kNW3), st>>>(fp);
+        else if (q.nx == 512) fbk_fast_rows_inverse<32, 16><<<grid, 32 * kNW3, fast_smem(512, kNW3), st>>>(fp);
+        else fbk_fast_rows_inverse<32, 32><<<grid, 32 * kNW3, fast_smem(1024, kNW3), st>>>(fp);
     }
     {
         ProfScope ps(ctx, st, SLOT_FINALIZE);

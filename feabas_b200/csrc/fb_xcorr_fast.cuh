@@ -39,9 +39,14 @@ template <int E, int T> struct WarpFFT {
     // conjugations folded into the neighbouring point-wise steps, so that every kernel
     // runs ONE butterfly body (instruction-cache footprint).
     template <bool PRUNED>
-    static __device__ __forceinline__ void run(cx<float>* v, cx<float>* region, const cx<float>* tw, int t)
+    static __device__ __forceinline__ void run(cx<float>* v, cx<float>* region, const cx<float>* tw, int t,
+                                               bool pruned_now = true)
     {
-        if (PRUNED) RegFFT<float, E, false>::run_pruned(v); else RegFFT<float, E, false>::run(v);
+        // first radix-2 level: skipped arithmetic when the upper half of the input is zero; the
+        // remaining levels are one shared body
+        if (PRUNED && pruned_now) DifLevelPruned<float, E, false>::run(v); else DifLevel<float, E, false>::run(v);
+        RegFFT<float, E / 2, false>::run(v);
+        RegFFT<float, E / 2, false>::run(v + E / 2);
 #pragma unroll
         for (int k1 = 0; k1 < E; ++k1) {
             cx<float> a = v[brev<E>(k1)];
@@ -77,23 +82,21 @@ struct FastParams {
     int hp0, hp1;
 };
 
-constexpr int kFastWarps = 8;
-
 // ---------------------------------------------------------------------------------------------
 // K1: forward row transforms, two image rows per complex line, transposed half-spectrum out.
-// grid-stride over (pair, image, tile of TR = 16*LPW rows).
+// grid-stride over (pair, image, tile of TR = 2*LPW*NW rows).  NW warps per CTA.
 // ---------------------------------------------------------------------------------------------
-template <int E, int T, typename TI, bool PRUNED>
+template <int E, int T, int NW, typename TI, bool PRUNED>
 __device__ void kfast_rows_forward(const FastParams& fp, unsigned char* smem)
 {
     using W = WarpFFT<E, T>;
-    constexpr int N = W::N, LPW = W::LPW, RS = W::RS, TR = 2 * LPW * kFastWarps;
+    constexpr int N = W::N, LPW = W::LPW, RS = W::RS, LPC = LPW * NW, TR = 2 * LPC, NT = 32 * NW;
     const XcParams& p = fp.x;
     cx<float>* regions = reinterpret_cast<cx<float>*>(smem);
-    cx<float>* tw = regions + kFastWarps * LPW * RS;
+    cx<float>* tw = regions + LPC * RS;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int t = lane % T, lw = lane / T;                 // lane within line, line within warp
-    for (int i = tid; i < N; i += blockDim.x) tw[i] = fp.twx[i];
+    for (int i = tid; i < N; i += NT) tw[i] = fp.twx[i];
     __syncthreads();
     const int tiles0 = fp.hp0 / TR, tiles1 = fp.hp1 / TR, tpp = tiles0 + tiles1;
     const int kp = p.kp;
@@ -129,18 +132,19 @@ __device__ void kfast_rows_forward(const FastParams& fp, unsigned char* smem)
 #pragma unroll
         for (int j = 0; j < E; ++j) region[W::out_k(t, j)] = v[W::out_reg(j)];
         __syncthreads();
-        // separation + transposed store: thread -> (row r minor, k major); r is fixed per thread
+        // separation + transposed store: thread -> (line l minor, k major); both rows of a line are
+        // adjacent in FT, so one 16-byte store writes the pair (A[k], B[k])
         {
-            constexpr int KSTEP = 256 / TR;
-            const int r = tid % TR;
-            const cx<float>* reg = regions + (r >> 1) * RS;
-            const bool odd = r & 1;
-            cx<float>* dst = FT + row0 + r;
-            for (int k = tid / TR; k < kp; k += KSTEP) {
+            constexpr int KSTEP = NT / LPC;
+            const int l = tid % LPC;
+            const cx<float>* reg = regions + l * RS;
+            float4* dst = reinterpret_cast<float4*>(FT + row0 + 2 * l);
+            for (int k = tid / LPC; k < kp; k += KSTEP) {
                 const cx<float> zk = reg[k], zm = reg[k ? N - k : 0];
-                const cx<float> o = odd ? mk<float>(0.5f * (zk.y + zm.y), 0.5f * (zm.x - zk.x))
-                                        : mk<float>(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
-                dst[(size_t)k * hp] = o;
+                float4 o;
+                o.x = 0.5f * (zk.x + zm.x); o.y = 0.5f * (zk.y - zm.y);      // row 2l   : (Z[k] + conj Z[N-k]) / 2
+                o.z = 0.5f * (zk.y + zm.y); o.w = 0.5f * (zm.x - zk.x);      // row 2l+1 : (Z[k] - conj Z[N-k]) / 2i
+                dst[(size_t)k * (hp / 2)] = o;
             }
         }
         __syncthreads();
@@ -148,30 +152,35 @@ __device__ void kfast_rows_forward(const FastParams& fp, unsigned char* smem)
 }
 
 // ---------------------------------------------------------------------------------------------
-// K2: column stage.  Warp w < 4 transforms the F0 column(s), warp w + 4 the same F1 column(s);
-// they swap spectra through shared memory, form P = conj(F0) F1 and Q = F0 F1, inverse
-// transform and store the P / Q columns contiguously.  grid-stride over (pair, column group).
+// K2: column stage.  Warp w < NW/2 transforms the F0 column(s), warp w + NW/2 the same F1
+// column(s); they swap spectra through shared memory, form conj(P) = F0 conj(F1) and
+// conj(Q) = conj(F0) conj(F1), and transform again (forward transform of the conjugate =
+// conjugate of the inverse transform; consumers undo the conjugation).  The two transforms of a
+// column run through ONE copy of the butterfly code (rolled two-phase loop).
+// grid-stride over (pair, column group).
 // ---------------------------------------------------------------------------------------------
-template <int E, int T, bool PRUNED0>
+template <int E, int T, int NW, bool PRUNED0>
 __device__ void kfast_columns(const FastParams& fp, unsigned char* smem)
 {
     using W = WarpFFT<E, T>;
-    constexpr int N = W::N, LPW = W::LPW, RS = W::RS, CPG = LPW * (kFastWarps / 2);   // columns per CTA
+    constexpr int N = W::N, LPW = W::LPW, RS = W::RS, CPG = LPW * (NW / 2), NT = 32 * NW;   // columns per CTA
     const XcParams& p = fp.x;
     cx<float>* regions = reinterpret_cast<cx<float>*>(smem);
-    cx<float>* tw = regions + kFastWarps * LPW * RS;
+    cx<float>* tw = regions + NW * LPW * RS;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int t = lane % T, lw = lane / T;
-    const bool roleB = warp >= kFastWarps / 2;
-    const int pw = roleB ? warp - kFastWarps / 2 : warp;   // pair-of-warps index
-    for (int i = tid; i < N; i += blockDim.x) tw[i] = fp.twy[i];
+    const bool roleB = warp >= NW / 2;
+    const int pw = roleB ? warp - NW / 2 : warp;           // pair-of-warps index
+    for (int i = tid; i < N; i += NT) tw[i] = fp.twy[i];
     __syncthreads();
     const bool mirror = p.conf_mode == CONF_MIRROR;
     const int kp = p.kp, groups = (kp + CPG - 1) / CPG;
     const float sc = (float)p.scale;
+    const float sgn = roleB ? -sc : sc;
     cx<float>* mine = regions + (warp * LPW + lw) * RS;
-    cx<float>* other = regions + ((roleB ? pw : pw + kFastWarps / 2) * LPW + lw) * RS;
+    cx<float>* other = regions + ((roleB ? pw : pw + NW / 2) * LPW + lw) * RS;
     const int hp = roleB ? fp.hp1 : fp.hp0;
+    const bool second_phase = !roleB || mirror;
     for (int work = blockIdx.x; work < p.n * groups; work += gridDim.x) {
         const int pair = work / groups, grp = work - pair * groups;
         const int col = grp * CPG + pw * LPW + lw;
@@ -185,29 +194,26 @@ __device__ void kfast_columns(const FastParams& fp, unsigned char* smem)
             if ((!PRUNED0 || n1 < E / 2) && y < hp) a = ldg(src + y);
             v[n1] = a;
         }
-        W::template run<PRUNED0>(v, mine, tw, t);
+#pragma unroll 1
+        for (int phase = 0; phase < 2; ++phase) {
+            W::template run<PRUNED0>(v, mine, tw, t, phase == 0);
+            if (phase == 0) {
 #pragma unroll
-        for (int j = 0; j < E; ++j) mine[W::out_k(t, j)] = v[W::out_reg(j)];
-        asm volatile("bar.sync %0, 64;" ::"r"(pw + 1) : "memory");
-        // role A: m = F0, o = F1: conj(P) = F0 conj(F1); role B: m = F1, o = F0: conj(Q) = conj(F1) conj(F0).
-        // The forward transform of conj(P) is conj(ifft-surface); consumers undo the conjugation.
-        const float sgn = roleB ? -sc : sc;
+                for (int j = 0; j < E; ++j) mine[W::out_k(t, j)] = v[W::out_reg(j)];
+                asm volatile("bar.sync %0, 64;" ::"r"(pw + 1) : "memory");
+                // the output of lane t, k = t + T j, is exactly the input element n1 = j of the
+                // next transform: a register permutation, no exchange needed
+                cx<float> u[E];
 #pragma unroll
-        for (int j = 0; j < E; ++j) {
-            const cx<float> o = other[W::out_k(t, j)], m = v[W::out_reg(j)];
-            v[W::out_reg(j)] = cmulc(mk<float>(m.x * sc, m.y * sgn), o);
-        }
-        asm volatile("bar.sync %0, 64;" ::"r"(pw + 1) : "memory");
-        if (!roleB || mirror) {
-            // natural order in -> registers n1: value at y-frequency k = n1 T + t
+                for (int j = 0; j < E; ++j) {
+                    const cx<float> o = other[W::out_k(t, j)], m = v[W::out_reg(j)];
+                    u[j] = cmulc(mk<float>(m.x * sc, m.y * sgn), o);
+                }
 #pragma unroll
-            for (int j = 0; j < E; ++j) mine[W::out_k(t, j)] = v[W::out_reg(j)];
-            __syncwarp();
-#pragma unroll
-            for (int n1 = 0; n1 < E; ++n1) v[n1] = mine[n1 * T + t];
-            __syncwarp();
-            W::template run<false>(v, mine, tw, t);
-            if (live) {
+                for (int j = 0; j < E; ++j) v[j] = u[j];
+                asm volatile("bar.sync %0, 64;" ::"r"(pw + 1) : "memory");
+                if (!second_phase) break;
+            } else if (live) {
                 cx<float>* dst = fp.GT + (((size_t)pair * 2 + (roleB ? 1 : 0)) * kp + col) * N;
 #pragma unroll
                 for (int j = 0; j < E; ++j) dst[W::out_k(t, j)] = v[W::out_reg(j)];
@@ -224,17 +230,17 @@ __device__ void kfast_columns(const FastParams& fp, unsigned char* smem)
 // Only the per-line maxima are reduced here; the finalize kernel locates x inside the winning
 // row (np.argmax order: lowest row, then lowest x).  grid-stride over (pair, tile of lines).
 // ---------------------------------------------------------------------------------------------
-template <int E, int T>
+template <int E, int T, int NW>
 __device__ void kfast_rows_inverse(const FastParams& fp, unsigned char* smem)
 {
     using W = WarpFFT<E, T>;
-    constexpr int N = W::N, LPW = W::LPW, RS = W::RS, LPC = LPW * kFastWarps;   // lines per CTA
+    constexpr int N = W::N, LPW = W::LPW, RS = W::RS, LPC = LPW * NW, NT = 32 * NW;   // LPC lines per CTA
     const XcParams& p = fp.x;
     cx<float>* regions = reinterpret_cast<cx<float>*>(smem);
     cx<float>* tw = regions + LPC * RS;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int t = lane % T, lw = lane / T;
-    for (int i = tid; i < N; i += blockDim.x) tw[i] = fp.twx[i];
+    for (int i = tid; i < N; i += NT) tw[i] = fp.twx[i];
     const bool mirror = p.conf_mode == CONF_MIRROR, want_std = p.conf_mode == CONF_STD;
     const int kp = p.kp, ny = p.ny;
     const int lines_pp = mirror ? ny : (ny + 1) / 2;          // lines per pair
@@ -252,14 +258,14 @@ __device__ void kfast_rows_inverse(const FastParams& fp, unsigned char* smem)
             if (y < ny) {
                 const cx<float>* src = GP + y;
                 cx<float>* dst = regions + r * RS;
-                for (int c = tid / LPC; c < 2 * kp; c += 256 / LPC) cp_async8(dst + c, src + (size_t)c * ny);
+                for (int c = tid / LPC; c < 2 * kp; c += NT / LPC) cp_async8(dst + c, src + (size_t)c * ny);
             }
         } else {
             const int r2 = tid % (2 * LPC), y = 2 * line0 + r2;
             if (y < ny) {
                 const cx<float>* src = GP + y;
                 cx<float>* dst = regions + (r2 >> 1) * RS + (r2 & 1) * kp;
-                for (int kx = tid / (2 * LPC); kx < kp; kx += 256 / (2 * LPC)) cp_async8(dst + kx, src + (size_t)kx * ny);
+                for (int kx = tid / (2 * LPC); kx < kp; kx += NT / (2 * LPC)) cp_async8(dst + kx, src + (size_t)kx * ny);
             }
         }
         cp_async_wait_all();

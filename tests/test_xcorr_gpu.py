@@ -156,7 +156,7 @@ FAST_CASES = [
     (3, (256, 128), (256, 128), dict(subpixel=True, conf_mode=0)),             # 512 x 256, NONE
     (3, (256, 256), (256, 256), dict(subpixel=True, conf_mode=1)),             # STD
     (3, (255, 255), (255, 255), dict(subpixel=True, conf_mode=0, pad=False)),  # 256^2 odd rows, NONE pairs rows
-    (2, (501, 480), (501, 480), dict(subpixel=True, conf_mode=1, pad=False)),  # 512 x 512 (ny odd rows)
+    (2, (501, 512), (501, 512), dict(subpixel=True, conf_mode=1, pad=False)),  # 512 x 512 (odd rows)
 ]
 
 
