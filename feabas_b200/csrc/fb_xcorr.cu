@@ -284,7 +284,7 @@ static int make_problem(Problem& q, int n, int h0, int w0, int h1, int w1, int i
     if (q.fast) {
         q.hp0 = (h0 + 31) & ~31; q.hp1 = (h1 + 31) & ~31;
         q.nrt = g.mirror ? fft_h : (fft_h + 1) / 2;
-        q.ws_per_pair = ((size_t)g.kp * (q.hp0 + q.hp1) + (size_t)2 * g.kp * fft_h) * 8 + (size_t)q.nrt * sizeof(Partial);
+        q.ws_per_pair = ((size_t)g.kp * (q.hp0 + q.hp1) + (size_t)2 * ((g.kp + 3) / 4) * 4 * fft_h) * 8 + (size_t)q.nrt * sizeof(Partial);
     }
     q.ws_per_pair = (q.ws_per_pair + 255) & ~(size_t)255;
     return FB_OK;
@@ -339,7 +339,7 @@ static void fast_et(int n, int& E, int& T)
 static size_t fast_smem(int n, int nw)
 {
     int E, T; fast_et(n, E, T);
-    return ((size_t)nw * (32 / T) * (n + E + 1) + n) * sizeof(cx<float>);
+    return ((size_t)nw * (32 / T) * (n + E + 16) + n) * sizeof(cx<float>);
 }
 
 static int g_num_sms = 0;
@@ -356,13 +356,14 @@ static int launch_fast(const Problem& q, StreamCtx& ctx, XcParams& p, int nb, cu
     if (!g_num_sms) { cudaDeviceProp pr; CU(cudaGetDeviceProperties(&pr, ctx.device)); g_num_sms = pr.multiProcessorCount; }
     const Geometry& g = q.g;
     unsigned char* w = reinterpret_cast<unsigned char*>(ctx.ws);
-    const size_t f0 = (size_t)nb * g.kp * q.hp0 * 8, f1 = (size_t)nb * g.kp * q.hp1 * 8, gg = (size_t)nb * 2 * g.kp * q.ny * 8;
+    const int nblk = (g.kp + 3) / 4;
+    const size_t f0 = (size_t)nb * g.kp * q.hp0 * 8, f1 = (size_t)nb * g.kp * q.hp1 * 8, gg = (size_t)nb * 2 * nblk * 4 * q.ny * 8;
     fp.FT0 = reinterpret_cast<cx<float>*>(w);
     fp.FT1 = reinterpret_cast<cx<float>*>(w + f0);
     fp.GT = reinterpret_cast<cx<float>*>(w + f0 + f1);
     p.part = reinterpret_cast<Partial*>(w + f0 + f1 + gg);
     p.G = fp.GT; p.gt_layout = 1; p.nrt = q.nrt;
-    fp.hp0 = q.hp0; fp.hp1 = q.hp1;
+    fp.hp0 = q.hp0; fp.hp1 = q.hp1; fp.nblk = nblk;
     fp.x = p;
     // K1
     {
@@ -391,9 +392,9 @@ static int launch_fast(const Problem& q, StreamCtx& ctx, XcParams& p, int nb, cu
     // K3
     {
         const int lpc = (32 / TX) * kNW3;
-        const int work = nb * ((q.nrt + lpc - 1) / lpc);
+        const long long work = ((long long)nb * q.nrt + lpc - 1) / lpc;
         const int cap = g_num_sms * (16 / kNW3);
-        const int grid = work < cap ? work : cap;
+        const int grid = work < cap ? (int)work : cap;
         ProfScope ps(ctx, st, SLOT_ROWS_INV);
         if (q.nx == 256) fbk_fast_rows_inverse<16, 16><<<grid, 32 * kNW3, fast_smem(256, kNW3), st>>>(fp);
         else if (q.nx == 512) fbk_fast_rows_inverse<32, 16><<<grid, 32 * kNW3, fast_smem(512, kNW3), st>>>(fp);

@@ -228,8 +228,10 @@ FB_DEV void rows_inverse_fill(const XcParams& p, const cx<T>* X, const cx<T>* Y,
     const int nx = p.nx, kp = p.kp;
     const int* pos = p.px.pos;
     for (int k = tid_in_line; k < kp; k += stride) {
-        cx<T> a = X[k * ks];
-        cx<T> b = Y ? Y[k * ks] : mk<T>(T(0), T(0));
+        // gt_layout: conjugated surfaces in 4-column blocks [blk][y][4]; ks = elements per block
+        const size_t off = p.gt_layout ? (size_t)(k >> 2) * ks + (k & 3) : (size_t)k * ks;
+        cx<T> a = X[off];
+        cx<T> b = Y ? Y[off] : mk<T>(T(0), T(0));
         if (p.gt_layout) { a.y = -a.y; b.y = -b.y; }
         if (k == 0 || 2 * k == nx) {
             s[(size_t)FB_LDG(pos + k) * pitch + l] = mk<T>(a.x, b.x);
@@ -462,9 +464,10 @@ FB_DEV void k4_finalize(const XcParams& p, int bid, int tid, int nthr, unsigned 
     }
     Acc<T> best = block_reduce<T>(acc, red, tid, nthr);
     if (p.gt_layout) {
-        // fast path: G^T[pair][P|Q][kx][y]
-        const cx<T>* Pb = reinterpret_cast<const cx<T>*>(p.G) + (size_t)bid * 2 * p.kp * p.ny;
-        finalize_pair<T>(p, bid, best, Pb, Pb + (size_t)p.kp * p.ny, 1, mirror, s, tid, nthr, (size_t)p.ny);
+        // fast path: G[pair][P|Q][blk][y][4], row y starts at element y * 4 of each block
+        const size_t plane = (size_t)((p.kp + 3) / 4) * p.ny * 4;
+        const cx<T>* Pb = reinterpret_cast<const cx<T>*>(p.G) + (size_t)bid * 2 * plane;
+        finalize_pair<T>(p, bid, best, Pb, Pb + plane, 4, mirror, s, tid, nthr, (size_t)p.ny * 4);
         return;
     }
     const cx<T>* Pb = reinterpret_cast<const cx<T>*>(p.G) + (size_t)bid * p.ny * 2 * p.fpitch;

@@ -27,7 +27,10 @@ template <int E, int T> struct WarpFFT {
     static constexpr int N = E * T;
     static constexpr int LPW = 32 / T;        // lines per warp
     static constexpr int M = E / T;           // stage-B transforms per lane
-    static constexpr int RS = N + E + 1;      // slots per line region (odd)
+    static constexpr int RS = N + E + 1;      // minimum slots per line region
+    // smallest region stride >= RS with stride % 16 == m: makes accesses by (line-minor, slot-major)
+    // thread groups of 16/m lines conflict free
+    static constexpr __host__ __device__ int stride_mod16(int m) { return RS + ((m - RS % 16) + 16) % 16; }
 
     // k (natural index) of register j after run(): see out_index()
     static __device__ __forceinline__ int out_k(int t, int j) { return t + T * (j % M) + E * (j / M); }
@@ -78,8 +81,9 @@ struct FastParams {
     const cx<float>* twy;   // [EY][TY]
     cx<float>* FT0;         // [n][kp][hp0]
     cx<float>* FT1;         // [n][kp][hp1]
-    cx<float>* GT;          // [n][2][kp][ny]
+    cx<float>* GT;          // [n][2][nblk][ny][4]: conj of the column-stage output, 4-column blocks
     int hp0, hp1;
+    int nblk;               // ceil(kp / 4)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -90,7 +94,8 @@ template <int E, int T, int NW, typename TI, bool PRUNED>
 __device__ void kfast_rows_forward(const FastParams& fp, unsigned char* smem)
 {
     using W = WarpFFT<E, T>;
-    constexpr int N = W::N, LPW = W::LPW, RS = W::RS, LPC = LPW * NW, TR = 2 * LPC, NT = 32 * NW;
+    constexpr int N = W::N, LPW = W::LPW, LPC = LPW * NW, TR = 2 * LPC, NT = 32 * NW;
+    constexpr int RS = W::stride_mod16(LPC >= 16 ? 1 : 16 / LPC);
     const XcParams& p = fp.x;
     cx<float>* regions = reinterpret_cast<cx<float>*>(smem);
     cx<float>* tw = regions + LPC * RS;
@@ -163,7 +168,10 @@ template <int E, int T, int NW, bool PRUNED0>
 __device__ void kfast_columns(const FastParams& fp, unsigned char* smem)
 {
     using W = WarpFFT<E, T>;
-    constexpr int N = W::N, LPW = W::LPW, RS = W::RS, CPG = LPW * (NW / 2), NT = 32 * NW;   // columns per CTA
+    constexpr int N = W::N, LPW = W::LPW, CPG = LPW * (NW / 2), NT = 32 * NW;   // CPG columns per CTA
+    constexpr int RS = W::stride_mod16(16 / CPG);
+    constexpr int GT_ = 32 * (NW / 2);                     // threads per role group
+    static_assert(CPG == 4 || CPG == 8, "column group");
     const XcParams& p = fp.x;
     cx<float>* regions = reinterpret_cast<cx<float>*>(smem);
     cx<float>* tw = regions + NW * LPW * RS;
@@ -171,6 +179,7 @@ __device__ void kfast_columns(const FastParams& fp, unsigned char* smem)
     const int t = lane % T, lw = lane / T;
     const bool roleB = warp >= NW / 2;
     const int pw = roleB ? warp - NW / 2 : warp;           // pair-of-warps index
+    const int g = tid - (roleB ? GT_ : 0);                 // thread index inside the role group
     for (int i = tid; i < N; i += NT) tw[i] = fp.twy[i];
     __syncthreads();
     const bool mirror = p.conf_mode == CONF_MIRROR;
@@ -179,6 +188,7 @@ __device__ void kfast_columns(const FastParams& fp, unsigned char* smem)
     const float sgn = roleB ? -sc : sc;
     cx<float>* mine = regions + (warp * LPW + lw) * RS;
     cx<float>* other = regions + ((roleB ? pw : pw + NW / 2) * LPW + lw) * RS;
+    cx<float>* grp_regions = regions + (roleB ? (NW / 2) * LPW : 0) * RS;
     const int hp = roleB ? fp.hp1 : fp.hp0;
     const bool second_phase = !roleB || mirror;
     for (int work = blockIdx.x; work < p.n * groups; work += gridDim.x) {
@@ -197,9 +207,9 @@ __device__ void kfast_columns(const FastParams& fp, unsigned char* smem)
 #pragma unroll 1
         for (int phase = 0; phase < 2; ++phase) {
             W::template run<PRUNED0>(v, mine, tw, t, phase == 0);
-            if (phase == 0) {
 #pragma unroll
-                for (int j = 0; j < E; ++j) mine[W::out_k(t, j)] = v[W::out_reg(j)];
+            for (int j = 0; j < E; ++j) mine[W::out_k(t, j)] = v[W::out_reg(j)];
+            if (phase == 0) {
                 asm volatile("bar.sync %0, 64;" ::"r"(pw + 1) : "memory");
                 // the output of lane t, k = t + T j, is exactly the input element n1 = j of the
                 // next transform: a register permutation, no exchange needed
@@ -213,10 +223,18 @@ __device__ void kfast_columns(const FastParams& fp, unsigned char* smem)
                 for (int j = 0; j < E; ++j) v[j] = u[j];
                 asm volatile("bar.sync %0, 64;" ::"r"(pw + 1) : "memory");
                 if (!second_phase) break;
-            } else if (live) {
-                cx<float>* dst = fp.GT + (((size_t)pair * 2 + (roleB ? 1 : 0)) * kp + col) * N;
-#pragma unroll
-                for (int j = 0; j < E; ++j) dst[W::out_k(t, j)] = v[W::out_reg(j)];
+            } else {
+                // role-group transpose through the (now free) regions: 4-column blocks GT[blk][y][4]
+                asm volatile("bar.sync %0, %1;" ::"r"(roleB ? 10 : 9), "r"(GT_) : "memory");
+                const int cc = g % CPG;
+                const int blk = (grp * CPG + cc) >> 2;
+                if (grp * CPG + cc < kp) {
+                    const cx<float>* reg = grp_regions + cc * RS;
+                    cx<float>* dst = fp.GT + ((((size_t)pair * 2 + (roleB ? 1 : 0)) * fp.nblk + blk) * N) * 4 + (cc & 3);
+#pragma unroll 4
+                    for (int y = g / CPG; y < N; y += GT_ / CPG) dst[(size_t)y * 4] = reg[y];
+                }
+                asm volatile("bar.sync %0, %1;" ::"r"(roleB ? 10 : 9), "r"(GT_) : "memory");
             }
         }
     }
@@ -224,77 +242,68 @@ __device__ void kfast_columns(const FastParams& fp, unsigned char* smem)
 
 // ---------------------------------------------------------------------------------------------
 // K3: inverse row transforms + per-line maxima.  A line is (P row y, Q row y) with the mirror
-// term, else (P row y, P row y+1).  GT holds the CONJUGATE of the column-stage output (see K2),
-// so the Hermitian extension below builds conj(Z) and the forward transform returns
+// term, else (P row y, P row y+1).  GT holds the CONJUGATE of the column-stage output in
+// 4-column blocks [blk][y][4], so a lane group reads whole 32-byte sectors straight into
+// registers; the Hermitian extension below builds conj(Z) and the forward transform returns
 // conj(surface): C = Re, mirror = -Im (only |.| is used), second row = -Im.
 // Only the per-line maxima are reduced here; the finalize kernel locates x inside the winning
-// row (np.argmax order: lowest row, then lowest x).  grid-stride over (pair, tile of lines).
+// row (np.argmax order: lowest row, then lowest x).  Warps are independent: grid-stride over lines.
 // ---------------------------------------------------------------------------------------------
 template <int E, int T, int NW>
 __device__ void kfast_rows_inverse(const FastParams& fp, unsigned char* smem)
 {
     using W = WarpFFT<E, T>;
-    constexpr int N = W::N, LPW = W::LPW, RS = W::RS, LPC = LPW * NW, NT = 32 * NW;   // LPC lines per CTA
+    constexpr int N = W::N, LPW = W::LPW, RS = W::RS, NT = 32 * NW;
     const XcParams& p = fp.x;
     cx<float>* regions = reinterpret_cast<cx<float>*>(smem);
-    cx<float>* tw = regions + LPC * RS;
+    cx<float>* tw = regions + NW * LPW * RS;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int t = lane % T, lw = lane / T;
     for (int i = tid; i < N; i += NT) tw[i] = fp.twx[i];
+    __syncthreads();
     const bool mirror = p.conf_mode == CONF_MIRROR, want_std = p.conf_mode == CONF_STD;
-    const int kp = p.kp, ny = p.ny;
+    const int ny = p.ny;
     const int lines_pp = mirror ? ny : (ny + 1) / 2;          // lines per pair
-    const int tiles = (lines_pp + LPC - 1) / LPC;
-    const int line = warp * LPW + lw;
-    cx<float>* region = regions + line * RS;
-    for (int work = blockIdx.x; work < p.n * tiles; work += gridDim.x) {
-        const int pair = work / tiles, tile = work - pair * tiles;
-        const int line0 = tile * LPC;
-        const cx<float>* GP = fp.GT + (size_t)pair * 2 * kp * ny;
-        __syncthreads();                                       // previous tile fully consumed (and tw visible)
-        if (mirror) {
-            // slots [0,kp): P^T[kx][y], slots [kp,2kp): Q^T[kx][y]; thread -> fixed line r, c strided
-            const int r = tid % LPC, y = line0 + r;
-            if (y < ny) {
-                const cx<float>* src = GP + y;
-                cx<float>* dst = regions + r * RS;
-                for (int c = tid / LPC; c < 2 * kp; c += NT / LPC) cp_async8(dst + c, src + (size_t)c * ny);
-            }
-        } else {
-            const int r2 = tid % (2 * LPC), y = 2 * line0 + r2;
-            if (y < ny) {
-                const cx<float>* src = GP + y;
-                cx<float>* dst = regions + (r2 >> 1) * RS + (r2 & 1) * kp;
-                for (int kx = tid / (2 * LPC); kx < kp; kx += NT / (2 * LPC)) cp_async8(dst + kx, src + (size_t)kx * ny);
-            }
-        }
-        cp_async_wait_all();
-        __syncthreads();
-        const int gl = line0 + line;                           // global line index
-        const bool live = gl < lines_pp;
-        const bool have2 = mirror || (2 * gl + 1 < ny);        // second half of the line present
+    const long long total = (long long)p.n * lines_pp;
+    cx<float>* region = regions + (warp * LPW + lw) * RS;
+    const size_t plane = (size_t)fp.nblk * ny * 4;            // elements per P / Q plane
+    const size_t bstride = (size_t)ny * 4;                    // elements per 4-column block
+    // warp-uniform trip count: the T-lane groups of a warp walk neighbouring lines
+    const long long first = ((long long)blockIdx.x * NW + warp) * LPW;
+    const long long step = (long long)gridDim.x * NW * LPW;
+    for (long long base = first; base < total; base += step) {
+        const long long lid = base + lw;
+        const bool live = lid < total;
+        const int pair = (int)((live ? lid : 0) / lines_pp), gl = (int)((live ? lid : 0) - (long long)pair * lines_pp);
+        const int y0 = mirror ? gl : 2 * gl;
+        const bool have2 = mirror || (y0 + 1 < ny);
+        const cx<float>* A = fp.GT + (size_t)pair * 2 * plane + (size_t)y0 * 4;           // first half of the line
+        const cx<float>* B = mirror ? A + plane : A + 4;                                   // second half
         const float h2 = have2 ? 1.f : 0.f;
+        if (!have2) B = A;
         cx<float> v[E];
 #pragma unroll
         for (int n1 = 0; n1 < E; ++n1) {
             const int k = n1 * T + t;
             cx<float> z;
             if (n1 < E / 2 || (n1 == E / 2 && t == 0)) {
-                const cx<float> a = region[k];
-                cx<float> b = region[kp + k];
+                const size_t off = (size_t)(k >> 2) * bstride + (k & 3);
+                const cx<float> a = ldg(A + off);
+                cx<float> b = ldg(B + off);
                 b = mk<float>(b.x * h2, b.y * h2);
                 // conj(P + iQ) with stored a = conj(P), b = conj(Q):  a - i b
                 z = (k == 0 || 2 * k == N) ? mk<float>(a.x, -b.x) : mk<float>(a.x + b.y, a.y - b.x);
             } else {
-                const cx<float> a = region[N - k];
-                cx<float> b = region[kp + N - k];
+                const int m = N - k;
+                const size_t off = (size_t)(m >> 2) * bstride + (m & 3);
+                const cx<float> a = ldg(A + off);
+                cx<float> b = ldg(B + off);
                 b = mk<float>(b.x * h2, b.y * h2);
                 // conj(conj(P) + i conj(Q)) = P - i Q = conj(a) - i conj(b)
                 z = mk<float>(a.x - b.y, -a.y - b.x);
             }
-            v[n1] = live ? z : mk<float>(0.f, 0.f);
+            v[n1] = z;
         }
-        __syncwarp();
         W::template run<false>(v, region, tw, t);
         // out = conj(surface line): Re -> first row, -Im -> mirror surface / second row
         float best = v[0].x, second = mirror ? fabsf(v[0].y) : -v[0].y;
@@ -322,7 +331,7 @@ __device__ void kfast_rows_inverse(const FastParams& fp, unsigned char* smem)
         }
         if (t == 0 && live) {
             // idx = first flat index of the row that holds the maximum; x is resolved by the finalize kernel
-            int row = mirror ? gl : 2 * gl;
+            int row = y0;
             float mir = 0.f;
             if (mirror) mir = second;
             else if (have2 && second > best) { best = second; row += 1; }
