@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(512) fbk_fused(const __grid_constant__ XcParam
 
 
 // ---- register-resident fast path (power-of-two grids, float32 compute) ----
-constexpr int kNW1 = 4, kNW2 = 8, kNW3 = 4;          // warps per CTA of K1 / K2 / K3
+constexpr int kNW1 = 4, kNW2 = 8;                    // warps per CTA of K1 / K2 (K3: 256 threads)
 template <int E, int T, typename TI, bool PRUNED>
 __global__ void __launch_bounds__(32 * kNW1, 16 / kNW1) fbk_fast_rows_forward(const __grid_constant__ FastParams fp)
 {
@@ -94,10 +94,10 @@ __global__ void __launch_bounds__(32 * kNW2, 16 / kNW2) fbk_fast_columns(const _
     kfast_columns<E, T, kNW2, PRUNED>(fp, smem);
 }
 template <int E, int T>
-__global__ void __launch_bounds__(32 * kNW3, 16 / kNW3) fbk_fast_rows_inverse(const __grid_constant__ FastParams fp)
+__global__ void __launch_bounds__(256, 2) fbk_fast_rows_inverse(const __grid_constant__ FastParams fp)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    kfast_rows_inverse<E, T, kNW3>(fp, smem);
+    kfast_rows_inverse<E, T>(fp, smem);
 }
 
 // ---------------------------------------------------------------------------
@@ -284,7 +284,7 @@ static int make_problem(Problem& q, int n, int h0, int w0, int h1, int w1, int i
     if (q.fast) {
         q.hp0 = (h0 + 31) & ~31; q.hp1 = (h1 + 31) & ~31;
         q.nrt = g.mirror ? fft_h : (fft_h + 1) / 2;
-        q.ws_per_pair = ((size_t)g.kp * (q.hp0 + q.hp1) + (size_t)2 * ((g.kp + 3) / 4) * 4 * fft_h) * 8 + (size_t)q.nrt * sizeof(Partial);
+        q.ws_per_pair = ((size_t)g.kp * (q.hp0 + q.hp1) + (size_t)2 * g.kp * fft_h) * 8 + (size_t)q.nrt * sizeof(Partial);
     }
     q.ws_per_pair = (q.ws_per_pair + 255) & ~(size_t)255;
     return FB_OK;
@@ -356,14 +356,13 @@ static int launch_fast(const Problem& q, StreamCtx& ctx, XcParams& p, int nb, cu
     if (!g_num_sms) { cudaDeviceProp pr; CU(cudaGetDeviceProperties(&pr, ctx.device)); g_num_sms = pr.multiProcessorCount; }
     const Geometry& g = q.g;
     unsigned char* w = reinterpret_cast<unsigned char*>(ctx.ws);
-    const int nblk = (g.kp + 3) / 4;
-    const size_t f0 = (size_t)nb * g.kp * q.hp0 * 8, f1 = (size_t)nb * g.kp * q.hp1 * 8, gg = (size_t)nb * 2 * nblk * 4 * q.ny * 8;
+    const size_t f0 = (size_t)nb * g.kp * q.hp0 * 8, f1 = (size_t)nb * g.kp * q.hp1 * 8, gg = (size_t)nb * 2 * g.kp * q.ny * 8;
     fp.FT0 = reinterpret_cast<cx<float>*>(w);
     fp.FT1 = reinterpret_cast<cx<float>*>(w + f0);
     fp.GT = reinterpret_cast<cx<float>*>(w + f0 + f1);
     p.part = reinterpret_cast<Partial*>(w + f0 + f1 + gg);
     p.G = fp.GT; p.gt_layout = 1; p.nrt = q.nrt;
-    fp.hp0 = q.hp0; fp.hp1 = q.hp1; fp.nblk = nblk;
+    fp.hp0 = q.hp0; fp.hp1 = q.hp1;
     fp.x = p;
     // K1
     {
@@ -389,16 +388,18 @@ static int launch_fast(const Problem& q, StreamCtx& ctx, XcParams& p, int nb, cu
         else if (q.ny == 512) launch_fast_k2<32, 16>(fp, pruned, grid, fast_smem(512, kNW2), st);
         else launch_fast_k2<32, 32>(fp, pruned, grid, fast_smem(1024, kNW2), st);
     }
-    // K3
+    // K3: 256 threads own R = 256 / TX lines
     {
-        const int lpc = (32 / TX) * kNW3;
-        const long long work = ((long long)nb * q.nrt + lpc - 1) / lpc;
-        const int cap = g_num_sms * (16 / kNW3);
-        const int grid = work < cap ? (int)work : cap;
+        const int R = 256 / TX;
+        const int work = nb * ((q.nrt + R - 1) / R);
+        const int cap = g_num_sms * 2;
+        const int grid = work < cap ? work : cap;
+        const int XS = TX * R + (R == 8 ? 8 : 0);
+        const size_t sm3 = ((size_t)EX * XS + q.nx) * sizeof(cx<float>) + 8 * R * 2 * (sizeof(float) + sizeof(double));
         ProfScope ps(ctx, st, SLOT_ROWS_INV);
-        if (q.nx == 256) fbk_fast_rows_inverse<16, 16><<<grid, 32 * kNW3, fast_smem(256, kNW3), st>>>(fp);
-        else if (q.nx == 512) fbk_fast_rows_inverse<32, 16><<<grid, 32 * kNW3, fast_smem(512, kNW3), st>>>(fp);
-        else fbk_fast_rows_inverse<32, 32><<<grid, 32 * kNW3, fast_smem(1024, kNW3), st>>>(fp);
+        if (q.nx == 256) fbk_fast_rows_inverse<16, 16><<<grid, 256, sm3, st>>>(fp);
+        else if (q.nx == 512) fbk_fast_rows_inverse<32, 16><<<grid, 256, sm3, st>>>(fp);
+        else fbk_fast_rows_inverse<32, 32><<<grid, 256, sm3, st>>>(fp);
     }
     {
         ProfScope ps(ctx, st, SLOT_FINALIZE);

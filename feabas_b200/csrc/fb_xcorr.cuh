@@ -228,8 +228,7 @@ FB_DEV void rows_inverse_fill(const XcParams& p, const cx<T>* X, const cx<T>* Y,
     const int nx = p.nx, kp = p.kp;
     const int* pos = p.px.pos;
     for (int k = tid_in_line; k < kp; k += stride) {
-        // gt_layout: conjugated surfaces in 4-column blocks [blk][y][4]; ks = elements per block
-        const size_t off = p.gt_layout ? (size_t)(k >> 2) * ks + (k & 3) : (size_t)k * ks;
+        const size_t off = (size_t)k * ks;
         cx<T> a = X[off];
         cx<T> b = Y ? Y[off] : mk<T>(T(0), T(0));
         if (p.gt_layout) { a.y = -a.y; b.y = -b.y; }
@@ -464,10 +463,10 @@ FB_DEV void k4_finalize(const XcParams& p, int bid, int tid, int nthr, unsigned 
     }
     Acc<T> best = block_reduce<T>(acc, red, tid, nthr);
     if (p.gt_layout) {
-        // fast path: G[pair][P|Q][blk][y][4], row y starts at element y * 4 of each block
-        const size_t plane = (size_t)((p.kp + 3) / 4) * p.ny * 4;
+        // fast path: conjugated G^T[pair][P|Q][kx][y]
+        const size_t plane = (size_t)p.kp * p.ny;
         const cx<T>* Pb = reinterpret_cast<const cx<T>*>(p.G) + (size_t)bid * 2 * plane;
-        finalize_pair<T>(p, bid, best, Pb, Pb + plane, 4, mirror, s, tid, nthr, (size_t)p.ny * 4);
+        finalize_pair<T>(p, bid, best, Pb, Pb + plane, 1, mirror, s, tid, nthr, (size_t)p.ny);
         return;
     }
     const cx<T>* Pb = reinterpret_cast<const cx<T>*>(p.G) + (size_t)bid * p.ny * 2 * p.fpitch;

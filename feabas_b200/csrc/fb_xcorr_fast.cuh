@@ -81,9 +81,8 @@ struct FastParams {
     const cx<float>* twy;   // [EY][TY]
     cx<float>* FT0;         // [n][kp][hp0]
     cx<float>* FT1;         // [n][kp][hp1]
-    cx<float>* GT;          // [n][2][nblk][ny][4]: conj of the column-stage output, 4-column blocks
+    cx<float>* GT;          // [n][2][kp][ny]: conjugate of the column-stage output, y contiguous
     int hp0, hp1;
-    int nblk;               // ceil(kp / 4)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -168,10 +167,7 @@ template <int E, int T, int NW, bool PRUNED0>
 __device__ void kfast_columns(const FastParams& fp, unsigned char* smem)
 {
     using W = WarpFFT<E, T>;
-    constexpr int N = W::N, LPW = W::LPW, CPG = LPW * (NW / 2), NT = 32 * NW;   // CPG columns per CTA
-    constexpr int RS = W::stride_mod16(16 / CPG);
-    constexpr int GT_ = 32 * (NW / 2);                     // threads per role group
-    static_assert(CPG == 4 || CPG == 8, "column group");
+    constexpr int N = W::N, LPW = W::LPW, RS = W::RS, CPG = LPW * (NW / 2), NT = 32 * NW;   // CPG columns per CTA
     const XcParams& p = fp.x;
     cx<float>* regions = reinterpret_cast<cx<float>*>(smem);
     cx<float>* tw = regions + NW * LPW * RS;
@@ -179,7 +175,6 @@ __device__ void kfast_columns(const FastParams& fp, unsigned char* smem)
     const int t = lane % T, lw = lane / T;
     const bool roleB = warp >= NW / 2;
     const int pw = roleB ? warp - NW / 2 : warp;           // pair-of-warps index
-    const int g = tid - (roleB ? GT_ : 0);                 // thread index inside the role group
     for (int i = tid; i < N; i += NT) tw[i] = fp.twy[i];
     __syncthreads();
     const bool mirror = p.conf_mode == CONF_MIRROR;
@@ -188,7 +183,6 @@ __device__ void kfast_columns(const FastParams& fp, unsigned char* smem)
     const float sgn = roleB ? -sc : sc;
     cx<float>* mine = regions + (warp * LPW + lw) * RS;
     cx<float>* other = regions + ((roleB ? pw : pw + NW / 2) * LPW + lw) * RS;
-    cx<float>* grp_regions = regions + (roleB ? (NW / 2) * LPW : 0) * RS;
     const int hp = roleB ? fp.hp1 : fp.hp0;
     const bool second_phase = !roleB || mirror;
     for (int work = blockIdx.x; work < p.n * groups; work += gridDim.x) {
@@ -207,9 +201,9 @@ __device__ void kfast_columns(const FastParams& fp, unsigned char* smem)
 #pragma unroll 1
         for (int phase = 0; phase < 2; ++phase) {
             W::template run<PRUNED0>(v, mine, tw, t, phase == 0);
-#pragma unroll
-            for (int j = 0; j < E; ++j) mine[W::out_k(t, j)] = v[W::out_reg(j)];
             if (phase == 0) {
+#pragma unroll
+                for (int j = 0; j < E; ++j) mine[W::out_k(t, j)] = v[W::out_reg(j)];
                 asm volatile("bar.sync %0, 64;" ::"r"(pw + 1) : "memory");
                 // the output of lane t, k = t + T j, is exactly the input element n1 = j of the
                 // next transform: a register permutation, no exchange needed
@@ -223,105 +217,113 @@ __device__ void kfast_columns(const FastParams& fp, unsigned char* smem)
                 for (int j = 0; j < E; ++j) v[j] = u[j];
                 asm volatile("bar.sync %0, 64;" ::"r"(pw + 1) : "memory");
                 if (!second_phase) break;
-            } else {
-                // role-group transpose through the (now free) regions: 4-column blocks GT[blk][y][4]
-                asm volatile("bar.sync %0, %1;" ::"r"(roleB ? 10 : 9), "r"(GT_) : "memory");
-                const int cc = g % CPG;
-                const int blk = (grp * CPG + cc) >> 2;
-                if (grp * CPG + cc < kp) {
-                    const cx<float>* reg = grp_regions + cc * RS;
-                    cx<float>* dst = fp.GT + ((((size_t)pair * 2 + (roleB ? 1 : 0)) * fp.nblk + blk) * N) * 4 + (cc & 3);
-#pragma unroll 4
-                    for (int y = g / CPG; y < N; y += GT_ / CPG) dst[(size_t)y * 4] = reg[y];
-                }
-                asm volatile("bar.sync %0, %1;" ::"r"(roleB ? 10 : 9), "r"(GT_) : "memory");
+            } else if (live) {
+                cx<float>* dst = fp.GT + (((size_t)pair * 2 + (roleB ? 1 : 0)) * kp + col) * N;
+#pragma unroll
+                for (int j = 0; j < E; ++j) dst[W::out_k(t, j)] = v[W::out_reg(j)];
             }
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3: inverse row transforms + per-line maxima.  A line is (P row y, Q row y) with the mirror
-// term, else (P row y, P row y+1).  GT holds the CONJUGATE of the column-stage output in
-// 4-column blocks [blk][y][4], so a lane group reads whole 32-byte sectors straight into
-// registers; the Hermitian extension below builds conj(Z) and the forward transform returns
-// conj(surface): C = Re, mirror = -Im (only |.| is used), second row = -Im.
-// Only the per-line maxima are reduced here; the finalize kernel locates x inside the winning
-// row (np.argmax order: lowest row, then lowest x).  Warps are independent: grid-stride over lines.
+// K3: inverse row transforms + per-line maxima, row-batched.  A line is (P row y, Q row y) with
+// the mirror term, else (P row y, P row y+1).  The CTA (256 threads) owns R = 256 / T consecutive
+// lines.  Stage A: thread (t, r) -- r minor, so a lane group reads R consecutive y of one GT
+// column, contiguous -- assembles conj(Z)[n1 T + t] of line r from the (conjugated) P / Q
+// columns by Hermitian extension, radix-E in registers, twiddles, writes X[k1][t][r].
+// Stage B: thread (k1, r) reads X[k1][.][r], radix-T, reduces maxima per line.
+// The forward transform of conj(Z) is conj(surface): C = Re, mirror = -Im (|.| only), second
+// row = -Im.  Only per-line maxima are produced; the finalize kernel locates x inside the
+// winning row (np.argmax order: lowest row, then lowest x).
 // ---------------------------------------------------------------------------------------------
-template <int E, int T, int NW>
+template <int E, int T>
 __device__ void kfast_rows_inverse(const FastParams& fp, unsigned char* smem)
 {
-    using W = WarpFFT<E, T>;
-    constexpr int N = W::N, LPW = W::LPW, RS = W::RS, NT = 32 * NW;
+    constexpr int N = E * T, R = 256 / T, M = E / T;
+    constexpr int XS = T * R + (R == 8 ? 8 : 0);              // k1 stride of the exchange tile
     const XcParams& p = fp.x;
-    cx<float>* regions = reinterpret_cast<cx<float>*>(smem);
-    cx<float>* tw = regions + NW * LPW * RS;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int t = lane % T, lw = lane / T;
-    for (int i = tid; i < N; i += NT) tw[i] = fp.twx[i];
-    __syncthreads();
+    cx<float>* X = reinterpret_cast<cx<float>*>(smem);
+    cx<float>* tw = X + E * XS;
+    float* red = reinterpret_cast<float*>(tw + N);            // [8 warps][R][2] floats + doubles after
+    double* redd = reinterpret_cast<double*>(red + 8 * R * 2);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int r = tid % R, tq = tid / R;                      // stage A: t = tq; stage B: k1 = tq + T m
+    for (int i = tid; i < N; i += 256) tw[i] = fp.twx[i];
     const bool mirror = p.conf_mode == CONF_MIRROR, want_std = p.conf_mode == CONF_STD;
-    const int ny = p.ny;
+    const int ny = p.ny, kp = p.kp;
     const int lines_pp = mirror ? ny : (ny + 1) / 2;          // lines per pair
-    const long long total = (long long)p.n * lines_pp;
-    cx<float>* region = regions + (warp * LPW + lw) * RS;
-    const size_t plane = (size_t)fp.nblk * ny * 4;            // elements per P / Q plane
-    const size_t bstride = (size_t)ny * 4;                    // elements per 4-column block
-    // warp-uniform trip count: the T-lane groups of a warp walk neighbouring lines
-    const long long first = ((long long)blockIdx.x * NW + warp) * LPW;
-    const long long step = (long long)gridDim.x * NW * LPW;
-    for (long long base = first; base < total; base += step) {
-        const long long lid = base + lw;
-        const bool live = lid < total;
-        const int pair = (int)((live ? lid : 0) / lines_pp), gl = (int)((live ? lid : 0) - (long long)pair * lines_pp);
+    const int tiles = (lines_pp + R - 1) / R;
+    const size_t plane = (size_t)kp * ny;
+    for (int work = blockIdx.x; work < p.n * tiles; work += gridDim.x) {
+        const int pair = work / tiles, tile = work - pair * tiles;
+        const int gl = tile * R + r;                           // line index inside the pair
+        const bool live = gl < lines_pp;
         const int y0 = mirror ? gl : 2 * gl;
-        const bool have2 = mirror || (y0 + 1 < ny);
-        const cx<float>* A = fp.GT + (size_t)pair * 2 * plane + (size_t)y0 * 4;           // first half of the line
-        const cx<float>* B = mirror ? A + plane : A + 4;                                   // second half
-        const float h2 = have2 ? 1.f : 0.f;
-        if (!have2) B = A;
-        cx<float> v[E];
+        const bool have2 = live && (mirror || (y0 + 1 < ny));
+        const float h1 = live ? 1.f : 0.f, h2 = have2 ? 1.f : 0.f;
+        const cx<float>* A = fp.GT + (size_t)pair * 2 * plane + (live ? y0 : 0);
+        const cx<float>* B = have2 ? (mirror ? A + plane : A + 1) : A;
+        __syncthreads();                                       // X free (and tw visible)
+        {
+            const int t = tq;
+            cx<float> v[E];
 #pragma unroll
-        for (int n1 = 0; n1 < E; ++n1) {
-            const int k = n1 * T + t;
-            cx<float> z;
-            if (n1 < E / 2 || (n1 == E / 2 && t == 0)) {
-                const size_t off = (size_t)(k >> 2) * bstride + (k & 3);
-                const cx<float> a = ldg(A + off);
-                cx<float> b = ldg(B + off);
-                b = mk<float>(b.x * h2, b.y * h2);
-                // conj(P + iQ) with stored a = conj(P), b = conj(Q):  a - i b
-                z = (k == 0 || 2 * k == N) ? mk<float>(a.x, -b.x) : mk<float>(a.x + b.y, a.y - b.x);
-            } else {
-                const int m = N - k;
-                const size_t off = (size_t)(m >> 2) * bstride + (m & 3);
-                const cx<float> a = ldg(A + off);
-                cx<float> b = ldg(B + off);
-                b = mk<float>(b.x * h2, b.y * h2);
-                // conj(conj(P) + i conj(Q)) = P - i Q = conj(a) - i conj(b)
-                z = mk<float>(a.x - b.y, -a.y - b.x);
+            for (int n1 = 0; n1 < E; ++n1) {
+                const int k = n1 * T + t;
+                cx<float> z;
+                if (n1 < E / 2 || (n1 == E / 2 && t == 0)) {
+                    cx<float> a = ldg(A + (size_t)k * ny), b = ldg(B + (size_t)k * ny);
+                    a = mk<float>(a.x * h1, a.y * h1); b = mk<float>(b.x * h2, b.y * h2);
+                    // conj(P + iQ) with stored a = conj(P), b = conj(Q):  a - i b
+                    z = (k == 0 || 2 * k == N) ? mk<float>(a.x, -b.x) : mk<float>(a.x + b.y, a.y - b.x);
+                } else {
+                    const int m = N - k;
+                    cx<float> a = ldg(A + (size_t)m * ny), b = ldg(B + (size_t)m * ny);
+                    a = mk<float>(a.x * h1, a.y * h1); b = mk<float>(b.x * h2, b.y * h2);
+                    // conj(conj(P) + i conj(Q)) = P - i Q = conj(a) - i conj(b)
+                    z = mk<float>(a.x - b.y, -a.y - b.x);
+                }
+                v[n1] = z;
             }
-            v[n1] = z;
+            RegFFT<float, E, false>::run(v);
+#pragma unroll
+            for (int k1 = 0; k1 < E; ++k1) {
+                cx<float> a = v[brev<E>(k1)];
+                if (k1) a = cmul(a, tw[k1 * T + t]);
+                X[k1 * XS + t * R + r] = a;
+            }
         }
-        W::template run<false>(v, region, tw, t);
-        // out = conj(surface line): Re -> first row, -Im -> mirror surface / second row
-        float best = v[0].x, second = mirror ? fabsf(v[0].y) : -v[0].y;
+        __syncthreads();
+        float best, second;
         double sum = 0.0, sumsq = 0.0;
+        {
+            cx<float> u[E];
 #pragma unroll
-        for (int j = 1; j < E; ++j) {
-            best = fmaxf(best, v[j].x);
-            second = fmaxf(second, mirror ? fabsf(v[j].y) : -v[j].y);
-        }
-        if (want_std) {
+            for (int m = 0; m < M; ++m) {
+                const int k1 = tq + T * m;
 #pragma unroll
-            for (int j = 0; j < E; ++j) {
-                sum += (double)v[j].x; sumsq += (double)v[j].x * (double)v[j].x;
-                if (have2 && !mirror) { sum -= (double)v[j].y; sumsq += (double)v[j].y * (double)v[j].y; }
+                for (int n2 = 0; n2 < T; ++n2) u[m * T + n2] = X[k1 * XS + n2 * R + r];
+            }
+#pragma unroll
+            for (int m = 0; m < M; ++m) RegFFT<float, T, false>::run(u + m * T);
+            best = u[0].x; second = mirror ? fabsf(u[0].y) : -u[0].y;
+#pragma unroll
+            for (int j = 1; j < E; ++j) {
+                best = fmaxf(best, u[j].x);
+                second = fmaxf(second, mirror ? fabsf(u[j].y) : -u[j].y);
+            }
+            if (want_std) {
+#pragma unroll
+                for (int j = 0; j < E; ++j) {
+                    sum += (double)u[j].x; sumsq += (double)u[j].x * (double)u[j].x;
+                    if (have2 && !mirror) { sum -= (double)u[j].y; sumsq += (double)u[j].y * (double)u[j].y; }
+                }
             }
         }
+        // lanes with equal r inside the warp, then the 8 warps through shared memory
 #pragma unroll
-        for (int off = T / 2; off > 0; off >>= 1) {
+        for (int off = R; off < 32; off <<= 1) {
             best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, off));
             second = fmaxf(second, __shfl_xor_sync(0xffffffffu, second, off));
             if (want_std) {
@@ -329,7 +331,16 @@ __device__ void kfast_rows_inverse(const FastParams& fp, unsigned char* smem)
                 sumsq += __shfl_xor_sync(0xffffffffu, sumsq, off);
             }
         }
-        if (t == 0 && live) {
+        if ((tid & 31) < R) {
+            red[(warp * R + r) * 2] = best; red[(warp * R + r) * 2 + 1] = second;
+            if (want_std) { redd[(warp * R + r) * 2] = sum; redd[(warp * R + r) * 2 + 1] = sumsq; }
+        }
+        __syncthreads();
+        if (tid < R && live) {
+            for (int w = 1; w < 8; ++w) {
+                best = fmaxf(best, red[(w * R + r) * 2]); second = fmaxf(second, red[(w * R + r) * 2 + 1]);
+                if (want_std) { sum += redd[(w * R + r) * 2]; sumsq += redd[(w * R + r) * 2 + 1]; }
+            }
             // idx = first flat index of the row that holds the maximum; x is resolved by the finalize kernel
             int row = y0;
             float mir = 0.f;
