@@ -1,0 +1,444 @@
+// fb_image.cu -- the image operators either side of the FFT matcher, on device pointers:
+//
+//   fb_masked_dog        common.masked_dog_filter            feabas/common.py:353-377
+//   fb_resize_area       cv2.resize(INTER_AREA), factor 1/k  feabas/matcher.py:254-256
+//   fb_resize_nearest    cv2.resize(INTER_NEAREST) of masks  feabas/matcher.py:257-264
+//   fb_crop_blocks       MeshRenderer.crop_multiple for affine block maps
+//                        feabas/renderer.py:419-450,601-648 -> feabas/common.py:256-350 (cv2.remap)
+//   fb_stack_minmax      np.ptp per image / per stack         feabas/matcher.py:196,205; common.py:369
+//
+// All of them are HBM-bound pixel kernels; arithmetic follows the reference's rounding where the
+// header says so (float64 accumulation of scipy.ndimage.correlate1d, OpenCV's fixed-point tables).
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include <vector>
+
+#include "../../include/feabas_cuda.h"
+#include "fb_common.h"
+
+namespace {
+
+constexpr int kMaxRadius = 40;     // sigma <= 10 at truncate = 4
+constexpr int kTH = 32, kTW = 64, kNT = 256;
+
+struct Taps {
+    int radius;
+    double w[kMaxRadius + 1];      // w[j] = weight at offset +-(radius - j); w[radius] = centre
+};
+
+// scipy.ndimage._filters._gaussian_kernel1d (order 0), radius = int(truncate * sigma + 0.5), truncate = 4
+bool make_taps(double sigma, Taps& t)
+{
+    int r = (int)(4.0 * sigma + 0.5);
+    if (r < 0 || r > kMaxRadius || !(sigma > 0)) return false;
+    std::vector<double> phi(2 * r + 1);
+    const double s2 = sigma * sigma;
+    double sum = 0;
+    for (int x = -r; x <= r; ++x) { phi[x + r] = exp(-0.5 / s2 * (double)(x * x)); }
+    for (double v : phi) sum += v;
+    t.radius = r;
+    for (int j = 0; j <= r; ++j) t.w[j] = phi[j] / sum;
+    return true;
+}
+
+enum { MODE_BLUR = 0, MODE_DOG = 1, MODE_MASK = 2 };
+
+struct GaussParams {
+    const void* src;       // BLUR: image (TS); DOG: first blur (float); MASK: mask bytes (nonzero = keep)
+    float* dst;            // BLUR: blur; DOG: blur - blur(blur); MASK: in-place mask suppression of dst
+    int n, h, w;
+    long long src_stride;  // elements between consecutive images of src (0: one mask for all)
+    const float* span;     // MASK: device pointer to {min, max} of the image stack, or null
+    float span_value;      //       used when span == null
+    float sc2, s02;        // MASK: sigma_c^2, sigma^2 as float32 (common.py:371)
+    int take_abs;          // unsigned output
+    Taps taps;
+};
+
+template <typename ACC> struct Sym;
+template <> struct Sym<double> {
+    // scipy ni_filters.c, symmetric branch: tmp = centre * w; tmp += (x[-i] + x[i]) * w[i] from the outside in,
+    // without contraction (the reference build has no FMA)
+    static __device__ __forceinline__ double init(float c, double w) { return __dmul_rn((double)c, w); }
+    static __device__ __forceinline__ double step(double acc, float a, float b, double w)
+    {
+        return __dadd_rn(acc, __dmul_rn(__dadd_rn((double)a, (double)b), w));
+    }
+};
+template <> struct Sym<float> {
+    static __device__ __forceinline__ float init(float c, double w) { return c * (float)w; }
+    static __device__ __forceinline__ float step(float acc, float a, float b, double w) { return fmaf(a + b, (float)w, acc); }
+};
+
+template <typename TS, int MODE> __device__ __forceinline__ float load_src(const GaussParams& p, const TS* base, int y, int x, float span)
+{
+    y = min(max(y, 0), p.h - 1);                   // mode='nearest'
+    x = min(max(x, 0), p.w - 1);
+    const TS v = __ldg(base + (size_t)y * p.w + x);
+    if (MODE == MODE_MASK) return v ? 0.f : span;  // np.ptp(img) * (mask == 0)
+    return (float)v;
+}
+
+// One separable Gaussian (row pass, float32 rounding, column pass) of a kTH x kTW output tile.
+template <typename TS, int MODE, typename ACC>
+__global__ void __launch_bounds__(kNT) fbk_gauss2d(const __grid_constant__ GaussParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int r = p.taps.radius;
+    const int in_w = kTW + 2 * r, in_h = kTH + 2 * r;
+    const int in_pitch = in_w | 1;
+    float* s_in = reinterpret_cast<float*>(smem_raw);             // [in_h][in_pitch]
+    float* s_row = s_in + (size_t)in_h * in_pitch;                // [in_h][kTW]
+    const int img = blockIdx.z, x0 = blockIdx.x * kTW, y0 = blockIdx.y * kTH, tid = threadIdx.x;
+    const TS* base = reinterpret_cast<const TS*>(p.src) + (size_t)img * p.src_stride;
+    float span = 0.f;
+    if (MODE == MODE_MASK) span = p.span ? (p.span[1] - p.span[0]) : p.span_value;
+    for (int i = tid; i < in_h * in_w; i += kNT) {
+        const int yy = i / in_w, xx = i - yy * in_w;
+        s_in[yy * in_pitch + xx] = load_src<TS, MODE>(p, base, y0 + yy - r, x0 + xx - r, span);
+    }
+    __syncthreads();
+    for (int i = tid; i < in_h * kTW; i += kNT) {
+        const int yy = i / kTW, xx = i - yy * kTW;
+        const float* c = s_in + yy * in_pitch + xx + r;
+        ACC acc = Sym<ACC>::init(c[0], p.taps.w[r]);
+        for (int j = 0; j < r; ++j) acc = Sym<ACC>::step(acc, c[j - r], c[r - j], p.taps.w[j]);
+        s_row[yy * kTW + xx] = (float)acc;
+    }
+    __syncthreads();
+    for (int i = tid; i < kTH * kTW; i += kNT) {
+        const int yy = i / kTW, xx = i - yy * kTW;
+        const int y = y0 + yy, x = x0 + xx;
+        if (y >= p.h || x >= p.w) continue;
+        const float* c = s_row + (yy + r) * kTW + xx;
+        ACC acc = Sym<ACC>::init(c[0], p.taps.w[r]);
+        for (int j = 0; j < r; ++j) acc = Sym<ACC>::step(acc, c[(j - r) * kTW], c[(r - j) * kTW], p.taps.w[j]);
+        const float g = (float)acc;
+        float* o = p.dst + ((size_t)img * p.h + y) * p.w + x;
+        if (MODE == MODE_BLUR) {
+            *o = g;
+        } else if (MODE == MODE_DOG) {
+            float f = __fsub_rn(s_in[(yy + r) * in_pitch + xx + r], g);     // img0f - img1f
+            *o = p.take_abs ? fabsf(f) : f;
+        } else {
+            const float mf = __fdiv_rn(__fmul_rn(g, p.sc2), p.s02);
+            const float f = *o;
+            float a = fmaxf(__fsub_rn(fabsf(f), mf), 0.f);
+            if (!p.take_abs) a = f > 0.f ? a : (f < 0.f ? -a : __fmul_rn(a, 0.f));
+            *o = a;
+        }
+    }
+}
+
+// per-image {min, max}; one CTA per image
+template <typename TS>
+__global__ void __launch_bounds__(512) fbk_minmax(const TS* src, long long elems, float* out)
+{
+    __shared__ float s_lo[16], s_hi[16];
+    const TS* base = src + (size_t)blockIdx.x * elems;
+    float lo = INFINITY, hi = -INFINITY;
+    for (long long i = threadIdx.x; i < elems; i += 512) {
+        const float v = (float)__ldg(base + i);
+        lo = fminf(lo, v); hi = fmaxf(hi, v);
+    }
+    for (int off = 16; off; off >>= 1) {
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, off));
+        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, off));
+    }
+    if ((threadIdx.x & 31) == 0) { s_lo[threadIdx.x >> 5] = lo; s_hi[threadIdx.x >> 5] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 16; ++i) { lo = fminf(lo, s_lo[i]); hi = fmaxf(hi, s_hi[i]); }
+        out[2 * blockIdx.x] = lo; out[2 * blockIdx.x + 1] = hi;
+    }
+}
+
+// {min, max} over rows of a [n][2] table -> out[0..1]
+__global__ void fbk_minmax_fold(const float* table, int n, float* out)
+{
+    float lo = INFINITY, hi = -INFINITY;
+    for (int i = threadIdx.x; i < n; i += 32) { lo = fminf(lo, table[2 * i]); hi = fmaxf(hi, table[2 * i + 1]); }
+    for (int off = 16; off; off >>= 1) {
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, off));
+        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, off));
+    }
+    if (threadIdx.x == 0) { out[0] = lo; out[1] = hi; }
+}
+
+// cv2.resize(INTER_AREA) with fx = fy = 1/k: mean of the k x k cell; cells cut by the border are
+// averaged over the pixels they contain (OpenCV resizeAreaFast_).  uint8: (sum + 2) >> 2 for k = 2,
+// else round-half-even of float(sum) * float(1/k^2) resp. float(sum) / count.
+template <typename TS>
+__global__ void __launch_bounds__(256) fbk_resize_area(const TS* src, int n, int h, int w, int k, int oh, int ow, TS* dst)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, img = blockIdx.z;
+    if (x >= ow) return;
+    const TS* s = src + (size_t)img * h * w;
+    const int ys = y * k, xs = x * k;
+    const int ny = min(k, h - ys), nx = min(k, w - xs);
+    TS out;
+    if (sizeof(TS) == 1) {
+        int sum = 0;
+        for (int j = 0; j < ny; ++j)
+            for (int i = 0; i < nx; ++i) sum += (int)s[(size_t)(ys + j) * w + xs + i];
+        float v;
+        if (ny == k && nx == k) {
+            if (k == 2) { dst[((size_t)img * oh + y) * ow + x] = (TS)((sum + 2) >> 2); return; }
+            v = __fmul_rn((float)sum, 1.f / (float)(k * k));
+        } else if (ny <= 0 || nx <= 0) {
+            v = 0.f;
+        } else {
+            v = __fdiv_rn((float)sum, (float)(ny * nx));
+        }
+        int q = __float2int_rn(v);
+        out = (TS)(q < 0 ? 0 : (q > 255 ? 255 : q));
+    } else {
+        float sum = 0.f;
+        for (int j = 0; j < ny; ++j)
+            for (int i = 0; i < nx; ++i) sum = __fadd_rn(sum, (float)s[(size_t)(ys + j) * w + xs + i]);
+        if (ny == k && nx == k) out = (TS)__fmul_rn(sum, 1.f / (float)(k * k));
+        else out = (TS)((ny <= 0 || nx <= 0) ? 0.f : __fdiv_rn(sum, (float)(ny * nx)));
+    }
+    dst[((size_t)img * oh + y) * ow + x] = out;
+}
+
+// cv2.resize(INTER_NEAREST): dst(y, x) = src(min(floor(y * ify), h - 1), min(floor(x * ifx), w - 1))
+__global__ void __launch_bounds__(256) fbk_resize_nearest(const unsigned char* src, int n, int h, int w, double ify, double ifx,
+                                                          int oh, int ow, unsigned char* dst)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, img = blockIdx.z;
+    if (x >= ow) return;
+    const int sy = min((int)floor(y * ify), h - 1), sx = min((int)floor(x * ifx), w - 1);
+    dst[((size_t)img * oh + y) * ow + x] = src[((size_t)img * h + sy) * w + sx];
+}
+
+struct CropParams {
+    const void* img;
+    int ih, iw;
+    const double* blocks;  // [n][10]: x0, y0, step_x, step_y, A00, A10, t0, A01, A11, t1
+    int n, bh, bw;
+    double ox, oy;         // integer-valued origin of the reference's source crop (common.py:300-304)
+    float fill;
+    void* out;
+    int has_cover;         // only pixels whose source position lies inside [cx0, cx1) x [cy0, cy1) are rendered
+    double cx0, cy0, cx1, cy1;
+    unsigned char* mask_out;
+};
+
+template <typename TS> __device__ __forceinline__ float fetch(const CropParams& p, const TS* img, int y, int x)
+{
+    if ((unsigned)y < (unsigned)p.ih && (unsigned)x < (unsigned)p.iw) return (float)__ldg(img + (size_t)y * p.iw + x);
+    return p.fill;
+}
+
+// renderer.py:419-450 (float64 field), common.py:318-321 (minus origin, float32), cv2.remap INTER_LINEAR:
+// fixed point with 5 fractional bits, float weights for float images, 15-bit integer weights for uint8.
+template <typename TS>
+__global__ void __launch_bounds__(256) fbk_crop_blocks(const __grid_constant__ CropParams p)
+{
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.bh * p.bw) return;
+    const int row = i / p.bw, col = i - row * p.bw;
+    const double* q = p.blocks + (size_t)b * 10;
+    const double xx = __dadd_rn(q[0], __dmul_rn((double)col, q[2]));
+    const double yy = __dadd_rn(q[1], __dmul_rn((double)row, q[3]));
+    const double xs = __dadd_rn(__dadd_rn(__dmul_rn(xx, q[4]), __dmul_rn(yy, q[5])), q[6]);
+    const double ys = __dadd_rn(__dadd_rn(__dmul_rn(xx, q[7]), __dmul_rn(yy, q[8])), q[9]);
+    if (p.has_cover) {
+        const bool inside = xs >= p.cx0 && xs < p.cx1 && ys >= p.cy0 && ys < p.cy1;
+        if (p.mask_out) p.mask_out[((size_t)b * p.bh + row) * p.bw + col] = inside ? 1 : 0;
+        if (!inside) {
+            reinterpret_cast<TS*>(p.out)[((size_t)b * p.bh + row) * p.bw + col] = (TS)p.fill;
+            return;
+        }
+    }
+    const float xf = (float)__dsub_rn(xs, p.ox), yf = (float)__dsub_rn(ys, p.oy);
+    const int fx = __float2int_rn(__fmul_rn(xf, 32.f)), fy = __float2int_rn(__fmul_rn(yf, 32.f));
+    const int ix = (fx >> 5) + (int)p.ox, iy = (fy >> 5) + (int)p.oy;
+    const int ax = fx & 31, ay = fy & 31;
+    const TS* img = reinterpret_cast<const TS*>(p.img);
+    const float v00 = fetch<TS>(p, img, iy, ix), v01 = fetch<TS>(p, img, iy, ix + 1);
+    const float v10 = fetch<TS>(p, img, iy + 1, ix), v11 = fetch<TS>(p, img, iy + 1, ix + 1);
+    TS* out = reinterpret_cast<TS*>(p.out) + ((size_t)b * p.bh + row) * p.bw + col;
+    if (sizeof(TS) == 1) {
+        // weights (32 - a) * (32 - b) * 32 sum to 2^15 exactly
+        const int w00 = (32 - ax) * (32 - ay) * 32, w01 = ax * (32 - ay) * 32, w10 = (32 - ax) * ay * 32, w11 = ax * ay * 32;
+        const int acc = (int)v00 * w00 + (int)v01 * w01 + (int)v10 * w10 + (int)v11 * w11;
+        const int r = (acc + (1 << 14)) >> 15;
+        *out = (TS)(r < 0 ? 0 : (r > 255 ? 255 : r));
+    } else {
+        const float cx1 = (float)ax * (1.f / 32.f), cy1 = (float)ay * (1.f / 32.f);
+        const float cx0 = 1.f - cx1, cy0 = 1.f - cy1;
+        const float w00 = __fmul_rn(cy0, cx0), w01 = __fmul_rn(cy0, cx1), w10 = __fmul_rn(cy1, cx0), w11 = __fmul_rn(cy1, cx1);
+        float acc = __fmul_rn(v00, w00);
+        acc = __fadd_rn(acc, __fmul_rn(v01, w01));
+        acc = __fadd_rn(acc, __fmul_rn(v10, w10));
+        acc = __fadd_rn(acc, __fmul_rn(v11, w11));
+        *out = (TS)acc;
+    }
+}
+
+int check_device(int device)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fb_failf(FB_ECUDA, "no CUDA device available (this library has no CPU fallback)");
+    }
+    if (device < 0 || device >= ndev) return fb_failf(FB_EINVAL, "device %d out of range (%d devices)", device, ndev);
+    FB_CU(cudaSetDevice(device));
+    return FB_OK;
+}
+
+size_t gauss_smem(int r)
+{
+    const int in_w = kTW + 2 * r, in_h = kTH + 2 * r;
+    return ((size_t)in_h * (in_w | 1) + (size_t)in_h * kTW) * sizeof(float);
+}
+
+template <typename TS, int MODE, typename ACC>
+int launch_gauss(const GaussParams& p, cudaStream_t st)
+{
+    const size_t smem = gauss_smem(p.taps.radius);
+    FB_CU(cudaFuncSetAttribute(fbk_gauss2d<TS, MODE, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((p.w + kTW - 1) / kTW, (p.h + kTH - 1) / kTH, p.n);
+    fbk_gauss2d<TS, MODE, ACC><<<grid, kNT, smem, st>>>(p);
+    fb_count_launches(1);
+    FB_CU(cudaGetLastError());
+    return FB_OK;
+}
+
+template <typename TS, int MODE>
+int launch_gauss_acc(const GaussParams& p, bool exact, cudaStream_t st)
+{
+    return exact ? launch_gauss<TS, MODE, double>(p, st) : launch_gauss<TS, MODE, float>(p, st);
+}
+
+}  // namespace
+
+extern "C" long long fb_masked_dog_workspace(int n, int h, int w)
+{
+    if (n < 0 || h < 1 || w < 1) return 0;
+    return (long long)n * h * w * (long long)sizeof(float) + (long long)(n + 1) * 2 * sizeof(float) + 256;
+}
+
+extern "C" int fb_masked_dog(const void* img, const unsigned char* mask, int n, int h, int w, int in_dtype, int mask_n,
+                             double sigma, double ptp, int flags, float* out, void* work, long long work_bytes,
+                             int device, void* stream)
+{
+    if (n < 0 || h < 1 || w < 1) return fb_failf(FB_EINVAL, "bad shape n=%d %dx%d", n, h, w);
+    if (in_dtype != FB_F32 && in_dtype != FB_U8) return fb_failf(FB_EINVAL, "masked_dog: dtype %d not supported (float32 / uint8)", in_dtype);
+    if (mask && mask_n != 1 && mask_n != n) return fb_failf(FB_EINVAL, "mask_n must be 1 or n");
+    if (n == 0) return FB_OK;
+    if (!img || !out || !work) return fb_failf(FB_EINVAL, "null pointer");
+    if (work_bytes < fb_masked_dog_workspace(n, h, w)) return fb_failf(FB_EINVAL, "workspace too small (%lld < %lld)", work_bytes, fb_masked_dog_workspace(n, h, w));
+    GaussParams p{};
+    if (!make_taps(sigma, p.taps)) return fb_failf(FB_ESIZE, "sigma %g outside (0, %g]", sigma, (kMaxRadius + 0.49) / 4.0);
+    int rc = check_device(device);
+    if (rc != FB_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool exact = flags & FB_DOG_EXACT;
+    float* blur = reinterpret_cast<float*>(work);
+    float* table = blur + (size_t)n * h * w;                      // [n][2] + [2]
+    p.n = n; p.h = h; p.w = w; p.src_stride = (long long)h * w;
+    // first blur
+    p.src = img; p.dst = blur;
+    rc = in_dtype == FB_F32 ? launch_gauss_acc<float, MODE_BLUR>(p, exact, st) : launch_gauss_acc<unsigned char, MODE_BLUR>(p, exact, st);
+    if (rc != FB_OK) return rc;
+    // second blur and difference
+    p.src = blur; p.dst = out; p.take_abs = (!mask && (flags & FB_DOG_UNSIGNED)) ? 1 : 0;
+    rc = launch_gauss_acc<float, MODE_DOG>(p, exact, st);
+    if (rc != FB_OK || !mask) return rc;
+    // suppression of the signal bleeding in from outside the mask
+    if (ptp != ptp) {
+        if (in_dtype == FB_F32) fbk_minmax<float><<<n, 512, 0, st>>>(reinterpret_cast<const float*>(img), (long long)h * w, table);
+        else fbk_minmax<unsigned char><<<n, 512, 0, st>>>(reinterpret_cast<const unsigned char*>(img), (long long)h * w, table);
+        fbk_minmax_fold<<<1, 32, 0, st>>>(table, n, table + 2 * (size_t)n);
+        fb_count_launches(2);
+        p.span = table + 2 * (size_t)n;
+    } else {
+        p.span = nullptr; p.span_value = (float)ptp;
+    }
+    const double sigma_c = sqrt(sigma * sigma + sigma * sigma);
+    if (!make_taps(sigma_c, p.taps)) return fb_failf(FB_ESIZE, "sigma %g too large for the mask term", sigma);
+    p.sc2 = (float)(sigma_c * sigma_c); p.s02 = (float)(sigma * sigma);
+    p.src = mask; p.dst = out; p.src_stride = mask_n == 1 ? 0 : (long long)h * w; p.take_abs = (flags & FB_DOG_UNSIGNED) ? 1 : 0;
+    return launch_gauss_acc<unsigned char, MODE_MASK>(p, exact, st);
+}
+
+extern "C" int fb_stack_minmax(const void* stack, int n, long long elems, int in_dtype, float* minmax, int device, void* stream)
+{
+    if (n < 0 || elems < 1) return fb_failf(FB_EINVAL, "bad shape");
+    if (in_dtype != FB_F32 && in_dtype != FB_U8) return fb_failf(FB_EINVAL, "stack_minmax: dtype %d not supported", in_dtype);
+    if (n == 0) return FB_OK;
+    if (!stack || !minmax) return fb_failf(FB_EINVAL, "null pointer");
+    int rc = check_device(device);
+    if (rc != FB_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (in_dtype == FB_F32) fbk_minmax<float><<<n, 512, 0, st>>>(reinterpret_cast<const float*>(stack), elems, minmax);
+    else fbk_minmax<unsigned char><<<n, 512, 0, st>>>(reinterpret_cast<const unsigned char*>(stack), elems, minmax);
+    fb_count_launches(1);
+    FB_CU(cudaGetLastError());
+    return FB_OK;
+}
+
+extern "C" int fb_resize_area(const void* src, int n, int h, int w, int in_dtype, int k, void* dst, int oh, int ow,
+                              int device, void* stream)
+{
+    if (n < 0 || h < 1 || w < 1 || k < 1 || oh < 1 || ow < 1) return fb_failf(FB_EINVAL, "bad shape");
+    if (in_dtype != FB_F32 && in_dtype != FB_U8) return fb_failf(FB_EINVAL, "resize_area: dtype %d not supported", in_dtype);
+    if ((long long)(oh - 1) * k >= h || (long long)(ow - 1) * k >= w) return fb_failf(FB_EINVAL, "output %dx%d too large for %dx%d / %d", oh, ow, h, w, k);
+    if (n == 0) return FB_OK;
+    if (!src || !dst) return fb_failf(FB_EINVAL, "null pointer");
+    int rc = check_device(device);
+    if (rc != FB_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid((ow + 255) / 256, oh, n);
+    if (in_dtype == FB_F32) fbk_resize_area<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(src), n, h, w, k, oh, ow, reinterpret_cast<float*>(dst));
+    else fbk_resize_area<unsigned char><<<grid, 256, 0, st>>>(reinterpret_cast<const unsigned char*>(src), n, h, w, k, oh, ow, reinterpret_cast<unsigned char*>(dst));
+    fb_count_launches(1);
+    FB_CU(cudaGetLastError());
+    return FB_OK;
+}
+
+extern "C" int fb_resize_nearest(const unsigned char* src, int n, int h, int w, double inv_fy, double inv_fx,
+                                 unsigned char* dst, int oh, int ow, int device, void* stream)
+{
+    if (n < 0 || h < 1 || w < 1 || oh < 1 || ow < 1 || !(inv_fx > 0) || !(inv_fy > 0)) return fb_failf(FB_EINVAL, "bad shape");
+    if (n == 0) return FB_OK;
+    if (!src || !dst) return fb_failf(FB_EINVAL, "null pointer");
+    int rc = check_device(device);
+    if (rc != FB_OK) return rc;
+    dim3 grid((ow + 255) / 256, oh, n);
+    fbk_resize_nearest<<<grid, 256, 0, (cudaStream_t)stream>>>(src, n, h, w, inv_fy, inv_fx, oh, ow, dst);
+    fb_count_launches(1);
+    FB_CU(cudaGetLastError());
+    return FB_OK;
+}
+
+extern "C" int fb_crop_blocks(const void* img, int ih, int iw, int in_dtype, const double* blocks, int n, int bh, int bw,
+                              double origin_x, double origin_y, double fillval, void* out,
+                              const double* cover, unsigned char* mask_out, int device, void* stream)
+{
+    if (n < 0 || ih < 1 || iw < 1 || bh < 1 || bw < 1) return fb_failf(FB_EINVAL, "bad shape");
+    if (in_dtype != FB_F32 && in_dtype != FB_U8) return fb_failf(FB_EINVAL, "crop_blocks: dtype %d not supported", in_dtype);
+    if (n > 65535) return fb_failf(FB_EINVAL, "at most 65535 blocks per call");
+    if (n == 0) return FB_OK;
+    if (!img || !blocks || !out) return fb_failf(FB_EINVAL, "null pointer");
+    int rc = check_device(device);
+    if (rc != FB_OK) return rc;
+    CropParams p{};
+    p.img = img; p.ih = ih; p.iw = iw; p.blocks = blocks; p.n = n; p.bh = bh; p.bw = bw;
+    p.ox = origin_x; p.oy = origin_y; p.out = out;
+    p.has_cover = cover ? 1 : 0; p.mask_out = cover ? mask_out : nullptr;
+    if (cover) { p.cx0 = cover[0]; p.cy0 = cover[1]; p.cx1 = cover[2]; p.cy1 = cover[3]; }
+    p.fill = in_dtype == FB_U8 ? (float)(fillval < 0 ? 0 : (fillval > 255 ? 255 : rint(fillval))) : (float)fillval;
+    dim3 grid((bh * bw + 255) / 256, n);
+    if (in_dtype == FB_F32) fbk_crop_blocks<float><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+    else fbk_crop_blocks<unsigned char><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+    fb_count_launches(1);
+    FB_CU(cudaGetLastError());
+    return FB_OK;
+}

@@ -38,6 +38,10 @@ static int fail(int code, const char* fmt, ...)
     return code;
 }
 
+// shared with the other translation units of the library (fb_common.h)
+int fb_set_error(int code, const char* msg) { g_err = msg; return code; }
+void fb_count_launches(int n) { g_launches += n; }
+
 #define CU(call)                                                                                  \
     do {                                                                                          \
         cudaError_t e_ = (call);                                                                  \

@@ -19,6 +19,8 @@ FB_FLAG_FORCE_STAGED = 0x10
 FB_FLAG_FORCE_FUSED = 0x20
 FB_FLAG_U8_AS_F32 = 0x40
 FB_FLAG_FORCE_GENERIC = 0x80
+FB_DOG_UNSIGNED = 0x1
+FB_DOG_EXACT = 0x2
 
 _vp, _i, _ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong
 _XCORR_ARGS = [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]
@@ -28,6 +30,12 @@ SYMBOLS = {
     'fb_xcorr_batch_device': (_i, _XCORR_ARGS),
     'fb_xcorr_batch_host': (_i, _XCORR_ARGS),
     'fb_xcorr_batch': (_i, _XCORR_ARGS),
+    'fb_masked_dog_workspace': (_ll, [_i, _i, _i]),
+    'fb_masked_dog': (_i, [_vp, _vp, _i, _i, _i, _i, _i, ctypes.c_double, ctypes.c_double, _i, _vp, _vp, _ll, _i, _vp]),
+    'fb_stack_minmax': (_i, [_vp, _i, _ll, _i, _vp, _i, _vp]),
+    'fb_resize_area': (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp]),
+    'fb_resize_nearest': (_i, [_vp, _i, _i, _i, ctypes.c_double, ctypes.c_double, _vp, _i, _i, _i, _vp]),
+    'fb_crop_blocks': (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, ctypes.c_double, ctypes.c_double, ctypes.c_double, _vp, _vp, _vp, _i, _vp]),
     'fb_next_fast_len': (_i, [_i]),
     'fb_xcorr_plan_info': (_i, [_i, _i, _i, _i, _i, _i, _i, _i, ctypes.POINTER(_ll)]),
     'fb_set_option': (_i, [ctypes.c_char_p, _ll]),

@@ -1,0 +1,217 @@
+"""Device image operators around the matcher, with the reference's call conventions.
+
+* ``masked_dog_filter``   feabas/common.py:353-377
+* ``resize_area``         ``cv2.resize(img, None, fx=f, fy=f, interpolation=cv2.INTER_AREA)``, f = 1/k
+                          (feabas/matcher.py:254-256)
+* ``resize_mask``         ``cv2.resize(mask.astype(uint8), ..., INTER_NEAREST).astype(bool)`` (matcher.py:257-264)
+* ``crop_blocks``         affine block gather (feabas/renderer.py:419-450,601-648; feabas/common.py:256-350)
+
+NumPy in -> NumPy out (host arrays are uploaded, results downloaded); CUDA tensor in -> CUDA
+tensor out on the current stream, nothing synchronised.  torch only provides memory and streams.
+"""
+import math
+
+import numpy as np
+
+from . import _lib
+
+try:
+    import torch
+except Exception:                       # pragma: no cover
+    torch = None
+
+
+def _need_torch():
+    if torch is None:
+        raise _lib.FeabasCudaError('feabas_b200.cuda needs torch for device memory')
+
+
+def is_cuda_tensor(x):
+    return torch is not None and isinstance(x, torch.Tensor) and x.is_cuda
+
+
+def to_device(x, device=None, dtype=None):
+    """numpy array / CPU tensor / CUDA tensor -> contiguous CUDA tensor (no copy if already there)."""
+    _need_torch()
+    if not torch.cuda.is_available():
+        _lib.lib()                                             # a missing .so is reported first
+        raise _lib.FeabasCudaError('no CUDA device available (feabas_b200 has no CPU fallback)')
+    if isinstance(x, torch.Tensor):
+        t = x
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(x))
+    if not t.is_cuda:
+        dev = torch.device('cuda', torch.cuda.current_device() if device is None else int(device))
+        t = t.to(dev, non_blocking=True)
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+def _code(t):
+    if t.dtype == torch.float32:
+        return _lib.FB_F32
+    if t.dtype == torch.uint8:
+        return _lib.FB_U8
+    raise TypeError(f'unsupported image dtype {t.dtype} (float32 / uint8)')
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def stack_minmax(stack):
+    """Per-image (min, max) of an ``N x ...`` CUDA tensor -> ``N x 2`` float32 CUDA tensor."""
+    n = stack.shape[0]
+    out = torch.empty((n, 2), dtype=torch.float32, device=stack.device)
+    if n:
+        _lib.check(_lib.lib().fb_stack_minmax(stack.data_ptr(), n, stack[0].numel(), _code(stack), out.data_ptr(),
+                                              stack.device.index, _stream(stack)))
+    return out
+
+
+def masked_dog_device(img, sigma, mask=None, signed=True, ptp=None, exact=False, out=None):
+    """``img``: CUDA tensor ``(..., H, W)`` float32 or uint8; ``mask``: None or CUDA tensor broadcastable to
+    ``img`` (nonzero = keep) that is known NOT to be all true.  Returns float32, same shape."""
+    shape = img.shape
+    h, w = shape[-2:]
+    n = int(np.prod(shape[:-2])) if len(shape) > 2 else 1
+    img = img.contiguous()
+    if img.dtype not in (torch.float32, torch.uint8):
+        # common.py:363-364: every non-floating dtype is converted to float32
+        if img.dtype.is_floating_point:
+            raise NotImplementedError('masked_dog_filter on %s images is not implemented (float32 / integer)' % img.dtype)
+        img = img.to(torch.float32)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.float32, device=img.device)
+    mask_n, mptr = 1, None
+    if mask is not None:
+        m = mask
+        if m.dtype != torch.uint8:
+            m = (m != 0).to(torch.uint8)
+        if m.dim() > 2 and int(np.prod(m.shape[:-2])) > 1:
+            m = m.expand(shape).contiguous()
+            mask_n = n
+        else:
+            m = m.reshape(h, w).contiguous()
+        mptr = m.data_ptr()
+    L = _lib.lib()
+    wb = L.fb_masked_dog_workspace(n, h, w)
+    work = torch.empty(wb, dtype=torch.uint8, device=img.device)
+    flags = (0 if signed else _lib.FB_DOG_UNSIGNED) | (_lib.FB_DOG_EXACT if exact else 0)
+    _lib.check(L.fb_masked_dog(img.data_ptr(), mptr, n, h, w, _code(img), mask_n, float(sigma),
+                               float('nan') if ptp is None else float(ptp), flags, out.data_ptr(), work.data_ptr(), wb,
+                               img.device.index, _stream(img)))
+    return out
+
+
+def masked_dog_filter(img, sigma, mask=None, signed=True, **kwargs):
+    """Drop-in for ``feabas.common.masked_dog_filter`` (common.py:353-377).
+
+    Extra keyword arguments (not in the reference): ``ptp`` -- the value of ``np.ptp`` the mask term
+    should use (the reference takes it over whatever array it is handed, so a caller that splits a
+    stack across GPUs passes the stack-global value); ``exact`` -- float64 accumulation in scipy's
+    order (reference rounding) instead of float32; ``device``.
+    """
+    ptp = kwargs.get('ptp', None)
+    exact = kwargs.get('exact', False)
+    on_gpu = is_cuda_tensor(img)
+    if mask is not None:
+        # common.py:368: an all-true mask is the same as no mask
+        if bool(mask.all()):
+            mask = None
+    t = to_device(img, kwargs.get('device', None))
+    m = None if mask is None else to_device(mask, t.device.index)
+    out = masked_dog_device(t, sigma, m, signed=signed, ptp=ptp, exact=exact)
+    return out if on_gpu else out.cpu().numpy()
+
+
+def _round_half_even(v):
+    return int(np.rint(v))
+
+
+def resize_area(img, factor, **kwargs):
+    """``cv2.resize(img, None, fx=factor, fy=factor, interpolation=cv2.INTER_AREA)`` for
+    ``factor = 1/k`` (k integer), ``img``: ``(..., H, W)`` uint8 (bit-exact) or float32."""
+    k = int(round(1.0 / factor))
+    if k < 1 or abs(1.0 / factor - k) > 1e-12:
+        raise NotImplementedError(f'INTER_AREA resize only for factors 1/k (got {factor})')
+    on_gpu = is_cuda_tensor(img)
+    t = to_device(img, kwargs.get('device', None))
+    if k == 1:
+        return t.clone() if on_gpu else np.array(img, copy=True)
+    shape = t.shape
+    h, w = shape[-2:]
+    n = int(np.prod(shape[:-2])) if len(shape) > 2 else 1
+    oh, ow = _round_half_even(h * factor), _round_half_even(w * factor)   # cv2: saturate_cast<int>(size * fx)
+    out = torch.empty(tuple(shape[:-2]) + (oh, ow), dtype=t.dtype, device=t.device)
+    _lib.check(_lib.lib().fb_resize_area(t.data_ptr(), n, h, w, _code(t), k, out.data_ptr(), oh, ow, t.device.index, _stream(t)))
+    return out if on_gpu else out.cpu().numpy()
+
+
+def resize_mask(mask, factor, **kwargs):
+    """Nearest-neighbour resize of a boolean mask, OpenCV's index rule."""
+    on_gpu = is_cuda_tensor(mask)
+    t = to_device(mask, kwargs.get('device', None))
+    t = (t != 0).to(torch.uint8).contiguous()
+    shape = t.shape
+    h, w = shape[-2:]
+    n = int(np.prod(shape[:-2])) if len(shape) > 2 else 1
+    oh, ow = _round_half_even(h * factor), _round_half_even(w * factor)
+    out = torch.empty(tuple(shape[:-2]) + (oh, ow), dtype=torch.uint8, device=t.device)
+    _lib.check(_lib.lib().fb_resize_nearest(t.data_ptr(), n, h, w, 1.0 / factor, 1.0 / factor, out.data_ptr(), oh, ow,
+                                            t.device.index, _stream(t)))
+    out = out.to(torch.bool)
+    return out if on_gpu else out.cpu().numpy()
+
+
+def crop_blocks_masked(img, blocks, block_shape, origin=None, fillval=0, cover=None, out=None):
+    """Gather ``len(blocks)`` blocks of ``block_shape = (bh, bw)`` from the 2-D CUDA tensor ``img``.
+
+    ``blocks``: ``N x 10`` float64 (numpy or CUDA): x0, y0, step_x, step_y, A00, A10, t0, A01, A11, t1
+    (see ``fb_crop_blocks`` in include/feabas_cuda.h).  ``origin``: the integer (x, y) origin OpenCV's
+    fixed-point coordinates are taken from; default = what the reference computes for the batch,
+    ``floor(min field) - 4`` (common.py:300-304).  ``cover``: (xmin, ymin, xmax, ymax) of the source region
+    the mesh covers, or None.  Returns ``(stack, mask)``; ``mask`` (uint8, 1 = rendered) is None without cover.
+    """
+    bh, bw = int(block_shape[0]), int(block_shape[1])
+    blk_host = None
+    if not is_cuda_tensor(blocks):
+        blk_host = np.ascontiguousarray(blocks, dtype=np.float64).reshape(-1, 10)
+        blocks = torch.from_numpy(blk_host).to(img.device, non_blocking=True)
+    n = blocks.shape[0]
+    if origin is None:
+        if blk_host is None:
+            blk_host = blocks.cpu().numpy()
+        origin = batch_origin(blk_host, bh, bw) if n else (0, 0)
+    if out is None:
+        out = torch.empty((n, bh, bw), dtype=img.dtype, device=img.device)
+    mask, cptr, mptr = None, None, None
+    if cover is not None:
+        import ctypes
+        carr = (ctypes.c_double * 4)(*[float(v) for v in cover])
+        cptr = ctypes.cast(carr, ctypes.c_void_p)
+        mask = torch.empty((n, bh, bw), dtype=torch.uint8, device=img.device)
+        mptr = mask.data_ptr()
+    if n:
+        ih, iw = img.shape
+        _lib.check(_lib.lib().fb_crop_blocks(img.data_ptr(), ih, iw, _code(img), blocks.data_ptr(), n, bh, bw,
+                                             float(origin[0]), float(origin[1]), float(fillval), out.data_ptr(),
+                                             cptr, mptr, img.device.index, _stream(img)))
+    return out, mask
+
+
+def crop_blocks(img, blocks, block_shape, origin=None, fillval=0, out=None):
+    """``crop_blocks_masked`` without a coverage region; returns the stack only."""
+    return crop_blocks_masked(img, blocks, block_shape, origin=origin, fillval=fillval, out=out)[0]
+
+
+def batch_origin(blocks, bh, bw):
+    """floor(min of the batch's coordinate field) - 4 per axis (common.py:300-304): the field is affine, so
+    its extrema sit at block corners."""
+    b = np.asarray(blocks, dtype=np.float64).reshape(-1, 10)
+    xe = np.stack((b[:, 0], b[:, 0] + (bw - 1) * b[:, 2]), axis=-1)[:, :, None]     # N x 2 x 1
+    ye = np.stack((b[:, 1], b[:, 1] + (bh - 1) * b[:, 3]), axis=-1)[:, None, :]     # N x 1 x 2
+    xs = xe * b[:, 4, None, None] + ye * b[:, 5, None, None] + b[:, 6, None, None]
+    ys = xe * b[:, 7, None, None] + ye * b[:, 8, None, None] + b[:, 9, None, None]
+    return math.floor(xs.min()) - 4, math.floor(ys.min()) - 4

@@ -1,0 +1,665 @@
+"""Matcher layers above ``xcorr_fft``, same names / arguments / return conventions as
+``feabas/matcher.py``, with the pixel work on the GPU.
+
+* ``global_translation_matcher``        feabas/matcher.py:138-221
+* ``stitching_matcher``                 feabas/matcher.py:224-367
+* ``section_matcher``                   feabas/matcher.py:370-427
+* ``iterative_xcorr_matcher_w_mesh``    feabas/matcher.py:430-778
+* ``bboxes_mesh_renderer_matcher``      feabas/matcher.py:781-861
+
+The control flow (pyramid level selection, confidence filtering, pad rule) is host Python, as in the
+reference.  Geometry and relaxation (the reference's ``Mesh`` / ``SLM`` / ``MeshRenderer``, SURVEY
+section 2 rows 9, 11, 12) are outside this package: the loop talks to them through the handful of
+methods the reference itself uses, so the reference's own objects plug in when FEABAS is
+installed; ``feabas_b200.cuda.surrogate`` provides an affine stand-in (``AffineMesh`` /
+``AffineSLM``) that keeps every matcher function runnable -- and testable -- without them.
+"""
+import numpy as np
+
+from . import blocks as _blk
+from . import image as _img
+from . import _lib
+from .constant import (ANNEAL_CONNECTED_RIGID as _ANNEAL_CONNECTED_RIGID, ANNEAL_COPY_EXACT as _ANNEAL_COPY_EXACT,
+                       DEFAULT_AVG_DEFORM, DEFAULT_RESOLUTION, DEFAULT_THICKNESS, FFT_CONF_MIRROR, MESH_GEAR_FIXED,
+                       MESH_GEAR_INITIAL, MESH_GEAR_MOVING, Match)
+from .surrogate import AffineMesh, AffineSLM, ArrayLoader
+from .xcorr import fft_shape, xcorr_fft, xcorr_fft_device
+
+try:
+    import torch
+except Exception:                       # pragma: no cover
+    torch = None
+
+
+# --------------------------------------------------------------------------------------------
+# global translation
+# --------------------------------------------------------------------------------------------
+def _fit_window(lo, hi, want, limit):
+    """Grow [lo, hi) symmetrically to ``want`` pixels, slide it back inside [0, limit], clip."""
+    grow = int(np.ceil((want - (hi - lo)) / 2))
+    lo, hi = lo - grow, hi + grow
+    slide = -min(lo, 0) - max(hi - limit, 0)
+    return int(min(max(lo + slide, 0), limit)), int(min(max(hi + slide, 0), limit))
+
+
+def _translation_blocks(windows):
+    """integer windows (x_lo, y_lo) -> fb_crop_blocks rows for an identity map"""
+    rows = np.zeros((len(windows), 10), dtype=np.float64)
+    for i, (x_lo, y_lo) in enumerate(windows):
+        rows[i] = (x_lo, y_lo, 1, 1, 1, 0, 0, 0, 1, 0)
+    return rows
+
+
+def global_translation_matcher(img0, img1, **kwargs):
+    """Whole-image translation (tx, ty, conf): one padded cross-correlation of the two images and, when its
+    confidence is not above ``conf_thresh``, a second try on a grid of sub-blocks.
+
+    ``img0`` / ``img1``: 2-D numpy arrays or CUDA tensors (already band-passed unless ``sigma`` > 0).
+    kwargs as the reference: ``sigma`` (0), ``mask0``/``mask1``, ``conf_mode`` (MIRROR), ``conf_thresh`` (0.3),
+    ``divide_factor`` (6).  Returns Python floats.
+    """
+    sigma = kwargs.get('sigma', 0.0)
+    conf_mode = kwargs.get('conf_mode', FFT_CONF_MIRROR)
+    conf_thresh = kwargs.get('conf_thresh', 0.3)
+    divide_factor = kwargs.get('divide_factor', 6)
+    dev = kwargs.get('device', None)
+    a = _img.to_device(img0, dev)
+    b = _img.to_device(img1, a.device.index)
+    if a.dtype != b.dtype:
+        a, b = a.to(torch.float64), b.to(torch.float64)
+    if sigma > 0:
+        a = _masked_dog_any(a, sigma, kwargs.get('mask0', None))
+        b = _masked_dog_any(b, sigma, kwargs.get('mask1', None))
+    h0, w0 = a.shape[-2:]
+    h1, w1 = b.shape[-2:]
+    res = xcorr_fft_device(a.reshape(1, h0, w0), b.reshape(1, h1, w1), conf_mode=conf_mode, pad=True).cpu().numpy()
+    tx, ty, conf = float(res[0, 0]), float(res[1, 0]), _conf_scalar(res[2, 0], conf_mode)
+    tx += (w1 - w0) / 2
+    ty += (h1 - h0) / 2
+    if conf > conf_thresh:
+        return tx, ty, conf
+    rows_cols = _blk.balanced_division(np.minimum((h0, w0), (h1, w1)), divide_factor)
+    xa0, ya0, xb0, yb0 = _blk.divide_bbox((0, 0, w0, h0), min_num_blocks=rows_cols)
+    xa1, ya1, xb1, yb1 = _blk.divide_bbox((0, 0, w1, h1), min_num_blocks=rows_cols)
+    win0, win1 = [], []
+    for k in range(xa0.size):
+        want_w = max(xb0[k] - xa0[k], xb1[k] - xa1[k])
+        want_h = max(yb0[k] - ya0[k], yb1[k] - ya1[k])
+        win0.append(_fit_window(xa0[k], xb0[k], want_w, w0) + _fit_window(ya0[k], yb0[k], want_h, h0))
+        win1.append(_fit_window(xa1[k], xb1[k], want_w, w1) + _fit_window(ya1[k], yb1[k], want_h, h1))
+    win0, win1 = np.array(win0), np.array(win1)          # columns: x_lo, x_hi, y_lo, y_hi
+    size0 = np.stack((win0[:, 3] - win0[:, 2], win0[:, 1] - win0[:, 0]), axis=-1)
+    size1 = np.stack((win1[:, 3] - win1[:, 2], win1[:, 1] - win1[:, 0]), axis=-1)
+    if np.any(size0 != size0[0]) or np.any(size1 != size1[0]):
+        # the reference np.stack()s the blocks and raises on ragged ones
+        raise ValueError('all input arrays must have the same shape')
+    if a.dtype in (torch.float32, torch.uint8):
+        s0 = _img.crop_blocks(a, _translation_blocks(win0[:, [0, 2]]), size0[0], origin=(0, 0))
+        s1 = _img.crop_blocks(b, _translation_blocks(win1[:, [0, 2]]), size1[0], origin=(0, 0))
+        flat = (np.ptp(_img.stack_minmax(s0).cpu().numpy(), axis=-1) == 0) | (np.ptp(_img.stack_minmax(s1).cpu().numpy(), axis=-1) == 0)
+    else:
+        s0 = torch.stack([a[w[2]:w[3], w[0]:w[1]] for w in win0])
+        s1 = torch.stack([b[w[2]:w[3], w[0]:w[1]] for w in win1])
+        flat = np.array([bool(x.max() == x.min()) or bool(y.max() == y.min()) for x, y in zip(s0, s1)])
+    keep = np.nonzero(~flat)[0]                          # constant blocks carry no signal (matcher.py:196,205)
+    if keep.size == 0:
+        return tx, ty, conf
+    if keep.size < flat.size:
+        sel = torch.from_numpy(keep).to(s0.device)
+        s0, s1 = s0.index_select(0, sel).contiguous(), s1.index_select(0, sel).contiguous()
+    res = xcorr_fft_device(s0, s1, conf_mode=conf_mode, pad=True).cpu().numpy()
+    off_x = ((win1[:, 1] - win1[:, 0]) - (win0[:, 1] - win0[:, 0])) / 2 + win1[:, 0] - win0[:, 0]
+    off_y = ((win1[:, 3] - win1[:, 2]) - (win0[:, 3] - win0[:, 2])) / 2 + win1[:, 2] - win0[:, 2]
+    block_tx, block_ty = res[0] + off_x[keep], res[1] + off_y[keep]
+    block_conf = res[2].astype(np.float64 if conf_mode == 1 else np.float32)
+    best = int(np.argmax(block_conf))
+    if block_conf[best] >= conf:
+        tx, ty, conf = float(block_tx[best]), float(block_ty[best]), _conf_scalar(block_conf[best], conf_mode)
+    return tx, ty, conf
+
+
+def _conf_scalar(v, conf_mode):
+    # the reference returns conf.item() of a float32 array (float64 for FFT_CONF_STD)
+    return float(v) if conf_mode == 1 else float(np.float32(v))
+
+
+def _masked_dog_any(t, sigma, mask):
+    if mask is not None:
+        if bool(mask.all()):
+            mask = None
+        else:
+            mask = _img.to_device(mask, t.device.index)
+    return _img.masked_dog_device(t, sigma, mask)
+
+
+# --------------------------------------------------------------------------------------------
+# one pass over a block grid
+# --------------------------------------------------------------------------------------------
+def _as_loader(loader, device=None):
+    """ArrayLoader as is; a reference ``StreamLoader`` (feabas/dal.py:1008) or any object exposing the in-RAM
+    image as ``_img`` with ``bounds`` is wrapped (image uploaded once)."""
+    if isinstance(loader, ArrayLoader):
+        return loader
+    if hasattr(loader, '_img') and hasattr(loader, 'bounds'):
+        cached = getattr(loader, '_fb_device_loader', None)
+        if cached is None:
+            b = loader.bounds
+            cached = ArrayLoader(loader._img, fillval=getattr(loader, '_default_fillval', 0),
+                                 resolution=getattr(loader, 'resolution', 4.0), x0=b[0], y0=b[1], device=device)
+            try:
+                loader._fb_device_loader = cached
+            except AttributeError:
+                pass
+        return cached
+    raise TypeError(f'cannot take pixels from {type(loader).__name__}: pass a feabas_b200.cuda.ArrayLoader '
+                    '(or a feabas StreamLoader)')
+
+
+def _block_rows(mesh, loader, bboxes):
+    """fb_crop_blocks rows for the blocks ``bboxes`` (output / MOVING frame) of an affine mesh over ``loader``:
+    source pixel = (moving @ Ainv + tinv) - loader origin   (feabas/renderer.py:419-450)."""
+    ainv, tinv = mesh.render_map()
+    b = np.asarray(bboxes, dtype=np.float64).reshape(-1, 4)
+    wd = np.round(b[:, 2] - b[:, 0])
+    ht = np.round(b[:, 3] - b[:, 1])
+    rows = np.empty((b.shape[0], 10), dtype=np.float64)
+    rows[:, 0], rows[:, 1] = b[:, 0], b[:, 1]
+    rows[:, 2], rows[:, 3] = (b[:, 2] - b[:, 0]) / wd, (b[:, 3] - b[:, 1]) / ht
+    rows[:, 4], rows[:, 5], rows[:, 6] = ainv[0, 0], ainv[1, 0], tinv[0] - loader.x0
+    rows[:, 7], rows[:, 8], rows[:, 9] = ainv[0, 1], ainv[1, 1], tinv[1] - loader.y0
+    return rows, (int(ht[0]), int(wd[0]))
+
+
+def _render_stack(mesh, loader, bboxes, sigma, ptp_hint=None):
+    """Blocks of one batch as an ``N x H x W`` CUDA tensor (band-passed when ``sigma`` > 0)."""
+    rows, shape = _block_rows(mesh, loader, bboxes)
+    cover = loader.cover_rect() if sigma > 0 else None
+    stack, mask = _img.crop_blocks_masked(loader.tensor, rows, shape, fillval=loader.default_fillval, cover=cover)
+    if sigma > 0:
+        if mask is not None and bool(mask.all()):
+            mask = None
+        stack = _img.masked_dog_device(stack, sigma, mask, ptp=ptp_hint)
+    return stack
+
+
+def bboxes_mesh_renderer_matcher(mesh0, mesh1, image_loader0, image_loader1, bboxes0, bboxes1, **kwargs):
+    """Render the blocks ``bboxes0`` / ``bboxes1`` of the two sections and cross-correlate them pairwise.
+
+    Returns ``(xy0, xy1, conf)``: matched points (K x 2 float64, in the frame the bboxes live in) and the
+    per-block confidence.  kwargs as the reference: ``batch_size``, ``sigma`` (0), ``conf_mode`` (MIRROR),
+    ``pad`` (True), ``subpixel`` (False); ``render_mode`` / ``geodesic_mask`` / ``mask_range`` /
+    ``affine_approx_tol`` / ``render_weight_threshold`` are accepted and only meaningful for reference meshes.
+    """
+    batch_size = kwargs.get('batch_size', None)
+    sigma = kwargs.get('sigma', 0.0)
+    conf_mode = kwargs.get('conf_mode', FFT_CONF_MIRROR)
+    pad = kwargs.get('pad', True)
+    subpixel = kwargs.get('subpixel', False)
+    empty = (np.empty((0, 2)), np.empty((0, 2)), np.empty(0))
+    if not (hasattr(mesh0, 'render_map') and hasattr(mesh1, 'render_map')):
+        return _reference_block_pass(mesh0, mesh1, image_loader0, image_loader1, bboxes0, bboxes1, **kwargs)
+    if bboxes0 is None or len(bboxes0) == 0:
+        return empty
+    loader0 = _as_loader(image_loader0, kwargs.get('device', None))
+    loader1 = _as_loader(image_loader1, loader0.tensor.device.index)
+    bboxes0, bboxes1 = np.asarray(bboxes0), np.asarray(bboxes1)
+    edges = _blk.split_batches(bboxes0, bboxes1, batch_size)
+    pending = []
+    for lo, hi in zip(edges[:-1], edges[1:]):
+        if hi <= lo:
+            continue
+        stack0 = _render_stack(mesh0, loader0, bboxes0[lo:hi], sigma)
+        stack1 = _render_stack(mesh1, loader1, bboxes1[lo:hi], sigma)
+        pending.append((lo, hi, xcorr_fft_device(stack0, stack1, conf_mode=conf_mode, pad=pad, subpixel=subpixel)))
+    if not pending:
+        return empty
+    xy0, xy1, conf = [], [], []
+    for lo, hi, res in pending:                           # one synchronising read per batch, after all were enqueued
+        res = res.cpu().numpy()
+        p0, p1 = _blk.block_points(bboxes0[lo:hi], bboxes1[lo:hi], res[0], res[1])
+        xy0.append(p0)
+        xy1.append(p1)
+        conf.append(res[2].astype(np.float64 if conf_mode == 1 else np.float32))
+    return np.concatenate(xy0, axis=0), np.concatenate(xy1, axis=0), np.concatenate(conf, axis=0)
+
+
+def _reference_block_pass(mesh0, mesh1, image_loader0, image_loader1, bboxes0, bboxes1, **kwargs):
+    """Reference ``Mesh`` objects: blocks are rendered by the reference's own ``MeshRenderer`` on the host
+    (piecewise-linear fields, shapely masks: SURVEY section 2 row 9, not part of this package) and matched by the
+    CUDA ``xcorr_fft``.  Needs FEABAS installed."""
+    try:
+        import feabas.matcher as ref
+    except Exception as exc:            # pragma: no cover - FEABAS is not installed in the build container
+        raise TypeError('meshes without render_map() need the FEABAS package for rendering') from exc
+    saved = ref.xcorr_fft               # pragma: no cover
+    ref.xcorr_fft = xcorr_fft           # pragma: no cover
+    try:                                # pragma: no cover
+        return ref.bboxes_mesh_renderer_matcher(mesh0, mesh1, image_loader0, image_loader1, bboxes0, bboxes1, **kwargs)
+    finally:                            # pragma: no cover
+        ref.xcorr_fft = saved
+
+
+# --------------------------------------------------------------------------------------------
+# coarse-to-fine loop
+# --------------------------------------------------------------------------------------------
+def _make_optimizer(mesh0, mesh1, stiffness_lambda, **kwargs):
+    if hasattr(mesh0, 'render_map'):
+        return AffineSLM([mesh0, mesh1], stiffness_lambda=stiffness_lambda, **kwargs)
+    from feabas import optimizer        # pragma: no cover - reference meshes bring the reference solver
+    return optimizer.SLM([mesh0, mesh1], stiffness_lambda=stiffness_lambda, **kwargs)   # pragma: no cover
+
+
+def _relax(opt, linear, tol, steps, opt_kwargs, **extra):
+    if linear:
+        opt.optimize_linear(tol=tol, **extra, **opt_kwargs)
+    else:
+        opt.optimize_Newton_Raphson(max_newtonstep=steps, tol=tol, **extra, **opt_kwargs)
+
+
+def _refine_mode_code(refine_mode):
+    if not isinstance(refine_mode, str):
+        return refine_mode
+    name = refine_mode.lower()
+    return 0 if name == 'none' else (1 if 'only' in name else 2)
+
+
+def _absolute_spacings(spacings, mesh0, mesh1):
+    """Spacings below 1 are fractions of the long side of the meshes' common bounding box."""
+    spacings = np.array(spacings, dtype=np.float64, copy=True).ravel()
+    if np.any(spacings < 1):
+        box, valid = _blk.intersect_bbox(mesh0.bbox(gear=MESH_GEAR_MOVING), mesh1.bbox(gear=MESH_GEAR_MOVING))
+        if not valid:
+            return None
+        spacings[spacings < 1] *= max(box[2] - box[0], box[3] - box[1])
+    return spacings
+
+
+def iterative_xcorr_matcher_w_mesh(mesh0, mesh1, image_loader0, image_loader1, spacings, **kwargs):
+    """Alternate block matching and mesh relaxation from the coarsest spacing to the finest.
+
+    Returns ``(xy0, xy1, weight, strain)``; ``(None, None, 0, strain)`` when nothing could be matched.
+    kwargs and their defaults are the reference's (feabas/matcher.py:485-507).
+    """
+    num_workers = kwargs.get('num_workers', 1)            # accepted; the GPU path batches instead of forking
+    conf_thresh = kwargs.get('conf_thresh', 0.3)
+    residue_mode = kwargs.get('residue_mode', 'huber')
+    residue_len = kwargs.get('residue_len', 0)
+    opt_tol = kwargs.get('opt_tol', None)
+    distributor = kwargs.get('distributor', 'cartesian_bbox')
+    min_num_blocks = kwargs.get('min_num_blocks', 2)
+    shrink_factor = kwargs.get('shrink_factor', 1)
+    allow_dwell = kwargs.get('allow_dwell', 0)
+    allow_enlarge = kwargs.get('allow_enlarge', False)
+    link_weight_decay = kwargs.get('link_weight_decay', 0.0)
+    compute_strain = kwargs.get('compute_strain', True)
+    batch_size = kwargs.pop('batch_size', None)
+    initial_matches = kwargs.get('initial_matches', None)
+    pad_request = kwargs.pop('pad', None)
+    refine_mode = _refine_mode_code(kwargs.get('refine_mode', 2))
+    subpixel_request = kwargs.pop('subpixel', None)
+    max_spacing_skip = kwargs.get('max_spacing_skip', 0)
+    callback_settings = kwargs.get('callback_settings', {'early_stop_thresh': 0.1, 'chances': 10, 'eval_step': 5})
+    render_weight_threshold = kwargs.get('render_weight_threshold', 0)
+    stiffness_lambda = kwargs.pop('stiffness_lambda', 1)
+    affine_render = kwargs.pop('affine_approximated_render', True)
+    del num_workers
+    strain = DEFAULT_AVG_DEFORM
+    nothing = (None, None, 0, strain)
+    if residue_len < 0:
+        # negative = in units of section thickness (feabas/matcher.py:523-525)
+        residue_len = max(1, abs(residue_len) * _section_thickness() / mesh0.resolution)
+    spacings = _absolute_spacings(spacings, mesh0, mesh1)
+    if spacings is None:
+        return nothing
+    opt_kwargs = {'callback_settings': callback_settings, 'check_converge': True}
+    linear = mesh0.is_linear and mesh1.is_linear
+    one_locked = mesh0.locked or mesh1.locked
+    if compute_strain:
+        pristine0, pristine1 = mesh0.copy(), mesh1.copy()
+    opt = _make_optimizer(mesh0, mesh1, stiffness_lambda)
+    if initial_matches is not None:
+        opt_kwargs['tolerated_perturbation'] = 0.1
+        opt.add_link_from_coordinates(mesh0.uid, mesh1.uid, initial_matches.xy0, initial_matches.xy1,
+                                      gear=(MESH_GEAR_INITIAL, MESH_GEAR_INITIAL), weight=initial_matches.weight,
+                                      check_duplicates=False, render_weight_threshold=render_weight_threshold)
+        opt.optimize_affine_cascade(start_gear=MESH_GEAR_FIXED, target_gear=MESH_GEAR_FIXED, svd_clip=None)
+        opt.anneal(gear=(MESH_GEAR_FIXED, MESH_GEAR_MOVING), mode=_ANNEAL_CONNECTED_RIGID)
+        if linear:
+            opt.optimize_linear(tol=1e-6, precondition='smoothed_aggregation', **opt_kwargs)
+        else:
+            opt.optimize_Newton_Raphson(max_newtonstep=5, tol=1e-4, precondition='smoothed_aggregation', **opt_kwargs)
+    else:
+        mesh0.anneal(gear=(MESH_GEAR_MOVING, MESH_GEAR_FIXED), mode=_ANNEAL_COPY_EXACT)
+        mesh1.anneal(gear=(MESH_GEAR_MOVING, MESH_GEAR_FIXED), mode=_ANNEAL_COPY_EXACT)
+    opt_kwargs['tolerated_perturbation'] = 0.5
+    spacings = np.sort(spacings)[::-1]
+    finest = spacings[-1]
+    spacing = spacings[0]
+    level = 0
+    started = False
+    may_enlarge = bool(allow_enlarge)
+    dwelled = 0
+    pad = True if pad_request is None else pad_request
+    while level < spacings.size:
+        at_finest = spacing == finest
+        subpixel = at_finest if subpixel_request is None else subpixel_request
+        if affine_render:
+            affine_tol = 0.1 if at_finest else max(1, 0.02 * spacing)
+        else:
+            affine_tol = 0
+        if distributor == 'cartesian_bbox':
+            boxes0, boxes1 = _blk.distributor_cartesian_bbox(mesh0, mesh1, spacing, min_num_blocks=min_num_blocks if at_finest else 1,
+                                                             shrink_factor=shrink_factor, zorder=True)
+        else:
+            boxes0, boxes1 = _region_blocks(mesh0, mesh1, spacing, distributor, at_finest, refine_mode, **kwargs)
+        if boxes0 is None:
+            return nothing
+        xy0, xy1, conf = bboxes_mesh_renderer_matcher(mesh0, mesh1, image_loader0, image_loader1, boxes0, boxes1,
+                                                      batch_size=batch_size, pad=pad, subpixel=subpixel,
+                                                      affine_approx_tol=affine_tol, **kwargs)
+        good = conf > conf_thresh
+        if not np.any(good):
+            if not started:
+                return nothing
+            break
+        if link_weight_decay == 0:
+            opt.clear_links()
+        else:
+            for link in opt.links:
+                link._weight = link._weight * link_weight_decay
+        xy0, xy1, weight = xy0[good], xy1[good], conf[good]
+        max_dis = np.max(np.sum((xy0 - xy1) ** 2, axis=-1)) ** 0.5
+        tol = 0.01 / max(1, max_dis) if opt_tol is None else opt_tol
+        # blocks of the next level must be at least 4x the largest displacement still unexplained
+        need = 4 * max_dis
+        target = np.searchsorted(-spacings, -need) - 1
+        if may_enlarge and target < 0:
+            may_enlarge = False
+            level = -1
+            spacing = np.ceil(need)
+            if pad_request is None:
+                pad = True
+            continue
+        may_enlarge = False
+        if target > level:
+            target = min(target, level + 1 + max_spacing_skip)
+            if pad_request is None:
+                pad = target > level + 1              # adjacent level: displacements are small, circular xcorr suffices
+            level, dwelled = target, 0
+        elif dwelled >= allow_dwell:
+            if pad_request is None:
+                pad = True
+            level, dwelled = level + 1, 0
+        else:
+            if pad_request is None:
+                pad = True
+            dwelled += 1
+        opt.add_link_from_coordinates(mesh0.uid, mesh1.uid, xy0, xy1, gear=(MESH_GEAR_MOVING, MESH_GEAR_MOVING),
+                                      weight=weight, check_duplicates=False, render_weight_threshold=render_weight_threshold)
+        if len(opt.links) == 0:
+            if not started:
+                return nothing
+            break
+        if max_dis > 0.1:
+            _relax(opt, linear, tol, 3, opt_kwargs)
+            if residue_len > 0:
+                if residue_mode == 'huber':
+                    opt.set_link_residue_huber(residue_len)
+                elif residue_mode == 'threshold':
+                    opt.set_link_residue_threshold(residue_len)
+                else:
+                    raise ValueError
+                changed, _ = opt.adjust_link_weight_by_residue(relax_first=True)
+                if changed and level < spacings.size:
+                    _relax(opt, linear, tol, 3, opt_kwargs)
+        started = True
+        if 0 <= level < spacings.size:
+            spacing = spacings[level]
+    if len(opt.links) == 0:
+        return nothing
+    last = opt.links[-1]
+    xy0 = last.xy0(gear=MESH_GEAR_INITIAL, use_mask=True, combine=True)
+    xy1 = last.xy1(gear=MESH_GEAR_INITIAL, use_mask=True, combine=True)
+    weight = last.weight(use_mask=True)
+    if compute_strain:
+        strain = _strain_ratio(pristine0, pristine1, xy0, xy1, weight, stiffness_lambda, one_locked, linear,
+                               render_weight_threshold, opt_kwargs)
+    return xy0, xy1, weight, strain
+
+
+def _section_thickness():
+    try:
+        from feabas.config import section_thickness     # pragma: no cover
+        return section_thickness()                      # pragma: no cover
+    except Exception:
+        return DEFAULT_THICKNESS
+
+
+def _region_blocks(mesh0, mesh1, spacing, distributor, at_finest, refine_mode, **kwargs):
+    """Region based distributors (shapely polygons, feabas/matcher.py:894-1058) belong to the reference's
+    geometry layer; with reference meshes they are called as is, the affine stand-in has no holes and uses the
+    cartesian grid."""
+    if hasattr(mesh0, 'render_map'):
+        return _blk.distributor_cartesian_bbox(mesh0, mesh1, spacing, min_num_blocks=kwargs.get('min_num_blocks', 2) if at_finest else 1,
+                                               shrink_factor=kwargs.get('shrink_factor', 1), zorder=True)
+    from feabas.matcher import distribute_matching_blocks                    # pragma: no cover
+    mode = refine_mode if (at_finest or refine_mode != 2) else 0             # pragma: no cover
+    return distribute_matching_blocks(mesh0, mesh1, spacing, dfunc=distributor, refine_mode=mode,   # pragma: no cover
+                                      min_boundary_distance=kwargs.get('min_boundary_distance', 0),
+                                      shrink_factor=kwargs.get('shrink_factor', 1), zorder=True,
+                                      render_weight_threshold=kwargs.get('render_weight_threshold', 0))
+
+
+def _strain_ratio(mesh0, mesh1, xy0, xy1, weight, stiffness_lambda, one_locked, linear, render_weight_threshold, opt_kwargs):
+    """Elastic energy of the final matches relative to that of the rigid shape (feabas/matcher.py:752-777)."""
+    opt = _make_optimizer(mesh0, mesh1, stiffness_lambda, assert_dominance=(not one_locked))
+    opt.add_link_from_coordinates(mesh0.uid, mesh1.uid, xy0, xy1, gear=(MESH_GEAR_INITIAL, MESH_GEAR_INITIAL), weight=weight,
+                                  check_duplicates=False, render_weight_threshold=render_weight_threshold)
+    opt.optimize_affine_cascade(start_gear=MESH_GEAR_INITIAL, target_gear=MESH_GEAR_FIXED, svd_clip=(1, 1))
+    opt.anneal(gear=(MESH_GEAR_FIXED, MESH_GEAR_MOVING), mode=_ANNEAL_COPY_EXACT)
+    if linear:
+        opt.optimize_linear(tol=1e-6, **opt_kwargs)
+    else:
+        opt.optimize_Newton_Raphson(max_newtonstep=5, tol=1e-4, **opt_kwargs)
+    soft_avg = np.mean([m.soft_factor for m in opt.meshes])
+    deformed = rigid = 0
+    for m in opt.meshes:
+        if (one_locked and not m.locked) or (not one_locked and m.soft_factor <= soft_avg):
+            v_fixed = m.vertices(gear=MESH_GEAR_FIXED)
+            move = m.vertices(gear=MESH_GEAR_MOVING) - v_fixed
+            v_fixed = v_fixed - np.mean(v_fixed, axis=0, keepdims=True)
+            move = move - np.mean(move, axis=0, keepdims=True)
+            stiff, _ = m.stiffness_matrix()
+            deformed += max(0, stiff.dot(move.ravel()).dot(move.ravel()))
+            rigid += max(0, stiff.dot(v_fixed.ravel()).dot(v_fixed.ravel()))
+    return (deformed / rigid) ** 0.5
+
+
+# --------------------------------------------------------------------------------------------
+# section and stitching entry points
+# --------------------------------------------------------------------------------------------
+def section_matcher(mesh0, mesh1, image_loader0, image_loader1, **kwargs):
+    """Match two sections (feabas/matcher.py:370-427).  Returns ``(xy0, xy1, weight, strain)``."""
+    initial_matches = kwargs.pop('initial_matches', None)
+    spacings = kwargs.pop('spacings', [100])
+    kwargs.setdefault('sigma', 2.5)
+    kwargs.setdefault('batch_size', 100)
+    kwargs.setdefault('distributor', 'cartesian_region')
+    kwargs.setdefault('link_weight_decay', 0.0)
+    compute_strain = kwargs.pop('compute_strain', False)
+    stiff_thresh = kwargs.get('stiffness_multiplier_threshold', 0.1)
+    kwargs.setdefault('render_weight_threshold', 0.1)
+    stiffness_lambda = kwargs.setdefault('stiffness_lambda', 0.5)
+    if stiff_thresh > 0 and hasattr(mesh0, 'triangle_mask_for_stiffness'):
+        mesh0 = mesh0.submesh(mesh0.triangle_mask_for_stiffness(stiffness_multiplier_threshold=stiff_thresh))
+        mesh1 = mesh1.submesh(mesh1.triangle_mask_for_stiffness(stiffness_multiplier_threshold=stiff_thresh))
+    single = initial_matches is None or (mesh0.connected_triangles()[0] == 1 and mesh1.connected_triangles()[0] == 1)
+    if single:
+        return iterative_xcorr_matcher_w_mesh(mesh0, mesh1, image_loader0, image_loader1, spacings=spacings,
+                                              initial_matches=initial_matches, compute_strain=compute_strain, **kwargs)
+    # disconnected pieces are matched one pair at a time
+    opt = _make_optimizer(mesh0, mesh1, stiffness_lambda)
+    opt.add_link_from_coordinates(mesh0.uid, mesh1.uid, initial_matches.xy0, initial_matches.xy1,
+                                  gear=(MESH_GEAR_INITIAL, MESH_GEAR_INITIAL), weight=initial_matches.weight, check_duplicates=False)
+    opt.divide_disconnected_submeshes(prune_links=True)
+    parts0, parts1, weights = [], [], []
+    strain = DEFAULT_AVG_DEFORM
+    for link in opt.links:
+        sub0, sub1 = link.meshes
+        seed = Match(link.xy0(gear=MESH_GEAR_INITIAL, use_mask=False, combine=True),
+                     link.xy1(gear=MESH_GEAR_INITIAL, use_mask=False, combine=True), link.weight(use_mask=False))
+        p0, p1, wt, strain = iterative_xcorr_matcher_w_mesh(sub0.copy(), sub1.copy(), image_loader0, image_loader1,
+                                                            spacings=spacings, compute_strain=compute_strain,
+                                                            initial_matches=seed, **kwargs)
+        if p0 is None:
+            continue
+        same_order = (sub0.uid - sub1.uid) * (mesh0.uid - mesh1.uid) > 0
+        parts0.append(p0 if same_order else p1)
+        parts1.append(p1 if same_order else p0)
+        weights.append(wt)
+    if not parts0:
+        return None, None, 0, DEFAULT_AVG_DEFORM
+    return np.concatenate(parts0, axis=0), np.concatenate(parts1, axis=0), np.concatenate(weights, axis=0), strain
+
+
+def _downsample(img, mask, factor, dev):
+    t = _img.to_device(img, dev)
+    if factor == 1:
+        return t, (None if mask is None else _img.to_device(mask, t.device.index))
+    small = _img.resize_area(t, factor)
+    small_mask = None if mask is None else _img.resize_mask(_img.to_device(mask, t.device.index), factor)
+    return small, small_mask
+
+
+def _photometric(raw0, raw1, dog0, dog1, mask0, mask1, tx, ty, filtered):
+    """Mean / spread of the two images inside their overlap (feabas/matcher.py:279-314); small reductions done
+    with torch on the device tensors."""
+    sx, sy = int(tx), int(ty)
+    h0, w0 = dog0.shape
+    h1, w1 = dog1.shape
+    (x_lo, y_lo, x_hi, y_hi), _ = _blk.intersect_bbox((sx, sy, w0 + sx, h0 + sy), (0, 0, w1, h1))
+    win0 = (slice(y_lo - sy, y_hi - sy), slice(x_lo - sx, x_hi - sx))
+    win1 = (slice(y_lo, y_hi), slice(x_lo, x_hi))
+    ones = torch.ones((max(y_hi - y_lo, 0), max(x_hi - x_lo, 0)), dtype=torch.bool, device=dog0.device)
+    m0 = ones if mask0 is None else mask0[win0].to(torch.bool)
+    m1 = ones if mask1 is None else mask1[win1].to(torch.bool)
+    both = m0 & m1
+    if int(m0.sum()) <= 3:
+        return None
+    if filtered:
+        av0 = raw0[win0][both].to(torch.float64).mean().item()
+        av1 = raw1[win1][both].to(torch.float64).mean().item()
+        sd0 = dog0[win0][both].abs().mean().item()
+        sd1 = dog1[win1][both].abs().mean().item()
+    else:
+        v0, v1 = dog0[win0][both].to(torch.float64), dog1[win1][both].to(torch.float64)
+        av0, av1 = v0.mean().item(), v1.mean().item()
+        sd0, sd1 = v0.std(unbiased=False).item(), v1.std(unbiased=False).item()
+    return av0, av1, sd0, sd1
+
+
+def stitching_matcher(img0, img1, **kwargs):
+    """Displacement samples between two overlapping tile strips (feabas/matcher.py:224-367).
+
+    Returns ``(xy0, xy1, weight, strain, phtm)`` -- points in each strip's own pixel frame -- or
+    ``(None, None, conf_thresh, None, None)`` when the coarse translation is not trustworthy.
+    The strips are uploaded once; resize, band-pass, block extraction and correlation run on the GPU.
+    """
+    sigma = kwargs.pop('sigma', 2.5)
+    mask0 = kwargs.pop('mask0', None)
+    mask1 = kwargs.pop('mask1', None)
+    compute_photometric = kwargs.pop('compute_photometric', False)
+    coarse = kwargs.pop('coarse_downsample', 1)
+    fine = kwargs.pop('fine_downsample', 1)
+    spacings = kwargs.pop('spacings', None)
+    residue_len = kwargs.pop('residue_len', 5)
+    dev = kwargs.pop('device', None)
+    conf_mode = kwargs.get('conf_mode', FFT_CONF_MIRROR)
+    conf_thresh = kwargs.get('conf_thresh', 0.3)
+    min_num_blocks = kwargs.get('min_num_blocks', 2)
+    kwargs.setdefault('residue_mode', 'huber')
+    kwargs.setdefault('opt_tol', None)
+    shape0 = tuple(img0.shape)
+    shape1 = tuple(img1.shape)
+    if spacings is None:
+        spacings = _blk.auto_spacings(shape0, shape1)
+    else:
+        spacings = np.array(spacings, dtype=np.float64, copy=True).ravel()
+    raw0, cmask0 = _downsample(img0, mask0, coarse, dev)
+    dev = raw0.device.index
+    raw1, cmask1 = _downsample(img1, mask1, coarse, dev)
+    if sigma > 0:
+        g0 = _masked_dog_any(raw0, sigma * coarse, cmask0)
+        g1 = _masked_dog_any(raw1, sigma * coarse, cmask1)
+    else:
+        g0, g1 = raw0, raw1
+    tx, ty, conf = global_translation_matcher(g0, g1, conf_mode=conf_mode, conf_thresh=conf_thresh)
+    if conf < conf_thresh:
+        return None, None, conf_thresh, None, None
+    phtm = None
+    if compute_photometric:
+        phtm = _photometric(raw0, raw1, g0, g1, cmask0, cmask1, tx, ty, sigma > 0)
+    if fine == coarse:
+        f0, f1 = g0, g1
+    else:
+        f0, fmask0 = _downsample(img0, mask0, fine, dev)
+        f1, fmask1 = _downsample(img1, mask1, fine, dev)
+        if sigma > 0:
+            f0 = _masked_dog_any(f0, sigma * fine, fmask0)
+            f1 = _masked_dog_any(f1, sigma * fine, fmask1)
+    tx = tx * fine / coarse
+    ty = ty * fine / coarse
+    resolution = _data_resolution() / fine
+    residue_len = residue_len * fine
+    loader0 = ArrayLoader(f0, fillval=0, resolution=resolution)
+    loader1 = ArrayLoader(f1, fillval=0, resolution=resolution)
+    if np.any(spacings < 1):
+        box, _ = _blk.intersect_bbox(np.array(loader0.bounds) + np.tile((tx, ty), 2), loader1.bounds)
+        spacings[spacings < 1] *= max(box[2] - box[0], box[3] - box[1])
+    spacings = spacings * fine
+    mesh0, mesh1 = _stitch_meshes(loader0, loader1, np.min(spacings), min_num_blocks)
+    mesh0.apply_translation((tx, ty), MESH_GEAR_FIXED)
+    mesh0.lock()
+    xy0, xy1, weight, strain = iterative_xcorr_matcher_w_mesh(mesh0, mesh1, loader0, loader1, spacings=spacings,
+                                                              distributor='cartesian_bbox', residue_len=residue_len, **kwargs)
+    if fine != 1 and xy0 is not None:
+        xy0 = _scale_coordinates(xy0, 1 / fine)
+        xy1 = _scale_coordinates(xy1, 1 / fine)
+    return xy0, xy1, weight, strain, phtm
+
+
+def _scale_coordinates(xy, scale):
+    """Pixel-centre preserving rescale (feabas/spatial.py:77-89)."""
+    return (np.asarray(xy) + 0.5) * scale - 0.5
+
+
+def _data_resolution():
+    try:
+        from feabas.config import data_resolution       # pragma: no cover
+        return data_resolution()                        # pragma: no cover
+    except Exception:
+        return DEFAULT_RESOLUTION
+
+
+_MESH_FACTORY = None
+
+
+def set_mesh_factory(factory):
+    """``factory(bounds, mesh_size, min_num_blocks, uid, resolution) -> mesh``.  ``None`` restores the default:
+    the reference's ``Mesh.from_bbox`` when FEABAS imports, else the affine stand-in."""
+    global _MESH_FACTORY
+    _MESH_FACTORY = factory
+
+
+def _stitch_meshes(loader0, loader1, mesh_size, min_num_blocks):
+    factory = _MESH_FACTORY
+    if factory is None:
+        factory = _default_mesh_factory()
+    return (factory(loader0.bounds, mesh_size, min_num_blocks, 0, loader0.resolution),
+            factory(loader1.bounds, mesh_size, min_num_blocks, 1, loader1.resolution))
+
+
+def _default_mesh_factory():
+    def affine(bounds, mesh_size, min_num_blocks, uid, resolution):
+        return AffineMesh(bounds, uid=uid, resolution=resolution)
+    return affine

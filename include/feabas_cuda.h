@@ -76,6 +76,62 @@ int fb_xcorr_batch(const void* img0, const void* img1, int n, int h0, int w0, in
                    double* dx, double* dy, double* conf, double* peak, double* mirror,
                    int device, void* stream);
 
+/* ---- image operators either side of the matcher (device pointers on `device`, work enqueued on
+ * `stream`, no synchronisation) ------------------------------------------------------------- */
+
+#define FB_DOG_UNSIGNED 0x1   /* signed=False: absolute value of the band-pass                      */
+#define FB_DOG_EXACT 0x2      /* float64 accumulation in scipy.ndimage.correlate1d's order: the
+                                 reference's rounding; default is float32 accumulation           */
+
+/* common.masked_dog_filter (feabas/common.py:353-377) on a stack of n images h x w
+ * (in_dtype FB_F32 or FB_U8), two cascaded separable Gaussians (scipy.ndimage.gaussian_filter1d:
+ * radius int(4 sigma + 0.5), mode='nearest'), out = G(img) - G(G(img)), float32.
+ * mask: NULL, or mask_n (1 or n) images of h x w bytes, nonzero = keep; when given, the term
+ * 2 G_{sqrt2 sigma}(ptp * (mask == 0)) is subtracted from |out| (sign kept).  The caller decides
+ * "mask is all true -> pass NULL" as the reference does (common.py:368).
+ * ptp: np.ptp of the WHOLE array the reference would have been handed (common.py:369); NaN = take
+ * it from this stack on the device.
+ * work: scratch of fb_masked_dog_workspace(n, h, w) bytes.                                       */
+long long fb_masked_dog_workspace(int n, int h, int w);
+int fb_masked_dog(const void* img, const unsigned char* mask, int n, int h, int w, int in_dtype, int mask_n,
+                  double sigma, double ptp, int flags, float* out, void* work, long long work_bytes,
+                  int device, void* stream);
+
+/* {min, max} (float32) of each of n images of `elems` elements: np.ptp of blocks
+ * (feabas/matcher.py:196,205) and of stacks (feabas/common.py:369).  minmax: n x 2 floats.      */
+int fb_stack_minmax(const void* stack, int n, long long elems, int in_dtype, float* minmax, int device, void* stream);
+
+/* cv2.resize(src, None, fx=1/k, fy=1/k, interpolation=cv2.INTER_AREA) as called at
+ * feabas/matcher.py:254-256,321-322: k x k cell means, OpenCV's rounding (uint8 bit-exact).
+ * oh, ow: the output size OpenCV picks, round-half-even(h / k), round-half-even(w / k).           */
+int fb_resize_area(const void* src, int n, int h, int w, int in_dtype, int k, void* dst, int oh, int ow,
+                   int device, void* stream);
+
+/* cv2.resize(..., interpolation=cv2.INTER_NEAREST) of uint8 masks (feabas/matcher.py:257-264):
+ * dst(y, x) = src(min(floor(y * inv_fy), h - 1), min(floor(x * inv_fx), w - 1)).                */
+int fb_resize_nearest(const unsigned char* src, int n, int h, int w, double inv_fy, double inv_fx,
+                      unsigned char* dst, int oh, int ow, int device, void* stream);
+
+/* Block extraction for affine block maps: MeshRenderer.crop_multiple (feabas/renderer.py:601-648)
+ * -> crop_field_affine (:419-450) -> common.render_by_subregions (feabas/common.py:256-350) ->
+ * cv2.remap(INTER_LINEAR, BORDER_CONSTANT).  Gathers n blocks of bh x bw pixels from ONE source
+ * image (ih x iw, FB_F32 or FB_U8; output has the same dtype).
+ * blocks: n x 10 doubles (device): x0, y0, step_x, step_y, A00, A10, t0, A01, A11, t1; output
+ * pixel (row, col) samples the source at
+ *     xx = x0 + col * step_x,  yy = y0 + row * step_y            (np.linspace, endpoint=False)
+ *     xs = xx * A00 + yy * A10 + t0,   ys = xx * A01 + yy * A11 + t1        (float64)
+ * then, as OpenCV does, (xs - origin_x, ys - origin_y) is rounded to float32 and to 1/32 px,
+ * and the four neighbours are blended with OpenCV's float (float32 images) or 15-bit integer
+ * (uint8 images) weights; pixels outside the image read `fillval`.
+ * origin_x, origin_y: integer-valued; the reference uses floor(min field) - 4 of the batch.
+ * cover (HOST pointer, may be NULL): xmin, ymin, xmax, ymax of the region of the source covered by
+ * the mesh; pixels whose source position falls outside it are not rendered (they keep `fillval`)
+ * and, when mask_out != NULL (n x bh x bw bytes, device), are flagged 0 there: the validity mask
+ * of crop_field_affine(precise_mask=True) that masked_dog_filter consumes.                      */
+int fb_crop_blocks(const void* img, int ih, int iw, int in_dtype, const double* blocks, int n, int bh, int bw,
+                   double origin_x, double origin_y, double fillval, void* out,
+                   const double* cover, unsigned char* mask_out, int device, void* stream);
+
 /* Smallest 2^a 3^b 5^c >= target: scipy.fftpack.next_fast_len as used at
  * feabas/matcher.py:60,62.  Pure host arithmetic.                          */
 int fb_next_fast_len(int target);

@@ -276,3 +276,202 @@ def auto_spacings_oracle(shape0, shape1):
         return np.array([smn])
     nsp = max(1, round(np.log(smx / smn) / np.log(4)))
     return np.exp(np.linspace(np.log(smn), np.log(smx), num=nsp, endpoint=True))
+
+
+# --------------------------------------------------------------------------- #
+# block rendering through an affine map (cv2.remap, as the reference does)
+# --------------------------------------------------------------------------- #
+def resize_area_oracle(img, factor):
+    """matcher.py:254-256 -- the very cv2 call of the reference."""
+    import cv2
+    return cv2.resize(img, None, fx=factor, fy=factor, interpolation=cv2.INTER_AREA)
+
+
+def resize_mask_oracle(mask, factor):
+    """matcher.py:257-264."""
+    import cv2
+    return cv2.resize(mask.astype(np.uint8), None, fx=factor, fy=factor, interpolation=cv2.INTER_NEAREST).astype(bool)
+
+
+def render_blocks_oracle(img, bboxes, ainv, tinv, fillval=0, origin_xy=(0, 0), cover=None):
+    """``MeshRenderer.crop_multiple`` for ONE affine map (renderer.py:601-648 with ``crop_field_affine``
+    renderer.py:419-450 for every block) over an in-RAM image whose pixel (0, 0) sits at ``origin_xy``
+    (``dal.StreamLoader``), rendered by ``common.render_by_subregions`` (common.py:256-350): fields of all
+    blocks concatenated, source crop = floor(min) - 4 .. ceil(max) + 4, ``cv2.remap(INTER_LINEAR,
+    BORDER_CONSTANT, fillval)``.  ``cover``: (xmin, ymin, xmax, ymax) in source pixels outside of which the
+    mask is False (only masked pixels are rendered).  Returns (stack N x H x W, mask N x H x W)."""
+    import cv2
+    fx, fy = [], []
+    for b in np.asarray(bboxes, dtype=np.float64).reshape(-1, 4):
+        wd, ht = round(b[2] - b[0]), round(b[3] - b[1])
+        xs = np.linspace(b[0], b[2], num=wd, endpoint=False, dtype=float)
+        ys = np.linspace(b[1], b[3], num=ht, endpoint=False, dtype=float)
+        xx, yy = np.meshgrid(xs, ys)
+        fx.append(xx * ainv[0, 0] + yy * ainv[1, 0] + tinv[0] - origin_xy[0])
+        fy.append(xx * ainv[0, 1] + yy * ainv[1, 1] + tinv[1] - origin_xy[1])
+    nblk = len(fx)
+    map_x, map_y = np.concatenate(fx, 0), np.concatenate(fy, 0)
+    if cover is None:
+        mask = np.ones(map_x.shape, dtype=bool)
+    else:
+        mask = (map_x >= cover[0]) & (map_x < cover[2]) & (map_y >= cover[1]) & (map_y < cover[3])
+    out = np.full(map_x.shape, fillval, dtype=img.dtype)
+    if mask.any():
+        x_lo, x_hi = np.floor(map_x[mask].min()) - 4, np.ceil(map_x[mask].max()) + 4
+        y_lo, y_hi = np.floor(map_y[mask].min()) - 4, np.ceil(map_y[mask].max()) + 4
+        src = crop_with_fill(img, (int(x_lo), int(y_lo), int(x_hi), int(y_hi)), fillval)
+        warped = cv2.remap(src, (map_x - x_lo).astype(np.float32), (map_y - y_lo).astype(np.float32),
+                           interpolation=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT, borderValue=fillval)
+        out[mask] = warped[mask]
+    return out.reshape(nblk, -1, out.shape[-1]), mask.reshape(nblk, -1, out.shape[-1])
+
+
+# --------------------------------------------------------------------------- #
+# coarse-to-fine loop with an affine section model (surrogate relaxation)
+# --------------------------------------------------------------------------- #
+class _Section:
+    """One affine map instead of an elastic mesh: moving = initial @ a + t."""
+
+    def __init__(self, bounds, locked=False):
+        self.bounds = bounds
+        self.a, self.t = np.eye(2), np.zeros(2)
+        self.locked = locked
+
+    def bbox(self):
+        x0, y0, x1, y1 = self.bounds
+        c = np.array([[x0, y0], [x1, y0], [x1, y1], [x0, y1]], dtype=np.float64) @ self.a + self.t
+        return np.array([c[:, 0].min(), c[:, 1].min(), c[:, 0].max(), c[:, 1].max()])
+
+    def fwd(self, p):
+        return p @ self.a + self.t
+
+    def inv(self, p):
+        return (p - self.t) @ np.linalg.inv(self.a)
+
+    def sampler(self):
+        ai = np.linalg.inv(self.a)
+        return ai, -self.t @ ai
+
+
+def _wls_affine(src, dst, w):
+    if src.shape[0] < 3 or np.linalg.matrix_rank(src - src.mean(0)) < 2:
+        return np.eye(2), (np.average(dst - src, axis=0, weights=w) if w.sum() > 0 else np.zeros(2))
+    sw = np.sqrt(w)[:, None]
+    design = np.concatenate((src, np.ones((src.shape[0], 1))), axis=1)
+    sol = np.linalg.lstsq(design * sw, dst * sw, rcond=None)[0]
+    return sol[:2], sol[2]
+
+
+def surrogate_loop_oracle(sec0, sec1, img0, img1, spacings, conf_thresh=0.3, residue_mode='huber', residue_len=0,
+                          min_num_blocks=2, pad=None, subpixel=None, batch_size=None, conf_mode=FFT_CONF_MIRROR,
+                          xcorr=xcorr_oracle, trace=None):
+    """Control flow of ``iterative_xcorr_matcher_w_mesh`` (matcher.py:567-751) for distributor
+    'cartesian_bbox', sec0 locked, ``allow_enlarge=False``, ``allow_dwell=0``, ``max_spacing_skip=0``,
+    ``link_weight_decay=0``, sigma=0, with the affine relaxation model of feabas_b200.cuda.surrogate."""
+    spacings = np.sort(np.asarray(spacings, dtype=np.float64))[::-1]
+    sp, idx, started = spacings[0], 0, False
+    use_pad = True if pad is None else pad
+    link = None
+    while idx < spacings.size:
+        finest = sp == spacings[-1]
+        sub = finest if subpixel is None else subpixel
+        box, ok = intersect_bbox_oracle(sec0.bbox(), sec1.bbox())
+        if not ok:
+            return None, None, 0
+        b0, b1 = cartesian_blocks_oracle(sec0.bbox(), sec1.bbox(), sp, min_num_blocks=min_num_blocks if finest else 1, zorder=True)
+        n = b0.shape[0]
+        z0 = np.round(bbox_sizes_oracle(b0))
+        brk = np.nonzero(np.any(np.diff(z0, axis=0), axis=-1))[0]
+        edges = np.concatenate(([0], brk + 1, [n]), axis=None)
+        if batch_size is not None and batch_size < n:
+            parts = [np.linspace(lo, hi, num=max(1, int(np.ceil((hi - lo) / batch_size))) + 1, endpoint=True)
+                     for lo, hi in zip(edges[:-1], edges[1:])]
+            edges = np.unique(np.round(np.concatenate(parts, axis=-1)).astype(np.int32))
+        p0, p1, cf = [], [], []
+        for lo, hi in zip(edges[:-1], edges[1:]):
+            st0, _ = render_blocks_oracle(img0, b0[lo:hi], *sec0.sampler())
+            st1, _ = render_blocks_oracle(img1, b1[lo:hi], *sec1.sampler())
+            dx, dy, c = xcorr(st0, st1, conf_mode=conf_mode, pad=use_pad, subpixel=sub)
+            q0, q1 = block_points_oracle(b0[lo:hi], b1[lo:hi], dx, dy)
+            p0.append(q0), p1.append(q1), cf.append(c)
+        p0, p1, cf = np.concatenate(p0, 0), np.concatenate(p1, 0), np.concatenate(cf, 0)
+        if trace is not None:
+            trace.append(dict(spacing=float(sp), pad=bool(use_pad), subpixel=bool(sub), nblocks=int(n), conf=cf.copy(),
+                              xy0=p0.copy(), xy1=p1.copy()))
+        if np.all(cf <= conf_thresh):
+            if not started:
+                return None, None, 0
+            break
+        good = cf > conf_thresh
+        p0, p1, wt = p0[good], p1[good], cf[good].astype(np.float64)
+        max_dis = np.max(np.sum((p0 - p1) ** 2, axis=-1)) ** 0.5
+        nxt = np.searchsorted(-spacings, -4 * max_dis) - 1
+        if nxt > idx:
+            nxt = min(nxt, idx + 1)
+            if pad is None:
+                use_pad = False          # matcher.py:701-705: adjacent level
+            idx = nxt
+        else:
+            if pad is None:
+                use_pad = True
+            idx += 1
+        link = dict(i0=sec0.inv(p0), i1=sec1.inv(p1), w=wt, rw=np.ones_like(wt))
+        if max_dis > 0.1:
+            def relax():
+                a, t = _wls_affine(sec1.fwd(link['i1']), sec0.fwd(link['i0']), link['w'] * link['rw'])
+                sec1.a, sec1.t = sec1.a @ a, sec1.t @ a + t
+            relax()
+            if residue_len > 0:
+                r = np.sum((sec1.fwd(link['i1']) - sec0.fwd(link['i0'])) ** 2, axis=-1) ** 0.5
+                if residue_mode == 'huber':
+                    new = np.where(r > residue_len, residue_len / np.maximum(r, 1e-30), 1.0)
+                else:
+                    new = (r <= residue_len).astype(np.float64)
+                changed = np.any(np.abs(new - link['rw']) > 1e-3)
+                link['rw'] = new
+                if changed and idx < spacings.size:
+                    relax()
+        started = True
+        if idx < spacings.size:
+            sp = spacings[idx]
+    if link is None:
+        return None, None, 0
+    keep = (link['w'] * link['rw']) > 0
+    return link['i0'][keep], link['i1'][keep], (link['w'] * link['rw'])[keep]
+
+
+def stitching_oracle(img0, img1, sigma=2.5, coarse_downsample=1, fine_downsample=1, spacings=None, residue_len=5,
+                     conf_thresh=0.3, min_num_blocks=2, pad=None, residue_mode='huber', xcorr=xcorr_oracle, trace=None):
+    """``stitching_matcher`` (matcher.py:224-367) without masks / photometric output, on the affine section model."""
+    if spacings is None:
+        spacings = auto_spacings_oracle(img0.shape, img1.shape)
+    spacings = np.array(spacings, dtype=np.float64)
+    g0 = resize_area_oracle(img0, coarse_downsample) if coarse_downsample != 1 else img0
+    g1 = resize_area_oracle(img1, coarse_downsample) if coarse_downsample != 1 else img1
+    if sigma > 0:
+        g0 = masked_dog_oracle(g0, sigma * coarse_downsample)
+        g1 = masked_dog_oracle(g1, sigma * coarse_downsample)
+    tx, ty, cf = global_translation_oracle(g0, g1, conf_thresh=conf_thresh, xcorr=xcorr)
+    if trace is not None:
+        trace.append(dict(coarse=(tx, ty, cf)))
+    if cf < conf_thresh:
+        return None, None, conf_thresh
+    if fine_downsample == coarse_downsample:
+        f0, f1 = g0, g1
+    else:
+        f0 = resize_area_oracle(img0, fine_downsample) if fine_downsample != 1 else img0
+        f1 = resize_area_oracle(img1, fine_downsample) if fine_downsample != 1 else img1
+        if sigma > 0:
+            f0 = masked_dog_oracle(f0, sigma * fine_downsample)
+            f1 = masked_dog_oracle(f1, sigma * fine_downsample)
+    tx, ty = tx * fine_downsample / coarse_downsample, ty * fine_downsample / coarse_downsample
+    sec0 = _Section((0, 0, f0.shape[1], f0.shape[0]), locked=True)
+    sec1 = _Section((0, 0, f1.shape[1], f1.shape[0]))
+    sec0.t = np.array([tx, ty], dtype=np.float64)
+    xy0, xy1, wt = surrogate_loop_oracle(sec0, sec1, f0, f1, spacings * fine_downsample, conf_thresh=conf_thresh,
+                                         residue_mode=residue_mode, residue_len=residue_len * fine_downsample,
+                                         min_num_blocks=min_num_blocks, pad=pad, xcorr=xcorr, trace=trace)
+    if xy0 is not None and fine_downsample != 1:
+        xy0 = (xy0 + 0.5) / fine_downsample - 0.5       # spatial.scale_coordinates, spatial.py:77-89
+        xy1 = (xy1 + 0.5) / fine_downsample - 0.5
+    return xy0, xy1, wt
