@@ -93,4 +93,76 @@ template <typename T, bool INV> struct RegFFT<T, 1, INV> {
     static FB_HD void run(cx<T>*) {}
 };
 
+#if defined(__CUDACC__)
+// ---------------------------------------------------------------------------------------------
+// Packed variant for float on sm_100a: a complex number lives in an aligned register pair, so
+// complex add / subtract / scale are ONE FADD2 / FMUL2 (f32x2) instead of two scalar
+// instructions.  The FP32 lanes do the same work, but the issue slots halve -- the column and row
+// kernels are issue bound (profiles/r1: not_selected + selected > 50 % of samples).  Multiplies
+// by -i and the cross terms of general twiddles stay scalar (they mix .x and .y).  Forward only.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ cx<float> padd(cx<float> a, cx<float> b)
+{
+    const float2 r = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
+    return mk<float>(r.x, r.y);
+}
+__device__ __forceinline__ cx<float> psub(cx<float> a, cx<float> b)
+{
+    const float2 r = __fadd2_rn(make_float2(a.x, a.y), make_float2(-b.x, -b.y));
+    return mk<float>(r.x, r.y);
+}
+__device__ __forceinline__ cx<float> pscale(cx<float> a, float s)
+{
+    const float2 r = __fmul2_rn(make_float2(a.x, a.y), make_float2(s, s));
+    return mk<float>(r.x, r.y);
+}
+
+template <int N, int J> __device__ __forceinline__ cx<float> ptwiddle_diff(cx<float> a, cx<float> b)
+{
+    constexpr int j32 = (J * (32 / N)) & 31;
+    if constexpr (j32 == 0) {
+        return psub(a, b);
+    } else if constexpr (j32 == 8) {            // -i (a - b)
+        return mk<float>(a.y - b.y, b.x - a.x);
+    } else if constexpr (j32 == 16) {
+        return psub(b, a);
+    } else if constexpr (j32 == 24) {           // +i (a - b)
+        return mk<float>(b.y - a.y, a.x - b.x);
+    } else if constexpr (j32 == 4) {
+        const cx<float> d = psub(a, b);
+        return pscale(mk<float>(d.x + d.y, d.y - d.x), 0.70710678118654752440f);
+    } else if constexpr (j32 == 12) {
+        const cx<float> d = psub(a, b);
+        return pscale(mk<float>(d.y - d.x, -d.x - d.y), 0.70710678118654752440f);
+    } else {
+        const cx<float> d = psub(a, b);
+        constexpr float c = (float)cos32(j32);
+        constexpr float s = (float)(-sin32(j32));
+        return mk<float>(d.x * c - d.y * s, d.x * s + d.y * c);
+    }
+}
+
+template <int N, int J = 0> struct PDifLevel {
+    static __device__ __forceinline__ void run(cx<float>* v)
+    {
+        const cx<float> a = v[J], b = v[J + N / 2];
+        v[J] = padd(a, b);
+        v[J + N / 2] = ptwiddle_diff<N, J>(a, b);
+        if constexpr (J + 1 < N / 2) PDifLevel<N, J + 1>::run(v);
+    }
+};
+
+template <int N> struct PRegFFT {
+    static __device__ __forceinline__ void run(cx<float>* v)
+    {
+        PDifLevel<N>::run(v);
+        PRegFFT<N / 2>::run(v);
+        PRegFFT<N / 2>::run(v + N / 2);
+    }
+};
+template <> struct PRegFFT<1> {
+    static __device__ __forceinline__ void run(cx<float>*) {}
+};
+#endif
+
 }  // namespace fb

@@ -84,7 +84,9 @@ __global__ void __launch_bounds__(512) fbk_fused(const __grid_constant__ XcParam
 
 
 // ---- register-resident fast path (power-of-two grids, float32 compute) ----
-constexpr int kNW1 = 4, kNW2 = 8;                    // warps per CTA of K1 / K2 (K3: 256 threads)
+constexpr int kNW1 = 4, kNW2 = 8;                    // warps per CTA of K1 / K2
+// K3: lines (= GT tile rows) per CTA for T lanes per line; CTA = T * R threads, 512 threads per SM
+template <int T> constexpr int kR3() { return 8; }
 template <int E, int T, typename TI, bool PRUNED>
 __global__ void __launch_bounds__(32 * kNW1, 16 / kNW1) fbk_fast_rows_forward(const __grid_constant__ FastParams fp)
 {
@@ -97,11 +99,11 @@ __global__ void __launch_bounds__(32 * kNW2, 16 / kNW2) fbk_fast_columns(const _
     extern __shared__ __align__(16) unsigned char smem[];
     kfast_columns<E, T, kNW2, PRUNED>(fp, smem);
 }
-template <int E, int T>
-__global__ void __launch_bounds__(256, 2) fbk_fast_rows_inverse(const __grid_constant__ FastParams fp)
+template <int E, int T, int R>
+__global__ void __launch_bounds__(T * R, 512 / (T * R)) fbk_fast_rows_inverse(const __grid_constant__ FastParams fp)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    kfast_rows_inverse<E, T>(fp, smem);
+    kfast_rows_inverse<E, T, R>(fp, smem);
 }
 
 // ---------------------------------------------------------------------------
@@ -140,6 +142,7 @@ static std::map<int, bool> g_attr_done;
 static long long g_opt_ws_bytes = 2LL << 30;
 static long long g_opt_host_chunk = 64LL << 20;
 static long long g_opt_profile = 0;
+static long long g_opt_fast_flags = 0;       // experiment switches, see FastParams::flags (+16: K2 unbatched twiddles, +32: K3 8 lines)
 
 template <typename T>
 static int get_tables(int device, int n, Plan1D& out)
@@ -167,7 +170,7 @@ static int get_tables(int device, int n, Plan1D& out)
     return FB_OK;
 }
 
-static std::map<std::tuple<int, int, int>, void*> g_wtables;           // (device, n, T) -> cx<float>[E][T]
+static std::map<std::tuple<int, int, int>, void*> g_wtables;           // (device, n, T) -> cx<float>[E / 2][T][2]
 
 static int get_warp_table(int device, int n, int T, const cx<float>*& out)
 {
@@ -179,8 +182,9 @@ static int get_warp_table(int device, int n, int T, const cx<float>*& out)
         for (int k1 = 0; k1 < E; ++k1)
             for (int t = 0; t < T; ++t) {
                 long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)((k1 * t) % n) / (long double)n;
-                tw[(size_t)k1 * T + t].x = (float)std::cos(a);
-                tw[(size_t)k1 * T + t].y = (float)std::sin(a);
+                const size_t slot = ((size_t)(k1 / 2) * T + t) * 2 + (k1 & 1);     // rows (k1, k1 + 1) paired per lane
+                tw[slot].x = (float)std::cos(a);
+                tw[slot].y = (float)std::sin(a);
             }
         void* d = nullptr;
         CU(cudaMalloc(&d, tw.size() * sizeof(cx<float>)));
@@ -224,10 +228,11 @@ static int set_attrs(int device)
     RS((fbk_fast_rows_forward<E, T, unsigned char, false>)); \
     RS((fbk_fast_columns<E, T, true>));                      \
     RS((fbk_fast_columns<E, T, false>));                     \
-    RS((fbk_fast_rows_inverse<E, T>))
+    RS((fbk_fast_rows_inverse<E, T, kR3<T>()>))
     RSF(16, 16);
     RSF(32, 16);
     RSF(32, 32);
+    RS((fbk_fast_rows_inverse<32, 32, 4>));
 #undef RSF
 #undef RS
     g_attr_done[device] = true;
@@ -343,7 +348,7 @@ static void fast_et(int n, int& E, int& T)
 static size_t fast_smem(int n, int nw)
 {
     int E, T; fast_et(n, E, T);
-    return ((size_t)nw * (32 / T) * (n + E + 16) + n) * sizeof(cx<float>);
+    return ((size_t)nw * (32 / T) * (n + E + 16) + (kLaneTwiddles ? 0 : n)) * sizeof(cx<float>);
 }
 
 static int g_num_sms = 0;
@@ -365,7 +370,10 @@ static int launch_fast(const Problem& q, StreamCtx& ctx, XcParams& p, int nb, cu
     fp.FT1 = reinterpret_cast<cx<float>*>(w + f0);
     fp.GT = reinterpret_cast<cx<float>*>(w + f0 + f1);
     p.part = reinterpret_cast<Partial*>(w + f0 + f1 + gg);
-    p.G = fp.GT; p.gt_layout = 1; p.nrt = q.nrt;
+    fp.rblk = TX == 32 ? kR3<32>() : kR3<16>();          // rows per K3 tile
+    if (TX == 32 && (g_opt_fast_flags & 32)) fp.rblk = 4;
+    fp.flags = (int)(g_opt_fast_flags & (15 | 64 | 128));
+    p.G = fp.GT; p.gt_layout = fp.rblk; p.nrt = q.nrt; p.out_scale = p.scale;
     fp.hp0 = q.hp0; fp.hp1 = q.hp1;
     fp.x = p;
     // K1
@@ -392,18 +400,19 @@ static int launch_fast(const Problem& q, StreamCtx& ctx, XcParams& p, int nb, cu
         else if (q.ny == 512) launch_fast_k2<32, 16>(fp, pruned, grid, fast_smem(512, kNW2), st);
         else launch_fast_k2<32, 32>(fp, pruned, grid, fast_smem(1024, kNW2), st);
     }
-    // K3: 256 threads own R = 256 / TX lines
+    // K3: TX * R threads own R lines
     {
-        const int R = 256 / TX;
-        const int work = nb * ((q.nrt + R - 1) / R);
-        const int cap = g_num_sms * 2;
+        const int R = fp.rblk, nt = TX * R;
+        const int work = nb * (q.nrt / R);
+        const int cap = g_num_sms * (512 / nt);
         const int grid = work < cap ? work : cap;
-        const int XS = TX * R + (R == 8 ? 8 : 0);
-        const size_t sm3 = ((size_t)EX * XS + q.nx) * sizeof(cx<float>) + 8 * R * 2 * (sizeof(float) + sizeof(double));
+        const int XS = TX * R + (R < 16 ? R : 0);
+        const size_t sm3 = ((size_t)EX * XS + (kLaneTwiddles ? 0 : q.nx)) * sizeof(cx<float>) + (nt / 32) * R * 2 * (sizeof(float) + sizeof(double));
         ProfScope ps(ctx, st, SLOT_ROWS_INV);
-        if (q.nx == 256) fbk_fast_rows_inverse<16, 16><<<grid, 256, sm3, st>>>(fp);
-        else if (q.nx == 512) fbk_fast_rows_inverse<32, 16><<<grid, 256, sm3, st>>>(fp);
-        else fbk_fast_rows_inverse<32, 32><<<grid, 256, sm3, st>>>(fp);
+        if (q.nx == 256) fbk_fast_rows_inverse<16, 16, kR3<16>()><<<grid, nt, sm3, st>>>(fp);
+        else if (q.nx == 512) fbk_fast_rows_inverse<32, 16, kR3<16>()><<<grid, nt, sm3, st>>>(fp);
+        else if (R == 4) fbk_fast_rows_inverse<32, 32, 4><<<grid, nt, sm3, st>>>(fp);
+        else fbk_fast_rows_inverse<32, 32, kR3<32>()><<<grid, nt, sm3, st>>>(fp);
     }
     {
         ProfScope ps(ctx, st, SLOT_FINALIZE);
@@ -430,6 +439,7 @@ static int launch_chunk(const Problem& q, StreamCtx& ctx, const void* img0, cons
     p.h0 = q.h0; p.w0 = q.w0; p.h1 = q.h1; p.w1 = q.w1; p.ny = q.ny; p.nx = q.nx; p.kp = g.kp;
     p.fpitch = g.fpitch; p.dx = dx; p.dy = dy; p.conf = conf; p.peak = peak; p.mir = mir;
     p.conf_mode = q.conf_mode; p.subpixel = q.subpixel; p.scale = 1.0 / ((double)q.ny * (double)q.nx);
+    p.out_scale = 1.0;
     if (q.fused) {
         p.tl = g.tl_fused; p.spitch = g.spitch;
         int nthr = g.smem_fused > 100 * 1024 ? 512 : 256;
@@ -672,6 +682,7 @@ extern "C" int fb_set_option(const char* name, long long value)
     std::lock_guard<std::mutex> lk(g_mu);
     if (!strcmp(name, "ws_bytes")) { if (value < (1 << 20)) return fail(FB_EINVAL, "ws_bytes too small"); g_opt_ws_bytes = value; return FB_OK; }
     if (!strcmp(name, "profile")) { g_opt_profile = value ? 1 : 0; return FB_OK; }
+    if (!strcmp(name, "fast_flags")) { g_opt_fast_flags = value; return FB_OK; }
     if (!strcmp(name, "host_chunk_bytes")) { if (value < 4096) return fail(FB_EINVAL, "host_chunk_bytes too small"); g_opt_host_chunk = value; return FB_OK; }
     return fail(FB_EINVAL, "unknown option %s", name);
 }

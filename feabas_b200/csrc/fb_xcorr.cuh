@@ -58,11 +58,14 @@ struct XcParams {
     int conf_mode;
     int subpixel;
     double scale;         // 1 / (ny * nx)
+    double out_scale;     // K4: factor applied to the reported peak / mirror maxima (fast path: the surfaces
+                          //     in G are unscaled, out_scale = scale; otherwise 1)
     int tl;               // lines per row tile
     int tc;               // columns per image per column tile
     int spitch;           // fused: row pitch of the resident spectra
-    int gt_layout;        // K4: G holds the fast path's transposed, conjugated surfaces and the
-                          //     partial's idx only identifies the ROW of the maximum
+    int gt_layout;        // K4: != 0: G holds the fast path's conjugated surfaces, tiled
+                          //     [ny / gt_layout][P|Q][kx][gt_layout] (gt_layout = rows per K3 tile), and
+                          //     the partial's idx only identifies the ROW of the maximum
 };
 
 template <typename T> struct Acc {
@@ -303,8 +306,10 @@ FB_DEV void finalize_pair(const XcParams& p, int pair, const Acc<T>& best, const
             int l = idx / kp, k = idx - l * kp;
             int y = py - 1 + l;
             y = y < 0 ? y + ny : (y >= ny ? y - ny : y);
-            rows_inverse_fill<T>(p, Pb + (size_t)y * rpitch, mirror ? Qb + (size_t)y * rpitch : nullptr,
-                                 s, pitch, l, k, kp, ks);
+            // tiled fast-path layout: row y starts at (y / R) * 2 kp R + y % R, R = gt_layout
+            const size_t ro = p.gt_layout ? (size_t)(y / p.gt_layout) * 2 * kp * p.gt_layout + (y % p.gt_layout)
+                                          : (size_t)y * rpitch;
+            rows_inverse_fill<T>(p, Pb + ro, mirror ? Qb + ro : nullptr, s, pitch, l, k, kp, ks);
         }
         FB_SYNC();
         fft_lines<T, true>(p.px, s, pitch, 3, tid, nthr);
@@ -364,8 +369,8 @@ FB_DEV void finalize_pair(const XcParams& p, int pair, const Acc<T>& best, const
             conf = c;
         }
         p.dx[pair] = dx; p.dy[pair] = dy; p.conf[pair] = conf;
-        if (p.peak) p.peak[pair] = (double)best.val;
-        if (p.mir) p.mir[pair] = (double)best.mir;
+        if (p.peak) p.peak[pair] = (double)best.val * p.out_scale;
+        if (p.mir) p.mir[pair] = (double)best.mir * p.out_scale;
     }
     FB_SYNC();
 }
@@ -463,10 +468,10 @@ FB_DEV void k4_finalize(const XcParams& p, int bid, int tid, int nthr, unsigned 
     }
     Acc<T> best = block_reduce<T>(acc, red, tid, nthr);
     if (p.gt_layout) {
-        // fast path: conjugated G^T[pair][P|Q][kx][y]
+        // fast path: conjugated, tiled G^T[pair][ny / R][P|Q][kx][R]
         const size_t plane = (size_t)p.kp * p.ny;
         const cx<T>* Pb = reinterpret_cast<const cx<T>*>(p.G) + (size_t)bid * 2 * plane;
-        finalize_pair<T>(p, bid, best, Pb, Pb + plane, 1, mirror, s, tid, nthr, (size_t)p.ny);
+        finalize_pair<T>(p, bid, best, Pb, Pb + (size_t)p.kp * p.gt_layout, 0, mirror, s, tid, nthr, (size_t)p.gt_layout);
         return;
     }
     const cx<T>* Pb = reinterpret_cast<const cx<T>*>(p.G) + (size_t)bid * p.ny * 2 * p.fpitch;

@@ -21,6 +21,92 @@
 
 namespace fb {
 
+// The stage-A twiddles w_N^(k1 t) of a lane (fixed t, k1 = 0..E-1) held in REGISTERS for the life of
+// the kernel: k1 = 8 a + b, w^(k1 t) = w^(8 a t) w^(b t), i.e. 7 + (E/8 - 1) complex values per lane
+// instead of an E-entry shared-memory row per transform.  The kernels are bound by the LSU /
+// shared-memory pipe (profiles/r1: l1tex 70-78 % busy, FP32 40 %): this trades 2 E wavefronts per
+// transform for ~E extra complex multiplies.
+template <int E> struct LaneTw {
+    static constexpr int NA = E / 8;
+    cx<float> b[8];      // b[j] = w^(j t), j = 1..7
+    cx<float> a[NA];     // a[i] = w^(8 i t), i = 1..NA-1
+    // tab: [E / 2][T][2] paired table (fb_xcorr.cu get_warp_table)
+    template <int T> __device__ __forceinline__ void load(const cx<float>* tab, int t)
+    {
+#pragma unroll
+        for (int j = 1; j < 8; ++j) b[j] = ldg(tab + ((j / 2) * T + t) * 2 + (j & 1));
+#pragma unroll
+        for (int i = 1; i < NA; ++i) a[i] = ldg(tab + ((8 * i / 2) * T + t) * 2);
+    }
+    __device__ __forceinline__ cx<float> apply(cx<float> z, int k1) const
+    {
+        const int ia = k1 >> 3, ib = k1 & 7;       // compile-time after unrolling
+        if (ib) z = cmul(z, b[ib]);
+        if (ia) z = cmul(z, a[ia]);
+        return z;
+    }
+};
+
+// The same twiddles read from a shared-memory copy of the table instead (paired rows, one LDS.128 per
+// two outputs, fetched a batch ahead of use).  Cheaper in FP32 work, dearer in LSU wavefronts; the
+// two variants measure within 1 % of each other on B200 (profiles/r1/sweeps.md), this one slightly ahead.
+template <int E, int T> struct SmemTw {
+    const float4* tw4;   // + t applied
+    __device__ __forceinline__ void init(const cx<float>* smem_table, int t) { tw4 = reinterpret_cast<const float4*>(smem_table) + t; }
+    // out(k1, value) stores the twiddled value of output k1
+    template <typename F> __device__ __forceinline__ void apply_all(const cx<float>* v, F out) const
+    {
+        constexpr int TB = 4, NB = E / 2 / TB;
+        float4 wq[2][TB];
+#pragma unroll
+        for (int i = 0; i < TB; ++i) wq[0][i] = tw4[i * T];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            if (b + 1 < NB) {
+#pragma unroll
+                for (int i = 0; i < TB; ++i) wq[(b + 1) & 1][i] = tw4[((b + 1) * TB + i) * T];
+            }
+#pragma unroll
+            for (int i = 0; i < TB; ++i) {
+                const int k1 = 2 * (b * TB + i);
+                const float4 w = wq[b & 1][i];
+                cx<float> a0 = v[brev<E>(k1)], a1 = v[brev<E>(k1 + 1)];
+                if (k1) a0 = cmul(a0, mk<float>(w.x, w.y));
+                a1 = cmul(a1, mk<float>(w.z, w.w));
+                out(k1, a0);
+                out(k1 + 1, a1);
+            }
+        }
+    }
+};
+
+constexpr bool kLaneTwiddles = false;     // true: LaneTw (registers), false: SmemTw (shared-memory table)
+template <int E, int T> struct StageTw {
+    LaneTw<E> lane;
+    SmemTw<E, T> sm;
+    // table: global [E/2][T][2]; smem_table: room for E * T entries (unused with lane twiddles)
+    __device__ __forceinline__ void init(const cx<float>* table, cx<float>* smem_table, int t, int tid, int nthr)
+    {
+        if constexpr (kLaneTwiddles) {
+            lane.template load<T>(table, t);
+        } else {
+            for (int i = tid; i < E * T; i += nthr) smem_table[i] = table[i];
+            sm.init(smem_table, t);
+            __syncthreads();
+        }
+    }
+    template <typename F> __device__ __forceinline__ void apply_all(const cx<float>* v, F out) const
+    {
+        if constexpr (kLaneTwiddles) {
+#pragma unroll
+            for (int k1 = 0; k1 < E; ++k1) out(k1, lane.apply(v[brev<E>(k1)], k1));
+        } else {
+            sm.apply_all(v, out);
+        }
+    }
+    static constexpr __host__ __device__ int smem_entries() { return kLaneTwiddles ? 0 : E * T; }
+};
+
 template <int E, int T> struct WarpFFT {
     static_assert(T == 16 || T == 32, "lanes per line");
     static_assert(E % T == 0 && E / T <= 2, "E/T stage-B transforms per lane");
@@ -42,20 +128,15 @@ template <int E, int T> struct WarpFFT {
     // conjugations folded into the neighbouring point-wise steps, so that every kernel
     // runs ONE butterfly body (instruction-cache footprint).
     template <bool PRUNED>
-    static __device__ __forceinline__ void run(cx<float>* v, cx<float>* region, const cx<float>* tw, int t,
+    static __device__ __forceinline__ void run(cx<float>* v, cx<float>* region, const StageTw<E, T>& tw, int t,
                                                bool pruned_now = true)
     {
         // first radix-2 level: skipped arithmetic when the upper half of the input is zero; the
         // remaining levels are one shared body
-        if (PRUNED && pruned_now) DifLevelPruned<float, E, false>::run(v); else DifLevel<float, E, false>::run(v);
-        RegFFT<float, E / 2, false>::run(v);
-        RegFFT<float, E / 2, false>::run(v + E / 2);
-#pragma unroll
-        for (int k1 = 0; k1 < E; ++k1) {
-            cx<float> a = v[brev<E>(k1)];
-            if (k1) a = cmul(a, tw[k1 * T + t]);
-            region[k1 * (T + 1) + t] = a;
-        }
+        if (PRUNED && pruned_now) DifLevelPruned<float, E, false>::run(v); else PDifLevel<E>::run(v);
+        PRegFFT<E / 2>::run(v);
+        PRegFFT<E / 2>::run(v + E / 2);
+        tw.apply_all(v, [&](int k1, cx<float> a) { region[k1 * (T + 1) + t] = a; });
         __syncwarp();
 #pragma unroll
         for (int m = 0; m < M; ++m) {
@@ -64,7 +145,7 @@ template <int E, int T> struct WarpFFT {
         }
         __syncwarp();
 #pragma unroll
-        for (int m = 0; m < M; ++m) RegFFT<float, T, false>::run(v + m * T);
+        for (int m = 0; m < M; ++m) PRegFFT<T>::run(v + m * T);
     }
 };
 
@@ -74,16 +155,31 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc)
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc));
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+// one instruction: pull a contiguous, 16-byte aligned chunk (bytes % 16 == 0) into L2 ahead of use
+__device__ __forceinline__ void prefetch_l2_bulk(const void* gsrc, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(gsrc), "r"(bytes) : "memory");
+}
 
 struct FastParams {
     XcParams x;
-    const cx<float>* twx;   // [EX][TX] w_nx^(k1 t)
-    const cx<float>* twy;   // [EY][TY]
+    const cx<float>* twx;   // [EX / 2][TX][2]: w_nx^(k1 t) with rows (k1, k1 + 1) paired per lane
+    const cx<float>* twy;   // [EY / 2][TY][2]
     cx<float>* FT0;         // [n][kp][hp0]
     cx<float>* FT1;         // [n][kp][hp1]
-    cx<float>* GT;          // [n][2][kp][ny]: conjugate of the column-stage output, y contiguous
+    cx<float>* GT;          // [n][ny / rblk][P|Q][kp][rblk]: conjugate of the column-stage output, tiled so
+                            // that the rblk rows one K3 CTA owns are ONE contiguous chunk (all kx)
     int hp0, hp1;
+    int rblk;               // rows per K3 tile, a power of two <= 16
+    int flags;              // experiment switches (fb_set_option "fast_flags"): 1/2/4 = no L2 prefetch in
+                            // K1/K2/K3, 8 = K2 partners are warps (w, w + NW/2) instead of (2w, 2w+1)
 };
+
+// element offset of (row y, column 0, plane P) inside a pair's GT block
+__device__ __forceinline__ size_t gt_row_offset(int y, int kp, int rblk)
+{
+    return (size_t)(y / rblk) * 2 * kp * rblk + (y % rblk);
+}
 
 // ---------------------------------------------------------------------------------------------
 // K1: forward row transforms, two image rows per complex line, transposed half-spectrum out.
@@ -97,11 +193,10 @@ __device__ void kfast_rows_forward(const FastParams& fp, unsigned char* smem)
     constexpr int RS = W::stride_mod16(LPC >= 16 ? 1 : 16 / LPC);
     const XcParams& p = fp.x;
     cx<float>* regions = reinterpret_cast<cx<float>*>(smem);
-    cx<float>* tw = regions + LPC * RS;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int t = lane % T, lw = lane / T;                 // lane within line, line within warp
-    for (int i = tid; i < N; i += NT) tw[i] = fp.twx[i];
-    __syncthreads();
+    StageTw<E, T> tw;
+    tw.init(fp.twx, regions + LPC * RS, t, tid, NT);
     const int tiles0 = fp.hp0 / TR, tiles1 = fp.hp1 / TR, tpp = tiles0 + tiles1;
     const int kp = p.kp;
     for (int work = blockIdx.x; work < p.n * tpp; work += gridDim.x) {
@@ -113,6 +208,24 @@ __device__ void kfast_rows_forward(const FastParams& fp, unsigned char* smem)
         const TI* img = reinterpret_cast<const TI*>(second ? p.img1 : p.img0) + (size_t)pair * H * Wd;
         cx<float>* FT = (second ? fp.FT1 : fp.FT0) + (size_t)pair * kp * hp;
         const int row0 = tile * TR;
+        if (tid == 0 && !(fp.flags & 1)) {                 // next tile of this CTA -> L2 (rows are contiguous)
+            const int nw_ = work + gridDim.x;
+            if (nw_ < p.n * tpp) {
+                const int np = nw_ / tpp;
+                int nt = nw_ - np * tpp;
+                const bool ns = nt >= tiles0;
+                if (ns) nt -= tiles0;
+                const int nH = ns ? p.h1 : p.h0, nW = ns ? p.w1 : p.w0;
+                const TI* nimg = reinterpret_cast<const TI*>(ns ? p.img1 : p.img0) + (size_t)np * nH * nW + (size_t)nt * TR * nW;
+                int rows = nH - nt * TR; rows = rows > TR ? TR : rows;
+                if (rows > 0) {
+                    size_t a = reinterpret_cast<size_t>(nimg);
+                    size_t e = (a + (size_t)rows * nW * sizeof(TI)) & ~(size_t)15;
+                    a = (a + 15) & ~(size_t)15;
+                    if (e > a) prefetch_l2_bulk(reinterpret_cast<const void*>(a), (unsigned)(e - a));
+                }
+            }
+        }
         const int line = warp * LPW + lw;                  // line within the tile
         const int rA = row0 + 2 * line, rB = rA + 1;
         cx<float>* region = regions + line * RS;
@@ -156,7 +269,7 @@ __device__ void kfast_rows_forward(const FastParams& fp, unsigned char* smem)
 }
 
 // ---------------------------------------------------------------------------------------------
-// K2: column stage.  Warp w < NW/2 transforms the F0 column(s), warp w + NW/2 the same F1
+// K2: column stage.  Warp 2 pw transforms the F0 column(s), warp 2 pw + 1 the same F1
 // column(s); they swap spectra through shared memory, form conj(P) = F0 conj(F1) and
 // conj(Q) = conj(F0) conj(F1), and transform again (forward transform of the conjugate =
 // conjugate of the inverse transform; consumers undo the conjugation).  The two transforms of a
@@ -170,32 +283,41 @@ __device__ void kfast_columns(const FastParams& fp, unsigned char* smem)
     constexpr int N = W::N, LPW = W::LPW, RS = W::RS, CPG = LPW * (NW / 2), NT = 32 * NW;   // CPG columns per CTA
     const XcParams& p = fp.x;
     cx<float>* regions = reinterpret_cast<cx<float>*>(smem);
-    cx<float>* tw = regions + NW * LPW * RS;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int t = lane % T, lw = lane / T;
-    const bool roleB = warp >= NW / 2;
-    const int pw = roleB ? warp - NW / 2 : warp;           // pair-of-warps index
-    for (int i = tid; i < N; i += NT) tw[i] = fp.twy[i];
-    __syncthreads();
+    StageTw<E, T> tw;
+    tw.init(fp.twy, regions + NW * LPW * RS, t, tid, NT);
+    // partners are ADJACENT warps (2 pw, 2 pw + 1): they sit on different SM sub-partitions, so the
+    // four warps an SMSP schedules belong to four different pairs and drift through the
+    // FP-only and shared-memory-only phases independently
+    const bool split = fp.flags & 8;
+    const bool roleB = split ? warp >= NW / 2 : (warp & 1);
+    const int pw = split ? (roleB ? warp - NW / 2 : warp) : warp >> 1;   // pair-of-warps index
     const bool mirror = p.conf_mode == CONF_MIRROR;
     const int kp = p.kp, groups = (kp + CPG - 1) / CPG;
-    const float sc = (float)p.scale;
-    const float sgn = roleB ? -sc : sc;
     cx<float>* mine = regions + (warp * LPW + lw) * RS;
-    cx<float>* other = regions + ((roleB ? pw : pw + NW / 2) * LPW + lw) * RS;
+    cx<float>* other = regions + ((split ? (roleB ? pw : pw + NW / 2) : (warp ^ 1)) * LPW + lw) * RS;
     const int hp = roleB ? fp.hp1 : fp.hp0;
     const bool second_phase = !roleB || mirror;
     for (int work = blockIdx.x; work < p.n * groups; work += gridDim.x) {
         const int pair = work / groups, grp = work - pair * groups;
         const int col = grp * CPG + pw * LPW + lw;
         const bool live = col < kp;
+        if (lane == 0 && pw == 0 && !(fp.flags & 2)) {     // the CTA's next column group (contiguous in FT) -> L2
+            const int nw_ = work + gridDim.x;
+            if (nw_ < p.n * groups) {
+                const int np = nw_ / groups, ng = nw_ - np * groups;
+                int nc = kp - ng * CPG; nc = nc > CPG ? CPG : nc;
+                prefetch_l2_bulk((roleB ? fp.FT1 : fp.FT0) + ((size_t)np * kp + (size_t)ng * CPG) * hp, (unsigned)(nc * hp * 8));
+            }
+        }
         const cx<float>* src = (roleB ? fp.FT1 : fp.FT0) + ((size_t)pair * kp + (live ? col : 0)) * hp;
         cx<float> v[E];
 #pragma unroll
         for (int n1 = 0; n1 < E; ++n1) {
             const int y = n1 * T + t;
             cx<float> a = mk<float>(0.f, 0.f);
-            if ((!PRUNED0 || n1 < E / 2) && y < hp) a = ldg(src + y);
+            if ((!PRUNED0 || n1 < E / 2) && y < hp && !(fp.flags & 128)) a = ldg(src + y);
             v[n1] = a;
         }
 #pragma unroll 1
@@ -207,20 +329,30 @@ __device__ void kfast_columns(const FastParams& fp, unsigned char* smem)
                 asm volatile("bar.sync %0, 64;" ::"r"(pw + 1) : "memory");
                 // the output of lane t, k = t + T j, is exactly the input element n1 = j of the
                 // next transform: a register permutation, no exchange needed
+                // unscaled: 1 / (ny nx) is applied once per pair by the finalize kernel (XcParams::out_scale);
+                // confidence and sub-pixel offsets are ratios
                 cx<float> u[E];
+                if (!roleB) {
 #pragma unroll
-                for (int j = 0; j < E; ++j) {
-                    const cx<float> o = other[W::out_k(t, j)], m = v[W::out_reg(j)];
-                    u[j] = cmulc(mk<float>(m.x * sc, m.y * sgn), o);
+                    for (int j = 0; j < E; ++j) u[j] = cmulc(v[W::out_reg(j)], other[W::out_k(t, j)]);      // conj(P) = F0 conj(F1)
+                } else {
+#pragma unroll
+                    for (int j = 0; j < E; ++j) {                                                         // conj(Q) = conj(F1 F0)
+                        const cx<float> o = other[W::out_k(t, j)], m = v[W::out_reg(j)];
+                        u[j] = mk<float>(m.x * o.x - m.y * o.y, -(m.x * o.y) - m.y * o.x);
+                    }
                 }
 #pragma unroll
                 for (int j = 0; j < E; ++j) v[j] = u[j];
                 asm volatile("bar.sync %0, 64;" ::"r"(pw + 1) : "memory");
                 if (!second_phase) break;
-            } else if (live) {
-                cx<float>* dst = fp.GT + (((size_t)pair * 2 + (roleB ? 1 : 0)) * kp + col) * N;
+            } else if (live && !(fp.flags & 64)) {
+                // y = t + c, c a multiple of T >= rblk: the tile index advances by c / rblk
+                const int R = fp.rblk;
+                cx<float>* dst = fp.GT + (size_t)pair * 2 * kp * N + gt_row_offset(t, kp, R) + ((size_t)(roleB ? kp : 0) + col) * R;
+                const size_t cs = (size_t)2 * kp;
 #pragma unroll
-                for (int j = 0; j < E; ++j) dst[W::out_k(t, j)] = v[W::out_reg(j)];
+                for (int j = 0; j < E; ++j) dst[(W::out_k(t, j) - t) * cs] = v[W::out_reg(j)];
             }
         }
     }
@@ -228,7 +360,7 @@ __device__ void kfast_columns(const FastParams& fp, unsigned char* smem)
 
 // ---------------------------------------------------------------------------------------------
 // K3: inverse row transforms + per-line maxima, row-batched.  A line is (P row y, Q row y) with
-// the mirror term, else (P row y, P row y+1).  The CTA (256 threads) owns R = 256 / T consecutive
+// the mirror term, else (P row y, P row y+1).  The CTA (T * R threads) owns R consecutive
 // lines.  Stage A: thread (t, r) -- r minor, so a lane group reads R consecutive y of one GT
 // column, contiguous -- assembles conj(Z)[n1 T + t] of line r from the (conjugated) P / Q
 // columns by Hermitian extension, radix-E in registers, twiddles, writes X[k1][t][r].
@@ -237,19 +369,21 @@ __device__ void kfast_columns(const FastParams& fp, unsigned char* smem)
 // row = -Im.  Only per-line maxima are produced; the finalize kernel locates x inside the
 // winning row (np.argmax order: lowest row, then lowest x).
 // ---------------------------------------------------------------------------------------------
-template <int E, int T>
+template <int E, int T, int R>
 __device__ void kfast_rows_inverse(const FastParams& fp, unsigned char* smem)
 {
-    constexpr int N = E * T, R = 256 / T, M = E / T;
-    constexpr int XS = T * R + (R == 8 ? 8 : 0);              // k1 stride of the exchange tile
+    static_assert(R == 4 || R == 8 || R == 16, "lines per CTA");
+    constexpr int N = E * T, M = E / T, NT = T * R, NWARP = NT / 32;   // R == fp.rblk
+    constexpr int XS = T * R + (R < 16 ? R : 0);              // k1 stride of the exchange tile (conflict free)
     const XcParams& p = fp.x;
     cx<float>* X = reinterpret_cast<cx<float>*>(smem);
-    cx<float>* tw = X + E * XS;
-    float* red = reinterpret_cast<float*>(tw + N);            // [8 warps][R][2] floats + doubles after
-    double* redd = reinterpret_cast<double*>(red + 8 * R * 2);
+    cx<float>* twsm = X + E * XS;
+    float* red = reinterpret_cast<float*>(twsm + StageTw<E, T>::smem_entries());   // [NWARP][R][2] floats + doubles after
+    double* redd = reinterpret_cast<double*>(red + NWARP * R * 2);
     const int tid = threadIdx.x, warp = tid >> 5;
     const int r = tid % R, tq = tid / R;                      // stage A: t = tq; stage B: k1 = tq + T m
-    for (int i = tid; i < N; i += 256) tw[i] = fp.twx[i];
+    StageTw<E, T> tw;
+    tw.init(fp.twx, twsm, tq, tid, NT);
     const bool mirror = p.conf_mode == CONF_MIRROR, want_std = p.conf_mode == CONF_STD;
     const int ny = p.ny, kp = p.kp;
     const int lines_pp = mirror ? ny : (ny + 1) / 2;          // lines per pair
@@ -257,14 +391,24 @@ __device__ void kfast_rows_inverse(const FastParams& fp, unsigned char* smem)
     const size_t plane = (size_t)kp * ny;
     for (int work = blockIdx.x; work < p.n * tiles; work += gridDim.x) {
         const int pair = work / tiles, tile = work - pair * tiles;
-        const int gl = tile * R + r;                           // line index inside the pair
-        const bool live = gl < lines_pp;
-        const int y0 = mirror ? gl : 2 * gl;
-        const bool have2 = live && (mirror || (y0 + 1 < ny));
-        const float h1 = live ? 1.f : 0.f, h2 = have2 ? 1.f : 0.f;
-        const cx<float>* A = fp.GT + (size_t)pair * 2 * plane + (live ? y0 : 0);
-        const cx<float>* B = have2 ? (mirror ? A + plane : A + 1) : A;
-        __syncthreads();                                       // X free (and tw visible)
+        const int gl = tile * R + r;                           // line index inside the pair (always live:
+        const int y0 = mirror ? gl : 2 * gl;                   //  R divides the power-of-two line count)
+        const cx<float>* A = fp.GT + (size_t)pair * 2 * plane + gt_row_offset(y0, kp, R);
+        const cx<float>* B = mirror ? A + (size_t)kp * R : A + 1;
+        if (tid == 0 && !(fp.flags & 4)) {                     // the CTA's next tile is one contiguous chunk -> L2
+            const int nw_ = work + gridDim.x;
+            if (nw_ < p.n * tiles) {
+                const int np = nw_ / tiles, nt = nw_ - np * tiles;
+                const cx<float>* nb = fp.GT + (size_t)np * 2 * plane;
+                if (mirror) {
+                    prefetch_l2_bulk(nb + (size_t)nt * 2 * kp * R, (unsigned)(2 * kp * R * 8));
+                } else {
+                    prefetch_l2_bulk(nb + (size_t)(2 * nt) * 2 * kp * R, (unsigned)(kp * R * 8));
+                    prefetch_l2_bulk(nb + (size_t)(2 * nt + 1) * 2 * kp * R, (unsigned)(kp * R * 8));
+                }
+            }
+        }
+        __syncthreads();                                       // X free
         {
             const int t = tq;
             cx<float> v[E];
@@ -273,26 +417,19 @@ __device__ void kfast_rows_inverse(const FastParams& fp, unsigned char* smem)
                 const int k = n1 * T + t;
                 cx<float> z;
                 if (n1 < E / 2 || (n1 == E / 2 && t == 0)) {
-                    cx<float> a = ldg(A + (size_t)k * ny), b = ldg(B + (size_t)k * ny);
-                    a = mk<float>(a.x * h1, a.y * h1); b = mk<float>(b.x * h2, b.y * h2);
+                    const cx<float> a = ldg(A + (size_t)k * R), b = ldg(B + (size_t)k * R);
                     // conj(P + iQ) with stored a = conj(P), b = conj(Q):  a - i b
                     z = (k == 0 || 2 * k == N) ? mk<float>(a.x, -b.x) : mk<float>(a.x + b.y, a.y - b.x);
                 } else {
                     const int m = N - k;
-                    cx<float> a = ldg(A + (size_t)m * ny), b = ldg(B + (size_t)m * ny);
-                    a = mk<float>(a.x * h1, a.y * h1); b = mk<float>(b.x * h2, b.y * h2);
+                    const cx<float> a = ldg(A + (size_t)m * R), b = ldg(B + (size_t)m * R);
                     // conj(conj(P) + i conj(Q)) = P - i Q = conj(a) - i conj(b)
                     z = mk<float>(a.x - b.y, -a.y - b.x);
                 }
                 v[n1] = z;
             }
-            RegFFT<float, E, false>::run(v);
-#pragma unroll
-            for (int k1 = 0; k1 < E; ++k1) {
-                cx<float> a = v[brev<E>(k1)];
-                if (k1) a = cmul(a, tw[k1 * T + t]);
-                X[k1 * XS + t * R + r] = a;
-            }
+            PRegFFT<E>::run(v);
+            tw.apply_all(v, [&](int k1, cx<float> a) { X[k1 * XS + t * R + r] = a; });
         }
         __syncthreads();
         float best, second;
@@ -306,7 +443,7 @@ __device__ void kfast_rows_inverse(const FastParams& fp, unsigned char* smem)
                 for (int n2 = 0; n2 < T; ++n2) u[m * T + n2] = X[k1 * XS + n2 * R + r];
             }
 #pragma unroll
-            for (int m = 0; m < M; ++m) RegFFT<float, T, false>::run(u + m * T);
+            for (int m = 0; m < M; ++m) PRegFFT<T>::run(u + m * T);
             best = u[0].x; second = mirror ? fabsf(u[0].y) : -u[0].y;
 #pragma unroll
             for (int j = 1; j < E; ++j) {
@@ -317,11 +454,11 @@ __device__ void kfast_rows_inverse(const FastParams& fp, unsigned char* smem)
 #pragma unroll
                 for (int j = 0; j < E; ++j) {
                     sum += (double)u[j].x; sumsq += (double)u[j].x * (double)u[j].x;
-                    if (have2 && !mirror) { sum -= (double)u[j].y; sumsq += (double)u[j].y * (double)u[j].y; }
+                    if (!mirror) { sum -= (double)u[j].y; sumsq += (double)u[j].y * (double)u[j].y; }
                 }
             }
         }
-        // lanes with equal r inside the warp, then the 8 warps through shared memory
+        // lanes with equal r inside the warp, then the warps through shared memory
 #pragma unroll
         for (int off = R; off < 32; off <<= 1) {
             best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, off));
@@ -336,8 +473,8 @@ __device__ void kfast_rows_inverse(const FastParams& fp, unsigned char* smem)
             if (want_std) { redd[(warp * R + r) * 2] = sum; redd[(warp * R + r) * 2 + 1] = sumsq; }
         }
         __syncthreads();
-        if (tid < R && live) {
-            for (int w = 1; w < 8; ++w) {
+        if (tid < R) {
+            for (int w = 1; w < NWARP; ++w) {
                 best = fmaxf(best, red[(w * R + r) * 2]); second = fmaxf(second, red[(w * R + r) * 2 + 1]);
                 if (want_std) { sum += redd[(w * R + r) * 2]; sumsq += redd[(w * R + r) * 2 + 1]; }
             }
@@ -345,7 +482,7 @@ __device__ void kfast_rows_inverse(const FastParams& fp, unsigned char* smem)
             int row = y0;
             float mir = 0.f;
             if (mirror) mir = second;
-            else if (have2 && second > best) { best = second; row += 1; }
+            else if (second > best) { best = second; row += 1; }
             Partial& o = p.part[(size_t)pair * p.nrt + gl];
             o.val = (double)best; o.mir = (double)mir; o.sum = sum; o.sumsq = sumsq; o.idx = row * N; o.pad = 0;
         }
