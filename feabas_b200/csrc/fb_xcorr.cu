@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(512) fbk_fused(const __grid_constant__ XcParam
 
 
 // ---- register-resident fast path (power-of-two grids, float32 compute) ----
-constexpr int kNW1 = 4, kNW2 = 8;                    // warps per CTA of K1 / K2
+constexpr int kNW1 = 8, kNW2 = 8;                    // warps per CTA of K1 / K2
 // K3: lines (= GT tile rows) per CTA for T lanes per line; CTA = T * R threads, 512 threads per SM
 template <int T> constexpr int kR3() { return 8; }
 template <int E, int T, typename TI, bool PRUNED>
@@ -99,11 +99,11 @@ __global__ void __launch_bounds__(32 * kNW2, 16 / kNW2) fbk_fast_columns(const _
     extern __shared__ __align__(16) unsigned char smem[];
     kfast_columns<E, T, kNW2, PRUNED>(fp, smem);
 }
-template <int E, int T, int R>
+template <int E, int T, int R, int RB = R>
 __global__ void __launch_bounds__(T * R, 512 / (T * R)) fbk_fast_rows_inverse(const __grid_constant__ FastParams fp)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    kfast_rows_inverse<E, T, R>(fp, smem);
+    kfast_rows_inverse<E, T, R, RB>(fp, smem);
 }
 
 // ---------------------------------------------------------------------------
@@ -233,6 +233,7 @@ static int set_attrs(int device)
     RSF(32, 16);
     RSF(32, 32);
     RS((fbk_fast_rows_inverse<32, 32, 4>));
+    RS((fbk_fast_rows_inverse<32, 32, 4, 8>));
 #undef RSF
 #undef RS
     g_attr_done[device] = true;
@@ -372,7 +373,7 @@ static int launch_fast(const Problem& q, StreamCtx& ctx, XcParams& p, int nb, cu
     p.part = reinterpret_cast<Partial*>(w + f0 + f1 + gg);
     fp.rblk = TX == 32 ? kR3<32>() : kR3<16>();          // rows per K3 tile
     if (TX == 32 && (g_opt_fast_flags & 32)) fp.rblk = 4;
-    fp.flags = (int)(g_opt_fast_flags & (15 | 64 | 128));
+    fp.flags = (int)(g_opt_fast_flags & ~(16 | 32));
     p.G = fp.GT; p.gt_layout = fp.rblk; p.nrt = q.nrt; p.out_scale = p.scale;
     fp.hp0 = q.hp0; fp.hp1 = q.hp1;
     fp.x = p;
@@ -400,9 +401,11 @@ static int launch_fast(const Problem& q, StreamCtx& ctx, XcParams& p, int nb, cu
         else if (q.ny == 512) launch_fast_k2<32, 16>(fp, pruned, grid, fast_smem(512, kNW2), st);
         else launch_fast_k2<32, 32>(fp, pruned, grid, fast_smem(1024, kNW2), st);
     }
-    // K3: TX * R threads own R lines
+    // K3: TX * R threads own R lines (R <= rblk rows of a GT tile)
     {
-        const int R = fp.rblk, nt = TX * R;
+        int R = fp.rblk;
+        if (TX == 32 && (g_opt_fast_flags & 16)) R = 4;          // experiment: half-tile CTAs
+        const int nt = TX * R;
         const int work = nb * (q.nrt / R);
         const int cap = g_num_sms * (512 / nt);
         const int grid = work < cap ? work : cap;
@@ -411,6 +414,7 @@ static int launch_fast(const Problem& q, StreamCtx& ctx, XcParams& p, int nb, cu
         ProfScope ps(ctx, st, SLOT_ROWS_INV);
         if (q.nx == 256) fbk_fast_rows_inverse<16, 16, kR3<16>()><<<grid, nt, sm3, st>>>(fp);
         else if (q.nx == 512) fbk_fast_rows_inverse<32, 16, kR3<16>()><<<grid, nt, sm3, st>>>(fp);
+        else if (R == 4 && fp.rblk == 8) fbk_fast_rows_inverse<32, 32, 4, 8><<<grid, nt, sm3, st>>>(fp);
         else if (R == 4) fbk_fast_rows_inverse<32, 32, 4><<<grid, nt, sm3, st>>>(fp);
         else fbk_fast_rows_inverse<32, 32, kR3<32>()><<<grid, nt, sm3, st>>>(fp);
     }

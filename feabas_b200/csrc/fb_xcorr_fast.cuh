@@ -235,7 +235,7 @@ __device__ void kfast_rows_forward(const FastParams& fp, unsigned char* smem)
             for (int n1 = 0; n1 < E; ++n1) {
                 const int xx = n1 * T + t;
                 float a = 0.f, b = 0.f;
-                if ((!PRUNED || n1 < E / 2) && xx < Wd) {
+                if ((!PRUNED || n1 < E / 2) && xx < Wd && !(fp.flags & 512)) {
                     a = (float)__ldg(img + (size_t)rA * Wd + xx);
                     if (rB < H) b = (float)__ldg(img + (size_t)rB * Wd + xx);
                 }
@@ -256,7 +256,7 @@ __device__ void kfast_rows_forward(const FastParams& fp, unsigned char* smem)
             const int l = tid % LPC;
             const cx<float>* reg = regions + l * RS;
             float4* dst = reinterpret_cast<float4*>(FT + row0 + 2 * l);
-            for (int k = tid / LPC; k < kp; k += KSTEP) {
+            for (int k = tid / LPC; k < ((fp.flags & 1024) ? 0 : kp); k += KSTEP) {
                 const cx<float> zk = reg[k], zm = reg[k ? N - k : 0];
                 float4 o;
                 o.x = 0.5f * (zk.x + zm.x); o.y = 0.5f * (zk.y - zm.y);      // row 2l   : (Z[k] + conj Z[N-k]) / 2
@@ -369,11 +369,12 @@ __device__ void kfast_columns(const FastParams& fp, unsigned char* smem)
 // row = -Im.  Only per-line maxima are produced; the finalize kernel locates x inside the
 // winning row (np.argmax order: lowest row, then lowest x).
 // ---------------------------------------------------------------------------------------------
-template <int E, int T, int R>
+template <int E, int T, int R, int RB = R>
 __device__ void kfast_rows_inverse(const FastParams& fp, unsigned char* smem)
 {
     static_assert(R == 4 || R == 8 || R == 16, "lines per CTA");
-    constexpr int N = E * T, M = E / T, NT = T * R, NWARP = NT / 32;   // R == fp.rblk
+    static_assert(RB % R == 0, "a CTA owns a whole GT tile (RB rows) or an aligned part of one");
+    constexpr int N = E * T, M = E / T, NT = T * R, NWARP = NT / 32;   // RB == fp.rblk
     constexpr int XS = T * R + (R < 16 ? R : 0);              // k1 stride of the exchange tile (conflict free)
     const XcParams& p = fp.x;
     cx<float>* X = reinterpret_cast<cx<float>*>(smem);
@@ -393,18 +394,20 @@ __device__ void kfast_rows_inverse(const FastParams& fp, unsigned char* smem)
         const int pair = work / tiles, tile = work - pair * tiles;
         const int gl = tile * R + r;                           // line index inside the pair (always live:
         const int y0 = mirror ? gl : 2 * gl;                   //  R divides the power-of-two line count)
-        const cx<float>* A = fp.GT + (size_t)pair * 2 * plane + gt_row_offset(y0, kp, R);
-        const cx<float>* B = mirror ? A + (size_t)kp * R : A + 1;
-        if (tid == 0 && !(fp.flags & 4)) {                     // the CTA's next tile is one contiguous chunk -> L2
-            const int nw_ = work + gridDim.x;
-            if (nw_ < p.n * tiles) {
+        const cx<float>* A = fp.GT + (size_t)pair * 2 * plane + gt_row_offset(y0, kp, RB);
+        const cx<float>* B = mirror ? A + (size_t)kp * RB : A + 1;
+        if (tid == 0 && !(fp.flags & 4)) {                     // the GT tile of the CTA's next work item is one
+            const int nw_ = work + gridDim.x;                  // contiguous chunk -> L2 (once per GT tile)
+            const int rows = mirror ? R : 2 * R;               // surface rows per work item
+            if (nw_ < p.n * tiles && (nw_ * rows) % RB == 0) {
                 const int np = nw_ / tiles, nt = nw_ - np * tiles;
                 const cx<float>* nb = fp.GT + (size_t)np * 2 * plane;
+                const int yb = nt * rows / RB;                 // first GT tile of that work item
                 if (mirror) {
-                    prefetch_l2_bulk(nb + (size_t)nt * 2 * kp * R, (unsigned)(2 * kp * R * 8));
+                    prefetch_l2_bulk(nb + (size_t)yb * 2 * kp * RB, (unsigned)(2 * kp * RB * 8));
                 } else {
-                    prefetch_l2_bulk(nb + (size_t)(2 * nt) * 2 * kp * R, (unsigned)(kp * R * 8));
-                    prefetch_l2_bulk(nb + (size_t)(2 * nt + 1) * 2 * kp * R, (unsigned)(kp * R * 8));
+                    for (int i = 0; i < (rows + RB - 1) / RB; ++i)
+                        prefetch_l2_bulk(nb + (size_t)(yb + i) * 2 * kp * RB, (unsigned)(kp * RB * 8));
                 }
             }
         }
@@ -416,13 +419,15 @@ __device__ void kfast_rows_inverse(const FastParams& fp, unsigned char* smem)
             for (int n1 = 0; n1 < E; ++n1) {
                 const int k = n1 * T + t;
                 cx<float> z;
-                if (n1 < E / 2 || (n1 == E / 2 && t == 0)) {
-                    const cx<float> a = ldg(A + (size_t)k * R), b = ldg(B + (size_t)k * R);
+                if (fp.flags & 256) {                          // diagnostic: no global loads
+                    z = mk<float>((float)k, (float)r);
+                } else if (n1 < E / 2 || (n1 == E / 2 && t == 0)) {
+                    const cx<float> a = ldg(A + (size_t)k * RB), b = ldg(B + (size_t)k * RB);
                     // conj(P + iQ) with stored a = conj(P), b = conj(Q):  a - i b
                     z = (k == 0 || 2 * k == N) ? mk<float>(a.x, -b.x) : mk<float>(a.x + b.y, a.y - b.x);
                 } else {
                     const int m = N - k;
-                    const cx<float> a = ldg(A + (size_t)m * R), b = ldg(B + (size_t)m * R);
+                    const cx<float> a = ldg(A + (size_t)m * RB), b = ldg(B + (size_t)m * RB);
                     // conj(conj(P) + i conj(Q)) = P - i Q = conj(a) - i conj(b)
                     z = mk<float>(a.x - b.y, -a.y - b.x);
                 }
