@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(32 * kNW1, 16 / kNW1) fbk_fast_rows_forward(co
 template <int E, int T, bool PRUNED>
 __global__ void __launch_bounds__(32 * kNW2, 16 / kNW2) fbk_fast_columns(const __grid_constant__ FastParams fp)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem[];
     kfast_columns<E, T, kNW2, PRUNED>(fp, smem);
 }
 template <int E, int T, int R, int RB = R>
@@ -354,6 +354,35 @@ static size_t fast_smem(int n, int nw)
 
 static int g_num_sms = 0;
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode_tiled = nullptr;
+static bool g_encode_tried = false;
+
+// G^T of `nb` pairs as a 4-D tensor of 8-byte elements, innermost first: [rblk][kp][2][nb * ny / rblk];
+// box = one column of one plane of one pair: [rblk][1][1][ny / rblk] = ny elements in natural y order
+static bool make_gt_map(CUtensorMap* map, void* gt, int nb, int ny, int kp, int rblk)
+{
+    if (!g_encode_tried) {
+        g_encode_tried = true;
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            g_encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
+        cudaGetLastError();
+    }
+    if (!g_encode_tiled || ny / rblk > 256) return false;
+    const cuuint64_t dims[4] = {(cuuint64_t)rblk, (cuuint64_t)kp, 2, (cuuint64_t)nb * (ny / rblk)};
+    const cuuint64_t strides[3] = {(cuuint64_t)rblk * 8, (cuuint64_t)kp * rblk * 8, (cuuint64_t)2 * kp * rblk * 8};
+    const cuuint32_t box[4] = {(cuuint32_t)rblk, 1, 1, (cuuint32_t)(ny / rblk)};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    return g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, gt, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <typename TI>
 static int launch_fast(const Problem& q, StreamCtx& ctx, XcParams& p, int nb, cudaStream_t st)
 {
@@ -374,6 +403,7 @@ static int launch_fast(const Problem& q, StreamCtx& ctx, XcParams& p, int nb, cu
     fp.rblk = TX == 32 ? kR3<32>() : kR3<16>();          // rows per K3 tile
     if (TX == 32 && (g_opt_fast_flags & 32)) fp.rblk = 4;
     fp.flags = (int)(g_opt_fast_flags & ~(16 | 32));
+    fp.use_tma = make_gt_map(&fp.gt_map, fp.GT, nb, q.ny, g.kp, fp.rblk) ? 1 : 0;
     p.G = fp.GT; p.gt_layout = fp.rblk; p.nrt = q.nrt; p.out_scale = p.scale;
     fp.hp0 = q.hp0; fp.hp1 = q.hp1;
     fp.x = p;

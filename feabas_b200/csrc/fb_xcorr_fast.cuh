@@ -16,6 +16,7 @@
 // K3 rows: GT -> per-row arg-max partials.  Same arithmetic as the generic path
 // (feabas/matcher.py:63-68,82,114-125).  CUDA only (warp shuffles, cp.async).
 #pragma once
+#include <cuda.h>          // CUtensorMap (type only; the encoder is fetched at run time, no libcuda link)
 #include "fb_regfft.cuh"
 #include "fb_xcorr.cuh"
 
@@ -161,6 +162,20 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* gsrc, unsigned byte
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(gsrc), "r"(bytes) : "memory");
 }
 
+// ---- TMA (cp.async.bulk.tensor) store of one column: shared memory [ny] complex, natural y order ->
+// the tiled G^T layout; ONE instruction per column instead of 32 scattered STG.64 per lane.
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2, int c3)
+{
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_src);
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];\n"
+                 ::"l"(map), "r"(s), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+    asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+}
+// all bulk stores of this thread have finished READING shared memory (the buffer may be rewritten)
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+// make preceding generic-proxy shared-memory writes visible to the async (TMA) proxy
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
 struct FastParams {
     XcParams x;
     const cx<float>* twx;   // [EX / 2][TX][2]: w_nx^(k1 t) with rows (k1, k1 + 1) paired per lane
@@ -171,6 +186,8 @@ struct FastParams {
                             // that the rblk rows one K3 CTA owns are ONE contiguous chunk (all kx)
     int hp0, hp1;
     int rblk;               // rows per K3 tile, a power of two <= 16
+    int use_tma;            // K2 stores its columns with gt_map (cp.async.bulk.tensor)
+    alignas(64) CUtensorMap gt_map;   // G^T as a 4-D tensor of 8-byte elements: [n * ny / rblk][P|Q][kp][rblk], box = one column
     int flags;              // experiment switches (fb_set_option "fast_flags"): 1/2/4 = no L2 prefetch in
                             // K1/K2/K3, 8 = K2 partners are warps (w, w + NW/2) instead of (2w, 2w+1)
 };
@@ -280,7 +297,8 @@ template <int E, int T, int NW, bool PRUNED0>
 __device__ void kfast_columns(const FastParams& fp, unsigned char* smem)
 {
     using W = WarpFFT<E, T>;
-    constexpr int N = W::N, LPW = W::LPW, RS = W::RS, CPG = LPW * (NW / 2), NT = 32 * NW;   // CPG columns per CTA
+    constexpr int N = W::N, LPW = W::LPW, RS = (W::RS + 15) & ~15, CPG = LPW * (NW / 2), NT = 32 * NW;   // CPG columns per CTA;
+                                                                  // regions are 128-byte aligned (TMA source)
     const XcParams& p = fp.x;
     cx<float>* regions = reinterpret_cast<cx<float>*>(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -299,10 +317,15 @@ __device__ void kfast_columns(const FastParams& fp, unsigned char* smem)
     cx<float>* other = regions + ((split ? (roleB ? pw : pw + NW / 2) : (warp ^ 1)) * LPW + lw) * RS;
     const int hp = roleB ? fp.hp1 : fp.hp0;
     const bool second_phase = !roleB || mirror;
+    const bool tma = fp.use_tma && !(fp.flags & 2048);
     for (int work = blockIdx.x; work < p.n * groups; work += gridDim.x) {
         const int pair = work / groups, grp = work - pair * groups;
         const int col = grp * CPG + pw * LPW + lw;
         const bool live = col < kp;
+        if (tma) {                                         // the previous column's TMA store has read `mine`
+            if (t == 0) tma_store_wait_read();
+            __syncwarp();
+        }
         if (lane == 0 && pw == 0 && !(fp.flags & 2)) {     // the CTA's next column group (contiguous in FT) -> L2
             const int nw_ = work + gridDim.x;
             if (nw_ < p.n * groups) {
@@ -347,14 +370,28 @@ __device__ void kfast_columns(const FastParams& fp, unsigned char* smem)
                 asm volatile("bar.sync %0, 64;" ::"r"(pw + 1) : "memory");
                 if (!second_phase) break;
             } else if (live && !(fp.flags & 64)) {
-                // y = t + c, c a multiple of T >= rblk: the tile index advances by c / rblk
-                const int R = fp.rblk;
-                cx<float>* dst = fp.GT + (size_t)pair * 2 * kp * N + gt_row_offset(t, kp, R) + ((size_t)(roleB ? kp : 0) + col) * R;
-                const size_t cs = (size_t)2 * kp;
+                if (tma) {
+                    // natural y order into the (free) transpose region, then one bulk tensor store scatters
+                    // the column into its ny / rblk tiles
 #pragma unroll
-                for (int j = 0; j < E; ++j) dst[(W::out_k(t, j) - t) * cs] = v[W::out_reg(j)];
+                    for (int j = 0; j < E; ++j) mine[W::out_k(t, j)] = v[W::out_reg(j)];
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (t == 0) tma_store_4d(&fp.gt_map, mine, 0, col, roleB ? 1 : 0, pair * (N / fp.rblk));
+                } else {
+                    // y = t + c, c a multiple of T >= rblk: the tile index advances by c / rblk
+                    const int R = fp.rblk;
+                    cx<float>* dst = fp.GT + (size_t)pair * 2 * kp * N + gt_row_offset(t, kp, R) + ((size_t)(roleB ? kp : 0) + col) * R;
+                    const size_t cs = (size_t)2 * kp;
+#pragma unroll
+                    for (int j = 0; j < E; ++j) dst[(W::out_k(t, j) - t) * cs] = v[W::out_reg(j)];
+                }
             }
         }
+    }
+    if (tma) {                                             // shared memory must outlive the last store's read
+        if (t == 0) tma_store_wait_read();
+        __syncwarp();
     }
 }
 

@@ -121,8 +121,15 @@ def xcorr_fft(img0, img1, conf_mode=FFT_CONF_MIRROR, **kwargs):
     return_debug = kwargs.get('return_debug', False)
     force = kwargs.get('force', None)
     if sigma > 0:
-        raise NotImplementedError('sigma > 0 (DoG inside xcorr_fft, matcher.py:54-56) is not wired yet; '
-                                  'filter with feabas_b200.cuda.masked_dog_filter first')
+        # matcher.py:54-56: masked DoG band-pass of both stacks first (device kernel, float32 out; the
+        # channel axis moves in front of H x W before filtering, matcher.py:50-53)
+        from .image import masked_dog_filter, to_device
+        a = img0 if _is_torch(img0) else np.asarray(img0)
+        b = img1 if _is_torch(img1) else np.asarray(img1)
+        if a.ndim > 3 or b.ndim > 3:
+            raise NotImplementedError('multi-channel stacks are not implemented yet')
+        img0 = masked_dog_filter(to_device(a, device), sigma, mask=kwargs.get('mask0', None))
+        img1 = masked_dog_filter(to_device(b, img0.device.index), sigma, mask=kwargs.get('mask1', None))
     if normalize:
         raise NotImplementedError('normalize=True (matcher.py:71-81) is not implemented yet')
     on_gpu = _is_torch(img0) and img0.is_cuda
