@@ -188,6 +188,16 @@ def clocks_monitor_stop(proc, path):
     return out
 
 
+def measured_traffic(workload, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full
+    capture of this workload (profiles/traffic.json, written by profiles/ncu_summary.py --traffic), or None."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
+            return json.load(f)[workload][kernel]
+    except Exception:
+        return None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
@@ -199,7 +209,7 @@ def peaks():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--steps', type=int, default=300)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='xcorr512', choices=sorted(WORKLOADS))
@@ -230,7 +240,9 @@ def main():
             return
         import psutil
         cores = psutil.cpu_count(logical=False) or os.cpu_count() or 1
-        per_worker = cpu_pairs_per_worker(wl, 2.0 * cores, cores)      # ~2 s wall per step
+        # bounded sample per step: the whole --steps/--warmup run ends in about 90 s of wall clock
+        per_step_wall = min(3.0, max(0.2, 90.0 / (args.steps + warmup)))
+        per_worker = cpu_pairs_per_worker(wl, per_step_wall * cores, cores)
         arm = CpuArm(wl, per_worker)
         for _ in range(warmup):
             arm.step()
@@ -361,7 +373,8 @@ def main():
         bytes_per_pair = b_min
     achieved = bytes_per_pair * pairs_per_launch / (kern[dom]['ms_per_launch'] * 1e-3) / 1e9
     roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                'traffic': None, 'peak_kind': peak_kind, 'algorithmic_bytes_per_pair': bytes_per_pair,
+                'traffic': measured_traffic(args.workload, dom) if batch == WORKLOADS[args.workload]['batch'] else None,
+                'peak_kind': peak_kind, 'algorithmic_bytes_per_pair': bytes_per_pair,
                 'pairs_per_launch': pairs_per_launch, 'ms_per_launch': kern[dom]['ms_per_launch'],
                 'kernel_share_of_step': kern[dom]['ms_total'] / ms if world == 1 else None,
                 'pipeline': {'bytes_per_pair': b_alg, 'b_min': b_min, 'b_pass': b_pass,

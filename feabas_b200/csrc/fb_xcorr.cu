@@ -83,6 +83,22 @@ __global__ void __launch_bounds__(512) fbk_fused(const __grid_constant__ XcParam
 }
 
 
+// multi-channel stacks (matcher.py:66-67,115-116): the cross-power is averaged over channels before the
+// inverse transform; the column stage is linear, so the mean is taken over its per-channel outputs
+template <typename T>
+__global__ void __launch_bounds__(256) fbk_channel_mean(const cx<T>* __restrict__ g, cx<T>* __restrict__ out, int nchan,
+                                                         size_t elems, size_t total)
+{
+    const T inv = T(1) / T(nchan);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t pair = i / elems, e = i - pair * elems;
+        const cx<T>* src = g + (pair * nchan) * elems + e;
+        cx<T> a = src[0];
+        for (int c = 1; c < nchan; ++c) a = a + src[(size_t)c * elems];
+        out[i] = mk<T>(a.x * inv, a.y * inv);
+    }
+}
+
 // ---- register-resident fast path (power-of-two grids, float32 compute) ----
 constexpr int kNW1 = 8, kNW2 = 8;                    // warps per CTA of K1 / K2
 // K3: lines (= GT tile rows) per CTA for T lanes per line; CTA = T * R threads, 512 threads per SM
@@ -207,6 +223,7 @@ static int set_attrs(int device)
     if (g_attr_done[device]) return FB_OK;
     int rc;
 #define RS(k) if ((rc = raise_smem(k)) != FB_OK) return rc
+    (void)0;
     RS((fbk_rows_forward<float, float>));
     RS((fbk_rows_forward<float, unsigned char>));
     RS((fbk_rows_forward<double, unsigned char>));
@@ -254,12 +271,21 @@ struct Problem {
     int hp0, hp1;   // fast: padded heights of the transposed row spectra
     size_t ws_per_pair;
     int nrt;
+    int nchan;      // channels per image (cross-power averaged); > 1 or any fb_xcorr_ext pointer -> generic staged path
+    fb_xcorr_ext ext;
 };
 
 static bool fast_size(int n) { return n == 256 || n == 512 || n == 1024; }
 
-static int make_problem(Problem& q, int n, int h0, int w0, int h1, int w1, int in_dtype, int fft_h, int fft_w, int flags)
+static int make_problem(Problem& q, int n, int h0, int w0, int h1, int w1, int in_dtype, int fft_h, int fft_w, int flags,
+                        const fb_xcorr_ext* ext = nullptr)
 {
+    q.ext = fb_xcorr_ext{};
+    if (ext) q.ext = *ext;
+    q.nchan = q.ext.nchan > 1 ? q.ext.nchan : 1;
+    const bool ext_active = q.nchan > 1 || q.ext.norm || q.ext.norm_mirror || q.ext.surface || q.ext.surface_mirror;
+    if (ext && q.ext.nchan < 0) return fail(FB_EINVAL, "bad nchan %d", q.ext.nchan);
+    if (ext_active) flags = (flags & ~FB_FLAG_FORCE_FUSED) | FB_FLAG_FORCE_STAGED | FB_FLAG_FORCE_GENERIC;
     if (n < 0 || h0 < 1 || w0 < 1 || h1 < 1 || w1 < 1) return fail(FB_EINVAL, "bad shape n=%d %dx%d / %dx%d", n, h0, w0, h1, w1);
     if (in_dtype < FB_F32 || in_dtype > FB_F64) return fail(FB_EINVAL, "bad in_dtype %d", in_dtype);
     if (fft_h < (h0 > h1 ? h0 : h1) || fft_w < (w0 > w1 ? w0 : w1)) return fail(FB_EINVAL, "fft grid %dx%d smaller than the images", fft_h, fft_w);
@@ -289,7 +315,8 @@ static int make_problem(Problem& q, int n, int h0, int w0, int h1, int w1, int i
     const int rpt = g.mirror ? g.tl_row : 2 * g.tl_row;
     q.nrt = q.fused ? 0 : (fft_h + rpt - 1) / rpt;
     q.ws_per_pair = q.fused ? 0
-                            : ((size_t)(h0 + h1) * g.fpitch + (size_t)fft_h * 2 * g.fpitch) * g.esize + (size_t)q.nrt * sizeof(Partial);
+                            : ((size_t)(h0 + h1) * g.fpitch * q.nchan + (size_t)fft_h * 2 * g.fpitch * (q.nchan + (q.nchan > 1 ? 1 : 0))) * g.esize +
+                                  (size_t)q.nrt * sizeof(Partial);
     q.fast = !q.fused && !q.f64 && fast_size(fft_h) && fast_size(fft_w) && !(flags & FB_FLAG_FORCE_GENERIC);
     if (q.fast) {
         q.hp0 = (h0 + 31) & ~31; q.hp1 = (h1 + 31) & ~31;
@@ -487,13 +514,26 @@ static int launch_chunk(const Problem& q, StreamCtx& ctx, const void* img0, cons
         if constexpr (std::is_same<T, float>::value) return launch_fast<TI>(q, ctx, p, nb, st);
     }
     unsigned char* w = reinterpret_cast<unsigned char*>(ctx.ws);
-    size_t f0 = (size_t)nb * q.h0 * g.fpitch * g.esize, f1 = (size_t)nb * q.h1 * g.fpitch * g.esize;
-    size_t gg = (size_t)nb * q.ny * 2 * g.fpitch * g.esize;
-    p.F0 = w; p.F1 = w + f0; p.G = w + f0 + f1; p.part = reinterpret_cast<Partial*>(w + f0 + f1 + gg);
+    const int C = q.nchan;
+    size_t f0 = (size_t)nb * C * q.h0 * g.fpitch * g.esize, f1 = (size_t)nb * C * q.h1 * g.fpitch * g.esize;
+    const size_t gpair = (size_t)q.ny * 2 * g.fpitch;                       // complex elements of one pair's P | Q block
+    size_t gg = (size_t)nb * C * gpair * g.esize, gm = C > 1 ? (size_t)nb * gpair * g.esize : 0;
+    p.F0 = w; p.F1 = w + f0; p.G = w + f0 + f1; p.part = reinterpret_cast<Partial*>(w + f0 + f1 + gg + gm);
+    p.norm = q.ext.norm; p.norm_m = q.ext.norm_mirror; p.surf = q.ext.surface; p.surf_m = q.ext.surface_mirror;
     const int t0 = row_tiles<T>(q.h0, p.tl), t1 = row_tiles<T>(q.h1, p.tl);
     const int nct = (g.kp + p.tc - 1) / p.tc;
-    { ProfScope ps(ctx, st, SLOT_ROWS_FWD); fbk_rows_forward<T, TI><<<nb * (t0 + t1), g.nthreads_row, g.smem_row, st>>>(p); }
-    { ProfScope ps(ctx, st, SLOT_COLUMNS); fbk_columns<T><<<nb * nct, g.nthreads_col, g.smem_col, st>>>(p); }
+    p.n = nb * C;                                                           // channels are extra pairs up to the column stage
+    { ProfScope ps(ctx, st, SLOT_ROWS_FWD); fbk_rows_forward<T, TI><<<nb * C * (t0 + t1), g.nthreads_row, g.smem_row, st>>>(p); }
+    { ProfScope ps(ctx, st, SLOT_COLUMNS); fbk_columns<T><<<nb * C * nct, g.nthreads_col, g.smem_col, st>>>(p); }
+    if (C > 1) {
+        cx<T>* gout = reinterpret_cast<cx<T>*>(w + f0 + f1 + gg);
+        const size_t total = (size_t)nb * gpair;
+        const int grid = (int)((total + 255) / 256 < 65535 ? (total + 255) / 256 : 65535);
+        fbk_channel_mean<T><<<grid, 256, 0, st>>>(reinterpret_cast<const cx<T>*>(p.G), gout, C, gpair, total);
+        p.G = gout;
+        g_launches += 1;
+    }
+    p.n = nb;
     { ProfScope ps(ctx, st, SLOT_ROWS_INV); fbk_rows_inverse<T><<<nb * q.nrt, g.nthreads_row, g.smem_row, st>>>(p); }
     { ProfScope ps(ctx, st, SLOT_FINALIZE); fbk_finalize<T><<<nb, 256, (size_t)q.nx * 4 * sizeof(cx<T>) + 2048, st>>>(p); }
     g_launches += 4;
@@ -530,7 +570,7 @@ static int run_device(const Problem& q, StreamCtx& ctx, const void* img0, const 
     } else if (chunk > 65535 * 16) {
         chunk = 65535 * 16;
     }
-    const size_t b0 = (size_t)q.h0 * q.w0 * q.isz, b1 = (size_t)q.h1 * q.w1 * q.isz;
+    const size_t b0 = (size_t)q.h0 * q.w0 * q.isz * q.nchan, b1 = (size_t)q.h1 * q.w1 * q.isz * q.nchan;
     for (int lo = 0; lo < n; lo += chunk) {
         int nb = n - lo < chunk ? n - lo : chunk;
         int rc = launch_chunk_any(q, ctx, (const char*)img0 + lo * b0, (const char*)img1 + lo * b1, nb,
@@ -567,6 +607,22 @@ extern "C" int fb_xcorr_batch_device(const void* img0, const void* img1, int n, 
 {
     Problem q;
     int rc = make_problem(q, n, h0, w0, h1, w1, in_dtype, fft_h, fft_w, flags);
+    if (rc != FB_OK) return rc;
+    if (n == 0) return FB_OK;
+    if (!img0 || !img1 || !dx || !dy || !conf) return fail(FB_EINVAL, "null pointer");
+    std::lock_guard<std::mutex> lk(g_mu);
+    StreamCtx* ctx;
+    if ((rc = get_ctx(device, stream, ctx)) != FB_OK) return rc;
+    return run_device(q, *ctx, img0, img1, n, dx, dy, conf, peak, mirror, (cudaStream_t)stream);
+}
+
+extern "C" int fb_xcorr_batch_device_ex(const void* img0, const void* img1, int n, int h0, int w0, int h1, int w1,
+                                        int in_dtype, int fft_h, int fft_w, int flags,
+                                        double* dx, double* dy, double* conf, double* peak, double* mirror,
+                                        int device, void* stream, const fb_xcorr_ext* ext)
+{
+    Problem q;
+    int rc = make_problem(q, n, h0, w0, h1, w1, in_dtype, fft_h, fft_w, flags, ext);
     if (rc != FB_OK) return rc;
     if (n == 0) return FB_OK;
     if (!img0 || !img1 || !dx || !dy || !conf) return fail(FB_EINVAL, "null pointer");

@@ -63,6 +63,12 @@ struct XcParams {
     int tl;               // lines per row tile
     int tc;               // columns per image per column tile
     int spitch;           // fused: row pitch of the resident spectra
+    // optional extensions (generic staged path only; all null / 1 by default)
+    const void* norm;     // T[ny][nx]: the correlation surface is divided by it before the peak search
+                          //           (mask normalisation, matcher.py:71-81)
+    const void* norm_m;   // T[ny][nx]: same for the mirror surface (matcher.py:119-124)
+    void* surf;           // T[n][ny][nx] out: the (unnormalised) correlation surface
+    void* surf_m;         // T[n][ny][nx] out: |mirror surface|
     int gt_layout;        // K4: != 0: G holds the fast path's conjugated surfaces, tiled
                           //     [ny / gt_layout][P|Q][kx][gt_layout] (gt_layout = rows per K3 tile), and
                           //     the partial's idx only identifies the ROW of the maximum
@@ -246,7 +252,7 @@ FB_DEV void rows_inverse_fill(const XcParams& p, const cx<T>* X, const cx<T>* Y,
 
 template <typename T>
 FB_DEV void rows_inverse_tile(const XcParams& p, const cx<T>* Pb, const cx<T>* Qb, int rpitch, int row0, int nl,
-                              bool mirror, Acc<T>& acc, cx<T>* s, int pitch, int tid, int nthr)
+                              bool mirror, Acc<T>& acc, cx<T>* s, int pitch, int tid, int nthr, int pair = 0)
 {
     const int nx = p.nx, ny = p.ny, kp = p.kp;
     for (int idx = tid; idx < kp * nl; idx += nthr) {
@@ -265,23 +271,37 @@ FB_DEV void rows_inverse_tile(const XcParams& p, const cx<T>* Pb, const cx<T>* Q
     fft_lines<T, true>(p.px, s, pitch, nl, tid, nthr);
     const bool want_std = p.conf_mode == CONF_STD;
     const float inv_nl = 1.0f / (float)nl;
+    const T* norm = reinterpret_cast<const T*>(p.norm);
+    const T* norm_m = reinterpret_cast<const T*>(p.norm_m);
+    T* surf = p.surf ? reinterpret_cast<T*>(p.surf) + (size_t)pair * ny * nx : nullptr;
+    T* surf_m = p.surf_m ? reinterpret_cast<T*>(p.surf_m) + (size_t)pair * ny * nx : nullptr;
     for (int idx = tid; idx < nx * nl; idx += nthr) {
         int x = (int)(((float)idx + 0.5f) * inv_nl);
         int l = idx - x * nl;
         cx<T> v = s[(size_t)x * pitch + l];
         if (mirror) {
             int y = row0 + l;
-            acc_take(acc, v.x, y * nx + x);
-            T m = v.y < T(0) ? -v.y : v.y;
+            T c = v.x, m = v.y < T(0) ? -v.y : v.y;
+            if (surf) surf[(size_t)y * nx + x] = c;
+            if (surf_m) surf_m[(size_t)y * nx + x] = m;
+            if (norm) c = c / norm[(size_t)y * nx + x];
+            if (norm_m) m = m / norm_m[(size_t)y * nx + x];
+            acc_take(acc, c, y * nx + x);
             acc.mir = m > acc.mir ? m : acc.mir;
-            if (want_std) { acc.sum += (double)v.x; acc.sumsq += (double)v.x * (double)v.x; }
+            if (want_std) { acc.sum += (double)c; acc.sumsq += (double)c * (double)c; }
         } else {
             int y = row0 + 2 * l;
-            acc_take(acc, v.x, y * nx + x);
-            if (want_std) { acc.sum += (double)v.x; acc.sumsq += (double)v.x * (double)v.x; }
+            T c = v.x;
+            if (surf) surf[(size_t)y * nx + x] = c;
+            if (norm) c = c / norm[(size_t)y * nx + x];
+            acc_take(acc, c, y * nx + x);
+            if (want_std) { acc.sum += (double)c; acc.sumsq += (double)c * (double)c; }
             if (y + 1 < ny) {
-                acc_take(acc, v.y, (y + 1) * nx + x);
-                if (want_std) { acc.sum += (double)v.y; acc.sumsq += (double)v.y * (double)v.y; }
+                T c1 = v.y;
+                if (surf) surf[(size_t)(y + 1) * nx + x] = c1;
+                if (norm) c1 = c1 / norm[(size_t)(y + 1) * nx + x];
+                acc_take(acc, c1, (y + 1) * nx + x);
+                if (want_std) { acc.sum += (double)c1; acc.sumsq += (double)c1 * (double)c1; }
             }
         }
     }
@@ -313,6 +333,16 @@ FB_DEV void finalize_pair(const XcParams& p, int pair, const Acc<T>& best, const
         }
         FB_SYNC();
         fft_lines<T, true>(p.px, s, pitch, 3, tid, nthr);
+        if (p.norm) {                                        // sub-pixel fit runs on the normalised surface
+            const T* norm = reinterpret_cast<const T*>(p.norm);
+            for (int idx = tid; idx < nx * 3; idx += nthr) {
+                int l = idx / nx, x = idx - l * nx;
+                int y = py - 1 + l;
+                y = y < 0 ? y + ny : (y >= ny ? y - ny : y);
+                s[(size_t)x * pitch + l].x = s[(size_t)x * pitch + l].x / norm[(size_t)y * nx + x];
+            }
+            FB_SYNC();
+        }
     }
     if (p.gt_layout) {
         // locate the maximum inside row py (np.argmax: first occurrence)
@@ -445,7 +475,7 @@ FB_DEV void k3_rows_inverse(const XcParams& p, int bid, int tid, int nthr, unsig
     Acc<T>* red = reinterpret_cast<Acc<T>*>(smem + (size_t)p.nx * pitch * sizeof(cx<T>));
     const cx<T>* Pb = reinterpret_cast<const cx<T>*>(p.G) + (size_t)pair * p.ny * 2 * p.fpitch;
     Acc<T> acc; acc_init(acc);
-    rows_inverse_tile<T>(p, Pb, Pb + p.fpitch, 2 * p.fpitch, row0, nl, mirror, acc, s, pitch, tid, nthr);
+    rows_inverse_tile<T>(p, Pb, Pb + p.fpitch, 2 * p.fpitch, row0, nl, mirror, acc, s, pitch, tid, nthr, pair);
     Acc<T> r = block_reduce<T>(acc, red, tid, nthr);
     if (tid == 0) {
         Partial& o = p.part[(size_t)pair * p.nrt + rt];
@@ -509,7 +539,7 @@ FB_DEV void kf_fused(const XcParams& p, int bid, int tid, int nthr, unsigned cha
     for (int row0 = 0; row0 < ny; row0 += rpt) {
         int rows = ny - row0 < rpt ? ny - row0 : rpt;
         int nl = mirror ? rows : (rows + 1) / 2;
-        rows_inverse_tile<T>(p, S, S + kp, sp, row0, nl, mirror, acc, s, pitch, tid, nthr);
+        rows_inverse_tile<T>(p, S, S + kp, sp, row0, nl, mirror, acc, s, pitch, tid, nthr, pair);
     }
     Acc<T> best = block_reduce<T>(acc, red, tid, nthr);
     finalize_pair<T>(p, pair, best, S, S + kp, sp, mirror, s, tid, nthr);

@@ -25,11 +25,17 @@ FB_DOG_EXACT = 0x2
 _vp, _i, _ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong
 _XCORR_ARGS = [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]
 
+class XcorrExt(ctypes.Structure):
+    """fb_xcorr_ext of include/feabas_cuda.h."""
+    _fields_ = [('nchan', _i), ('norm', _vp), ('norm_mirror', _vp), ('surface', _vp), ('surface_mirror', _vp)]
+
+
 # every symbol include/feabas_cuda.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     'fb_xcorr_batch_device': (_i, _XCORR_ARGS),
     'fb_xcorr_batch_host': (_i, _XCORR_ARGS),
     'fb_xcorr_batch': (_i, _XCORR_ARGS),
+    'fb_xcorr_batch_device_ex': (_i, _XCORR_ARGS + [ctypes.POINTER(XcorrExt)]),
     'fb_masked_dog_workspace': (_ll, [_i, _i, _i]),
     'fb_masked_dog': (_i, [_vp, _vp, _i, _i, _i, _i, _i, ctypes.c_double, ctypes.c_double, _i, _vp, _vp, _ll, _i, _vp]),
     'fb_stack_minmax': (_i, [_vp, _i, _ll, _i, _vp, _i, _vp]),

@@ -104,6 +104,72 @@ def _conf_dtype(conf_mode, in_dtype):
     return np.float64 if conf_mode == FFT_CONF_STD else np.float32
 
 
+def _run_ext(t0, t1, nchan, conf_mode, subpixel, pad, fftshp, norm=None, norm_mirror=None, want_surfaces=False):
+    """``fb_xcorr_batch_device_ex`` on CUDA tensors ``N x (C x) H x W`` (channel axis already in front)."""
+    code = {torch.float32: _lib.FB_F32, torch.uint8: _lib.FB_U8, torch.float64: _lib.FB_F64}[t0.dtype]
+    n, (h0, w0), (h1, w1) = t0.shape[0], t0.shape[-2:], t1.shape[-2:]
+    ny, nx = fftshp
+    ctype = torch.float32 if t0.dtype == torch.float32 else torch.float64
+    out = torch.empty((5, n), dtype=torch.float64, device=t0.device)
+    surf = surf_m = None
+    ext = _lib.XcorrExt(nchan=int(nchan))
+    if want_surfaces:
+        surf = torch.empty((n, ny, nx), dtype=ctype, device=t0.device)
+        ext.surface = surf.data_ptr()
+        if conf_mode == FFT_CONF_MIRROR:
+            surf_m = torch.empty((n, ny, nx), dtype=ctype, device=t0.device)
+            ext.surface_mirror = surf_m.data_ptr()
+    if norm is not None:
+        ext.norm = norm.data_ptr()
+    if norm_mirror is not None:
+        ext.norm_mirror = norm_mirror.data_ptr()
+    dev = t0.device.index
+    with torch.cuda.device(dev):
+        base, step = out.data_ptr(), n * 8
+        _lib.check(_lib.lib().fb_xcorr_batch_device_ex(
+            t0.data_ptr(), t1.data_ptr(), n, h0, w0, h1, w1, code, ny, nx, _flags(conf_mode, subpixel, pad),
+            base, base + step, base + 2 * step, base + 3 * step, base + 4 * step, dev,
+            torch.cuda.current_stream().cuda_stream, ctypes.byref(ext)))
+    return out, surf, surf_m
+
+
+def _xcorr_fft_ext(img0, img1, conf_mode, subpixel, pad, normalize, mask0, mask1, device):
+    """Multi-channel stacks (matcher.py:50-53,66-67) and ``normalize=True`` (matcher.py:71-81,119-124):
+    the generic staged kernels through ``fb_xcorr_batch_device_ex``."""
+    from .image import to_device
+    t0, t1 = to_device(img0, device), None
+    t1 = to_device(img1, t0.device.index)
+    if t0.dtype != t1.dtype:
+        common = torch.promote_types(t0.dtype, t1.dtype)
+        t0, t1 = t0.to(common), t1.to(common)
+    t0, t1 = _canon_torch(t0), _canon_torch(t1)
+    nchan = 1
+    if t0.dim() > 3 or t1.dim() > 3:
+        if t0.dim() != 4 or t1.dim() != 4 or t0.shape[-1] != t1.shape[-1]:
+            raise ValueError('multi-channel stacks must both be N x H x W x C with the same C')
+        nchan = t0.shape[-1]
+        t0 = t0.movedim(-1, 1).contiguous()
+        t1 = t1.movedim(-1, 1).contiguous()
+    if t0.shape[0] != t1.shape[0]:
+        raise ValueError('expected two stacks with the same N')
+    fftshp = fft_shape(tuple(t0.shape[-2:]), tuple(t1.shape[-2:]), pad)
+    norm = norm_m = None
+    if normalize:
+        ctype = torch.float32 if t0.dtype == torch.float32 else torch.float64
+        # the masks default to all-ones of each image's H x W (matcher.py:72-75); their correlation
+        # surfaces come from the same kernels (one pair, no confidence needed beyond the mirror surface)
+        m0 = torch.ones(tuple(t0.shape[-2:]), dtype=ctype, device=t0.device) if mask0 is None else to_device(mask0, t0.device.index).to(ctype)
+        m1 = torch.ones(tuple(t1.shape[-2:]), dtype=ctype, device=t0.device) if mask1 is None else to_device(mask1, t0.device.index).to(ctype)
+        mode = FFT_CONF_MIRROR if conf_mode == FFT_CONF_MIRROR else FFT_CONF_NONE
+        _, s, sm = _run_ext(m0[None].contiguous(), m1[None].contiguous(), 1, mode, False, pad, fftshp, want_surfaces=True)
+        norm = (s[0] / s[0].max().clamp(min=1)).clamp(min=0.1).contiguous()
+        if sm is not None:
+            norm_m = (sm[0] / sm[0].max().clamp(min=1)).clamp(min=0.1).contiguous()
+    out, _, _ = _run_ext(t0, t1, nchan, conf_mode, subpixel, pad, fftshp, norm=norm, norm_mirror=norm_m)
+    in_dtype = np.float32 if t0.dtype == torch.float32 else np.float64
+    return out.cpu().numpy(), in_dtype
+
+
 def xcorr_fft(img0, img1, conf_mode=FFT_CONF_MIRROR, **kwargs):
     """Drop-in for ``feabas.matcher.xcorr_fft`` (matcher.py:22-135).
 
@@ -120,22 +186,25 @@ def xcorr_fft(img0, img1, conf_mode=FFT_CONF_MIRROR, **kwargs):
     device = kwargs.get('device', None)
     return_debug = kwargs.get('return_debug', False)
     force = kwargs.get('force', None)
+    ndim = max(img0.dim() if _is_torch(img0) else np.ndim(img0), img1.dim() if _is_torch(img1) else np.ndim(img1))
     if sigma > 0:
         # matcher.py:54-56: masked DoG band-pass of both stacks first (device kernel, float32 out; the
         # channel axis moves in front of H x W before filtering, matcher.py:50-53)
         from .image import masked_dog_filter, to_device
-        a = img0 if _is_torch(img0) else np.asarray(img0)
-        b = img1 if _is_torch(img1) else np.asarray(img1)
-        if a.ndim > 3 or b.ndim > 3:
-            raise NotImplementedError('multi-channel stacks are not implemented yet')
-        img0 = masked_dog_filter(to_device(a, device), sigma, mask=kwargs.get('mask0', None))
-        img1 = masked_dog_filter(to_device(b, img0.device.index), sigma, mask=kwargs.get('mask1', None))
-    if normalize:
-        raise NotImplementedError('normalize=True (matcher.py:71-81) is not implemented yet')
+        a, b = to_device(img0, device), None
+        b = to_device(img1, a.device.index)
+        if ndim > 3:
+            a, b = a.movedim(-1, 1).contiguous(), b.movedim(-1, 1).contiguous()
+        a = masked_dog_filter(a, sigma, mask=kwargs.get('mask0', None))
+        b = masked_dog_filter(b, sigma, mask=kwargs.get('mask1', None))
+        if ndim > 3:
+            a, b = a.movedim(1, -1), b.movedim(1, -1)
+        img0, img1 = a, b
     on_gpu = _is_torch(img0) and img0.is_cuda
-    if on_gpu:
-        if img0.dim() > 3:
-            raise NotImplementedError('multi-channel stacks are not implemented yet')
+    if ndim > 3 or normalize:
+        out, in_dtype = _xcorr_fft_ext(img0, img1, conf_mode, subpixel, pad, normalize,
+                                       kwargs.get('mask0', None), kwargs.get('mask1', None), device)
+    elif on_gpu:
         in_dtype = {torch.float32: np.float32}.get(img0.dtype, np.float64)
         out = xcorr_fft_device(img0, img1, conf_mode=conf_mode, subpixel=subpixel, pad=pad, force=force).cpu().numpy()
     else:
@@ -144,8 +213,6 @@ def xcorr_fft(img0, img1, conf_mode=FFT_CONF_MIRROR, **kwargs):
         if _is_torch(img1):
             img1 = img1.numpy()
         a, b = np.asarray(img0), np.asarray(img1)
-        if a.ndim > 3 or b.ndim > 3:
-            raise NotImplementedError('multi-channel stacks are not implemented yet')
         if a.dtype != b.dtype:
             common = np.promote_types(a.dtype, b.dtype)
             a, b = a.astype(common), b.astype(common)

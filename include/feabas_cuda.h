@@ -46,7 +46,7 @@ extern "C" {
 #define FB_FLAG_FORCE_GENERIC 0x80 /* testing: staged pipeline with the generic mixed-radix kernels */
 
 /* xcorr_fft (feabas/matcher.py:22-135) on a stack of n image pairs, sigma == 0,
- * single channel, no mask normalisation.
+ * single channel, no mask normalisation (those: fb_xcorr_batch_device_ex below).
  *
  *   img0 : n x h0 x w0, img1 : n x h1 x w1, row-major, dtype in_dtype
  *   fft_h, fft_w : the reference's fftshp (matcher.py:59-62), 5-smooth
@@ -75,6 +75,31 @@ int fb_xcorr_batch(const void* img0, const void* img1, int n, int h0, int w0, in
                    int in_dtype, int fft_h, int fft_w, int flags,
                    double* dx, double* dy, double* conf, double* peak, double* mirror,
                    int device, void* stream);
+
+/* The rarely used arguments of xcorr_fft, device pointers on `device` (NULL / 0 = off).  Any of them
+ * selects the generic HBM-staged kernels.
+ *   nchan          : channels per image; the stacks are n x nchan x h x w (the reference moves the channel
+ *                    axis in front of H x W, matcher.py:50-53) and the cross-power is averaged over
+ *                    channels before the inverse transform (matcher.py:66-67,115-116)
+ *   norm           : fft_h x fft_w divisors of the correlation surface, applied before the peak search --
+ *                    normalize=True (matcher.py:71-81); the caller builds them from the masks with a
+ *                    first call that requests `surface`
+ *   norm_mirror    : the same for the mirror surface (matcher.py:119-124)
+ *   surface        : out, n x fft_h x fft_w: the correlation surface irfft2(conj(F0) F1)
+ *   surface_mirror : out, n x fft_h x fft_w: |irfft2(F0 F1)| (FB_CONF_MIRROR only)
+ * Element type of the four arrays: float for FB_F32 input, double otherwise (the compute type).        */
+typedef struct fb_xcorr_ext {
+    int nchan;
+    const void* norm;
+    const void* norm_mirror;
+    void* surface;
+    void* surface_mirror;
+} fb_xcorr_ext;
+
+int fb_xcorr_batch_device_ex(const void* img0, const void* img1, int n, int h0, int w0, int h1, int w1,
+                             int in_dtype, int fft_h, int fft_w, int flags,
+                             double* dx, double* dy, double* conf, double* peak, double* mirror,
+                             int device, void* stream, const fb_xcorr_ext* ext);
 
 /* ---- image operators either side of the matcher (device pointers on `device`, work enqueued on
  * `stream`, no synchronisation) ------------------------------------------------------------- */

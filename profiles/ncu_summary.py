@@ -38,5 +38,37 @@ def main(path):
             print(f'      {v:8.3f}  ' + h.replace('smsp__average_warps_issue_stalled_', '').replace('_per_issue_active.ratio', ''))
 
 
+SLOTS = (('rows_forward', 'rows_forward'), ('columns', 'columns'), ('rows_inverse', 'rows_inverse'),
+         ('finalize', 'finalize'), ('fused', 'fused'))
+
+
+def traffic(path, workload, out_json):
+    """profiles/traffic.json[workload][kernel slot] = mean (dram read + write) bytes per launch."""
+    import json
+    import os
+    raw = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    scale = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+    acc = {}
+    for r in rows[2:]:
+        name = r[idx['Kernel Name']]
+        slot = next((s for key, s in SLOTS if key in name), None)
+        if slot is None:
+            continue
+        b = sum(float(r[idx[m]]) * scale[units[idx[m]]] for m in ('dram__bytes_read.sum', 'dram__bytes_write.sum'))
+        acc.setdefault(slot, []).append(b)
+    data = {}
+    if os.path.exists(out_json):
+        data = json.load(open(out_json))
+    data[workload] = {k: sum(v) / len(v) for k, v in acc.items()}
+    json.dump(data, open(out_json, 'w'), indent=1, sort_keys=True)
+    print(json.dumps(data[workload]))
+
+
 if __name__ == '__main__':
-    main(sys.argv[1])
+    if len(sys.argv) > 2 and sys.argv[2] == '--traffic':
+        traffic(sys.argv[1], sys.argv[3], sys.argv[4])
+    else:
+        main(sys.argv[1])

@@ -10,7 +10,7 @@ import parity
 
 pytestmark = pytest.mark.gpu
 
-UNSUPPORTED = ('multichannel', 'normalize_masks', 'normalize_default')
+UNSUPPORTED = ()
 
 
 @pytest.fixture(scope='module')
@@ -85,6 +85,42 @@ def test_float64_pipeline(fc, dtype):
     for kw in (dict(subpixel=True), dict(subpixel=True, pad=False), dict(subpixel=True, conf_mode=1)):
         got = fc.xcorr_fft(a, b, **kw)
         parity.check_against_oracle(got, a, b, conf_rtol=1e-6 if kw.get('conf_mode', 2) != 1 else 5e-2, **kw)
+
+
+def test_sigma_masks_normalize_multichannel(fc):
+    """The rarely used arguments of xcorr_fft (matcher.py:44-56,66-81): DoG inside the call, mask
+    normalisation with explicit / default masks, channel-mean of the cross-power."""
+    from oracle import matcher_oracle as mo
+    rng = np.random.default_rng(21)
+    a, b, _ = synth.block_pairs(3, (90, 70), seed=9, max_shift=8, band_pass=False)
+    m0 = np.ones((90, 70), bool); m0[:, :15] = False
+    m1 = np.ones((90, 70), bool); m1[60:, :] = False
+    # sigma > 0 with and without masks: oracle = masked DoG, then xcorr
+    for masks in ((None, None), (m0, m1)):
+        fa = mo.masked_dog_oracle(a, 2.5, mask=masks[0])
+        fb = mo.masked_dog_oracle(b, 2.5, mask=masks[1])
+        got = fc.xcorr_fft(a, b, sigma=2.5, mask0=masks[0], mask1=masks[1], subpixel=True)
+        parity.check_against_oracle(got, fa.astype(np.float32), fb.astype(np.float32), subpixel=True)
+    # normalize, float32 masks (the reference's default mask dtype) in every confidence mode
+    f0, f1 = m0.astype(np.float32), m1.astype(np.float32)
+    fa, fb, _ = synth.block_pairs(3, (90, 70), seed=10, max_shift=8)
+    for kw in (dict(subpixel=True), dict(subpixel=True, pad=False), dict(subpixel=True, conf_mode=0), dict(subpixel=False, conf_mode=1)):
+        for masks in ((None, None), (f0, f1)):
+            got = fc.xcorr_fft(fa, fb, normalize=True, mask0=masks[0], mask1=masks[1], **kw)
+            parity.check_against_oracle(got, fa, fb, normalize=True, mask0=masks[0], mask1=masks[1], **_tol(kw), **kw)
+    # multi-channel, incl. the float64 pipeline and more pairs than one chunk holds
+    c0 = rng.standard_normal((5, 40, 56, 3)).astype(np.float32)
+    c1 = np.roll(c0, (3, -5), axis=(1, 2)) + 0.1 * rng.standard_normal(c0.shape).astype(np.float32)
+    for kw in (dict(subpixel=True), dict(subpixel=True, pad=False, conf_mode=1)):
+        parity.check_against_oracle(fc.xcorr_fft(c0, c1, **kw), c0, c1, **_tol(kw), **kw)
+    u0 = (c0 * 40 + 128).clip(0, 255).astype(np.uint8)
+    u1 = (c1 * 40 + 128).clip(0, 255).astype(np.uint8)
+    parity.check_against_oracle(fc.xcorr_fft(u0, u1, subpixel=True), u0, u1, conf_rtol=1e-6, subpixel=True)
+    fc._lib.set_option('ws_bytes', 1 << 20)
+    try:
+        parity.check_against_oracle(fc.xcorr_fft(c0, c1, subpixel=True), c0, c1, subpixel=True)
+    finally:
+        fc._lib.set_option('ws_bytes', 2 << 30)
 
 
 def test_device_tensors_and_host_arrays_agree(fc):
