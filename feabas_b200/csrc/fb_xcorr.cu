@@ -122,6 +122,13 @@ __global__ void __launch_bounds__(T * R, 512 / (T * R)) fbk_fast_rows_inverse(co
     kfast_rows_inverse<E, T, R, RB>(fp, smem);
 }
 
+template <int E, int T, int R, bool MIRROR>
+__global__ void __launch_bounds__(T * R, 512 / (T * R)) fbk_fast_rows_inverse_tma(const __grid_constant__ FastParams fp)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    kfast_rows_inverse_tma<E, T, R, MIRROR>(fp, smem);
+}
+
 // ---------------------------------------------------------------------------
 // caches
 // ---------------------------------------------------------------------------
@@ -245,7 +252,9 @@ static int set_attrs(int device)
     RS((fbk_fast_rows_forward<E, T, unsigned char, false>)); \
     RS((fbk_fast_columns<E, T, true>));                      \
     RS((fbk_fast_columns<E, T, false>));                     \
-    RS((fbk_fast_rows_inverse<E, T, kR3<T>()>))
+    RS((fbk_fast_rows_inverse<E, T, kR3<T>()>));             \
+    RS((fbk_fast_rows_inverse_tma<E, T, kR3<T>(), true>));   \
+    RS((fbk_fast_rows_inverse_tma<E, T, kR3<T>(), false>))
     RSF(16, 16);
     RSF(32, 16);
     RSF(32, 32);
@@ -469,11 +478,20 @@ static int launch_fast(const Problem& q, StreamCtx& ctx, XcParams& p, int nb, cu
         const int XS = TX * R + (R < 16 ? R : 0);
         const size_t sm3 = ((size_t)EX * XS + (kLaneTwiddles ? 0 : q.nx)) * sizeof(cx<float>) + (nt / 32) * R * 2 * (sizeof(float) + sizeof(double));
         ProfScope ps(ctx, st, SLOT_ROWS_INV);
-        if (q.nx == 256) fbk_fast_rows_inverse<16, 16, kR3<16>()><<<grid, nt, sm3, st>>>(fp);
+        const bool tma3 = R == fp.rblk && !(g_opt_fast_flags & 4096);      // TMA-fed variant (default)
+        const bool mir = q.conf_mode == CONF_MIRROR;
+        const size_t sm3t = sm3 + 16;                                         // + mbarrier
+#define K3T(E_, T_) do { if (mir) fbk_fast_rows_inverse_tma<E_, T_, kR3<T_>(), true><<<grid, nt, sm3t, st>>>(fp); \
+                         else fbk_fast_rows_inverse_tma<E_, T_, kR3<T_>(), false><<<grid, nt, sm3t, st>>>(fp); } while (0)
+        if (tma3 && q.nx == 256) K3T(16, 16);
+        else if (tma3 && q.nx == 512) K3T(32, 16);
+        else if (tma3) K3T(32, 32);
+        else if (q.nx == 256) fbk_fast_rows_inverse<16, 16, kR3<16>()><<<grid, nt, sm3, st>>>(fp);
         else if (q.nx == 512) fbk_fast_rows_inverse<32, 16, kR3<16>()><<<grid, nt, sm3, st>>>(fp);
         else if (R == 4 && fp.rblk == 8) fbk_fast_rows_inverse<32, 32, 4, 8><<<grid, nt, sm3, st>>>(fp);
         else if (R == 4) fbk_fast_rows_inverse<32, 32, 4><<<grid, nt, sm3, st>>>(fp);
         else fbk_fast_rows_inverse<32, 32, kR3<32>()><<<grid, nt, sm3, st>>>(fp);
+#undef K3T
     }
     {
         ProfScope ps(ctx, st, SLOT_FINALIZE);

@@ -176,6 +176,36 @@ __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.b
 // make preceding generic-proxy shared-memory writes visible to the async (TMA) proxy
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
+// ---- mbarrier + 1-D bulk copy (TMA) global -> shared ------------------------------------------------
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(a), "r"(parity) : "memory");
+}
+// bytes % 16 == 0, both addresses 16-byte aligned; completion is signalled on `bar` (complete_tx)
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(bytes),
+                   "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+
 struct FastParams {
     XcParams x;
     const cx<float>* twx;   // [EX / 2][TX][2]: w_nx^(k1 t) with rows (k1, k1 + 1) paired per lane
@@ -524,6 +554,162 @@ __device__ void kfast_rows_inverse(const FastParams& fp, unsigned char* smem)
             int row = y0;
             float mir = 0.f;
             if (mirror) mir = second;
+            else if (second > best) { best = second; row += 1; }
+            Partial& o = p.part[(size_t)pair * p.nrt + gl];
+            o.val = (double)best; o.mir = (double)mir; o.sum = sum; o.sumsq = sumsq; o.idx = row * N; o.pad = 0;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3, TMA-fed: same arithmetic as kfast_rows_inverse, but the GT tile of the CTA (one contiguous chunk)
+// is brought into shared memory by ONE bulk copy (cp.async.bulk + mbarrier) that is issued as soon as
+// the exchange buffer of the previous tile has been read, i.e. it runs under the second butterfly
+// stage and the reductions of the previous tile.  The exchange tile X reuses the landing buffer in
+// place: every thread pulls its inputs into registers, a barrier, then X overwrites the tile.
+// MIRROR: line = (P row y, Q row y); otherwise line = (P row y, P row y + 1).
+// ---------------------------------------------------------------------------------------------
+template <int E, int T, int R, bool MIRROR>
+__device__ void kfast_rows_inverse_tma(const FastParams& fp, unsigned char* smem)
+{
+    static_assert(R == 8 || R == 16, "lines per CTA = rows per GT tile");
+    constexpr int N = E * T, M = E / T, NT = T * R, NWARP = NT / 32, KP = N / 2 + 1;
+    constexpr int XS = T * R + (R < 16 ? R : 0);              // k1 stride of the exchange tile (conflict free)
+    static_assert(E * XS >= 2 * KP * R, "the exchange tile covers the landing buffer");
+    constexpr unsigned TILE_BYTES = 2u * KP * R * 8u;
+    const XcParams& p = fp.x;
+    cx<float>* X = reinterpret_cast<cx<float>*>(smem);
+    cx<float>* twsm = X + E * XS;
+    float* red = reinterpret_cast<float*>(twsm + StageTw<E, T>::smem_entries());   // [NWARP][R][2] floats, doubles, mbarrier
+    double* redd = reinterpret_cast<double*>(red + NWARP * R * 2);
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(redd + NWARP * R * 2);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int r = tid % R, tq = tid / R;                      // stage A: t = tq; stage B: k1 = tq + T m
+    if (tid == 0) mbar_init(bar, 1);
+    StageTw<E, T> tw;
+    tw.init(fp.twx, twsm, tq, tid, NT);
+    fence_proxy_async_smem();
+    __syncthreads();
+    const bool want_std = !MIRROR && p.conf_mode == CONF_STD;
+    const int ny = p.ny;
+    const int lines_pp = MIRROR ? ny : ny / 2;                // lines per pair (R divides it: power-of-two grids)
+    const int tiles = lines_pp / R;
+    const int total = p.n * tiles;
+    const size_t plane = (size_t)KP * ny;
+    // issue the bulk copy of work item w (thread 0): MIRROR: GT tile w (P | Q planes, contiguous);
+    // otherwise the P planes of GT tiles 2 t and 2 t + 1
+    auto issue = [&](int w) {
+        const int np = w / tiles, nt = w - np * tiles;
+        const cx<float>* base = fp.GT + (size_t)np * 2 * plane;
+        mbar_expect_tx(bar, TILE_BYTES);
+        if (MIRROR) {
+            tma_load_1d(X, base + (size_t)nt * 2 * KP * R, TILE_BYTES, bar);
+        } else {
+            tma_load_1d(X, base + (size_t)(2 * nt) * 2 * KP * R, TILE_BYTES / 2, bar);
+            tma_load_1d(X + KP * R, base + (size_t)(2 * nt + 1) * 2 * KP * R, TILE_BYTES / 2, bar);
+        }
+    };
+    auto prefetch = [&](int w) {
+        if (w >= total || (fp.flags & 4)) return;
+        const int np = w / tiles, nt = w - np * tiles;
+        const cx<float>* base = fp.GT + (size_t)np * 2 * plane;
+        if (MIRROR) {
+            prefetch_l2_bulk(base + (size_t)nt * 2 * KP * R, TILE_BYTES);
+        } else {
+            prefetch_l2_bulk(base + (size_t)(2 * nt) * 2 * KP * R, TILE_BYTES / 2);
+            prefetch_l2_bulk(base + (size_t)(2 * nt + 1) * 2 * KP * R, TILE_BYTES / 2);
+        }
+    };
+    if (tid == 0 && (int)blockIdx.x < total) { issue(blockIdx.x); prefetch(blockIdx.x + gridDim.x); }
+    unsigned parity = 0;
+    // this thread's inputs inside the landing buffer
+    const int offA = MIRROR ? r : ((2 * r) / R) * KP * R + (2 * r) % R;
+    for (int work = blockIdx.x; work < total; work += gridDim.x) {
+        const int pair = work / tiles, tile = work - pair * tiles;
+        const int gl = tile * R + r;                           // line index inside the pair
+        const int y0 = MIRROR ? gl : 2 * gl;
+        mbar_wait(bar, parity);
+        parity ^= 1;
+        cx<float> v[E];
+        {
+            const int t = tq;
+            const cx<float>* A = X + offA;
+#pragma unroll
+            for (int n1 = 0; n1 < E; ++n1) {
+                const int k = n1 * T + t;
+                const bool direct = n1 < E / 2 || (n1 == E / 2 && t == 0);
+                const int kk = direct ? k : N - k;
+                cx<float> a, b;
+                if (MIRROR) {
+                    a = A[kk * R]; b = A[KP * R + kk * R];
+                } else {
+                    const float4 ab = *reinterpret_cast<const float4*>(A + kk * R);     // rows y0, y0 + 1 are adjacent
+                    a = mk<float>(ab.x, ab.y); b = mk<float>(ab.z, ab.w);
+                }
+                // stored values are conj(P), conj(Q).  direct: conj(P + iQ) = a - i b (k = 0, N/2: real parts
+                // only);  mirrored index: conj(conj(P) + i conj(Q)) = conj(a) - i conj(b)
+                v[n1] = direct ? ((k == 0 || 2 * k == N) ? mk<float>(a.x, -b.x) : mk<float>(a.x + b.y, a.y - b.x))
+                               : mk<float>(a.x - b.y, -a.y - b.x);
+            }
+        }
+        __syncthreads();                                       // every input is in registers: X may be overwritten
+        PRegFFT<E>::run(v);
+        tw.apply_all(v, [&](int k1, cx<float> a) { X[k1 * XS + tq * R + r] = a; });
+        __syncthreads();
+        float best, second;
+        double sum = 0.0, sumsq = 0.0;
+        {
+            cx<float> u[E];
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+                const int k1 = tq + T * m;
+#pragma unroll
+                for (int n2 = 0; n2 < T; ++n2) u[m * T + n2] = X[k1 * XS + n2 * R + r];
+            }
+            __syncthreads();                                   // X has been read: the next tile may land
+            if (tid == 0) {
+                const int nw_ = work + gridDim.x;
+                if (nw_ < total) { issue(nw_); prefetch(nw_ + gridDim.x); }
+            }
+#pragma unroll
+            for (int m = 0; m < M; ++m) PRegFFT<T>::run(u + m * T);
+            best = u[0].x; second = MIRROR ? fabsf(u[0].y) : -u[0].y;
+#pragma unroll
+            for (int j = 1; j < E; ++j) {
+                best = fmaxf(best, u[j].x);
+                second = fmaxf(second, MIRROR ? fabsf(u[j].y) : -u[j].y);
+            }
+            if (want_std) {
+#pragma unroll
+                for (int j = 0; j < E; ++j) {
+                    sum += (double)u[j].x; sumsq += (double)u[j].x * (double)u[j].x;
+                    sum -= (double)u[j].y; sumsq += (double)u[j].y * (double)u[j].y;
+                }
+            }
+        }
+        // lanes with equal r inside the warp, then the warps through shared memory
+#pragma unroll
+        for (int off = R; off < 32; off <<= 1) {
+            best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, off));
+            second = fmaxf(second, __shfl_xor_sync(0xffffffffu, second, off));
+            if (want_std) {
+                sum += __shfl_xor_sync(0xffffffffu, sum, off);
+                sumsq += __shfl_xor_sync(0xffffffffu, sumsq, off);
+            }
+        }
+        if ((tid & 31) < R) {
+            red[(warp * R + r) * 2] = best; red[(warp * R + r) * 2 + 1] = second;
+            if (want_std) { redd[(warp * R + r) * 2] = sum; redd[(warp * R + r) * 2 + 1] = sumsq; }
+        }
+        __syncthreads();
+        if (tid < R) {
+            for (int w = 1; w < NWARP; ++w) {
+                best = fmaxf(best, red[(w * R + r) * 2]); second = fmaxf(second, red[(w * R + r) * 2 + 1]);
+                if (want_std) { sum += redd[(w * R + r) * 2]; sumsq += redd[(w * R + r) * 2 + 1]; }
+            }
+            int row = y0;
+            float mir = 0.f;
+            if (MIRROR) mir = second;
             else if (second > best) { best = second; row += 1; }
             Partial& o = p.part[(size_t)pair * p.nrt + gl];
             o.val = (double)best; o.mir = (double)mir; o.sum = sum; o.sumsq = sumsq; o.idx = row * N; o.pad = 0;
