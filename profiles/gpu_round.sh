@@ -1,6 +1,6 @@
 #!/bin/bash
-# One GPU session: parity tests, bench, ncu launch list and full captures of the fast-path kernels.
-# usage (here): gpurun --timeout 1500 -- 'bash profiles/gpu_round.sh <tag>'
+# One GPU session: parity tests, smoke, bench (default + the other workloads), ncu launch list and full
+# captures of the fast-path kernels.   usage (here): gpurun --timeout 1800 -- 'bash profiles/gpu_round.sh <tag>'
 TAG=${1:-r1}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
@@ -8,9 +8,10 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit,memory.total --f
 timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_gpu.log
 tail -5 $OUT/pytest_gpu.log
 timeout 300 python __graft_entry__.py smoke > $OUT/smoke.log 2>&1; tail -2 $OUT/smoke.log
-timeout 600 python bench.py > $OUT/bench.json 2> $OUT/bench.err; tail -c 3000 $OUT/bench.json
-for wl in xcorr512_nopad xcorr256 xcorr128 xcorr1024 stitch_fine thumb150; do
-  timeout 300 python bench.py --workload $wl --steps 20 --no-cpu-baseline > $OUT/bench_$wl.json 2>> $OUT/bench.err
+timeout 900 python bench.py > $OUT/bench.json 2> $OUT/bench.err; tail -c 3000 $OUT/bench.json
+timeout 600 python bench.py --impl reference --steps 20 --warmup 3 > $OUT/bench_reference.json 2>> $OUT/bench.err; tail -c 600 $OUT/bench_reference.json
+for wl in xcorr512_nopad xcorr256 xcorr128 xcorr1024 xcorr2048 stitch_fine thumb150; do
+  timeout 300 python bench.py --workload $wl --steps 30 --no-cpu-baseline > $OUT/bench_$wl.json 2>> $OUT/bench.err
 done
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:fbk -c 400 --csv \
     --log-file $OUT/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/ncu_launches.log 2>&1
