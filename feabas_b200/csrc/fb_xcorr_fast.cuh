@@ -405,8 +405,9 @@ __device__ void kfast_columns(const FastParams& fp, unsigned char* smem)
                     // the column into its ny / rblk tiles
 #pragma unroll
                     for (int j = 0; j < E; ++j) mine[W::out_k(t, j)] = v[W::out_reg(j)];
+                    // only the lanes of this line: with two lines per warp (T = 16) `live` can differ between them
                     fence_proxy_async_smem();
-                    __syncwarp();
+                    __syncwarp(T == 32 ? 0xffffffffu : (0xffffu << (16 * lw)));
                     if (t == 0) tma_store_4d(&fp.gt_map, mine, 0, col, roleB ? 1 : 0, pair * (N / fp.rblk));
                 } else {
                     // y = t + c, c a multiple of T >= rblk: the tile index advances by c / rblk

@@ -214,3 +214,18 @@ def test_fast_path_against_oracle(fc, n, shape0, shape1, kw):
     gen = fc.xcorr_fft(a, b, force='generic', **kw)
     np.testing.assert_allclose(got[0], gen[0], atol=2e-3)
     np.testing.assert_allclose(got[1], gen[1], atol=2e-3)
+
+
+@pytest.mark.parametrize('size,n', [(128, 48), (256, 20)])
+def test_fast_path_many_work_items_per_cta(fc, size, n):
+    """More (pair, column group) / (pair, tile) work items than resident CTAs: the persistent loops of the
+    fast-path kernels (TMA store / load recycling, odd last column group) run several iterations."""
+    a, b, shifts = synth.block_pairs(n, size, seed=size + n, max_shift=size // 8)
+    got = fc.xcorr_fft(a, b, subpixel=True)
+    gen = fc.xcorr_fft(a, b, subpixel=True, force='generic')
+    np.testing.assert_array_equal(np.round(got[0]), shifts[:, 0])
+    np.testing.assert_array_equal(np.round(got[1]), shifts[:, 1])
+    np.testing.assert_allclose(got[0], gen[0], atol=2e-3)
+    np.testing.assert_allclose(got[1], gen[1], atol=2e-3)
+    np.testing.assert_allclose(got[2], gen[2], rtol=1e-4, atol=1e-6)
+    parity.check_against_oracle(tuple(v[:3] for v in got), a[:3], b[:3], subpixel=True)
