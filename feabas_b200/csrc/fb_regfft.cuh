@@ -1,4 +1,4 @@
-// fb_regfft.cuh -- register-resident FFTs of 8 / 16 / 32 complex points per thread.
+// fb_regfft.cuh -- register-resident FFTs of 8 / 16 / 32 / 64 complex points per thread.
 //
 // Radix-2 decimation-in-frequency, fully unrolled, twiddles as compile-time
 // constants with the trivial ones (1, -i, exp(-i pi/4)) special-cased.  The
@@ -16,41 +16,43 @@ template <int N> FB_HD constexpr int brev(int k)
     return r;
 }
 
-// cos / sin of 2 pi j / 32 for j = 0..8 (first octant + one), double precision literals
-FB_HD constexpr double cos32(int j)
+// cos / sin of 2 pi j / 64 for j = 0..16 (first quadrant), double precision literals
+FB_HD constexpr double cos64(int j)
 {
-    constexpr double c[9] = {1.0, 0.98078528040323044913, 0.92387953251128675613, 0.83146961230254523708,
-                             0.70710678118654752440, 0.55557023301960222474, 0.38268343236508977173,
-                             0.19509032201612826785, 0.0};
-    // reduce j (mod 32) to the first quadrant
-    j &= 31;
-    int q = j >> 3, r = j & 7;
-    double cs = c[r], sn = c[8 - r];
+    constexpr double c[17] = {1.0, 0.99518472667219688624, 0.98078528040323044913, 0.95694033573220886494,
+                              0.92387953251128675613, 0.88192126434835502971, 0.83146961230254523708,
+                              0.77301045336273696081, 0.70710678118654752440, 0.63439328416364549822,
+                              0.55557023301960222474, 0.47139673682599764856, 0.38268343236508977173,
+                              0.29028467725446236764, 0.19509032201612826785, 0.09801714032956060199, 0.0};
+    // reduce j (mod 64) to the first quadrant
+    j &= 63;
+    int q = j >> 4, r = j & 15;
+    double cs = c[r], sn = c[16 - r];
     return q == 0 ? cs : (q == 1 ? -sn : (q == 2 ? -cs : sn));
 }
-FB_HD constexpr double sin32(int j) { return cos32(j - 8); }
+FB_HD constexpr double sin64(int j) { return cos64(j - 16); }
 
-// v *= exp(-/+ 2 pi i j / n), n in {4, 8, 16, 32}
+// v *= exp(-/+ 2 pi i j / n), n in {2, 4, 8, 16, 32, 64}
 template <typename T, int N, int J, bool INV> FB_HD cx<T> twiddle_const(cx<T> v)
 {
-    constexpr int j32 = (J * (32 / N)) & 31;
-    if constexpr (j32 == 0) {
+    constexpr int j64 = (J * (64 / N)) & 63;
+    if constexpr (j64 == 0) {
         return v;
-    } else if constexpr (j32 == 8) {
+    } else if constexpr (j64 == 16) {
         return rot<T, INV>(v);
-    } else if constexpr (j32 == 16) {
+    } else if constexpr (j64 == 32) {
         return mk<T>(-v.x, -v.y);
-    } else if constexpr (j32 == 24) {
+    } else if constexpr (j64 == 48) {
         return rot<T, !INV>(v);
-    } else if constexpr (j32 == 4) {
+    } else if constexpr (j64 == 8) {
         constexpr T h = T(0.70710678118654752440);
         return INV ? mk<T>(h * (v.x - v.y), h * (v.x + v.y)) : mk<T>(h * (v.x + v.y), h * (v.y - v.x));
-    } else if constexpr (j32 == 12) {
+    } else if constexpr (j64 == 24) {
         constexpr T h = T(0.70710678118654752440);
         return INV ? mk<T>(-h * (v.x + v.y), h * (v.x - v.y)) : mk<T>(h * (v.y - v.x), -h * (v.x + v.y));
     } else {
-        constexpr T c = T(cos32(j32));
-        constexpr T s = T(INV ? sin32(j32) : -sin32(j32));
+        constexpr T c = T(cos64(j64));
+        constexpr T s = T(INV ? sin64(j64) : -sin64(j64));
         return mk<T>(v.x * c - v.y * s, v.x * s + v.y * c);
     }
 }
@@ -119,25 +121,25 @@ __device__ __forceinline__ cx<float> pscale(cx<float> a, float s)
 
 template <int N, int J> __device__ __forceinline__ cx<float> ptwiddle_diff(cx<float> a, cx<float> b)
 {
-    constexpr int j32 = (J * (32 / N)) & 31;
-    if constexpr (j32 == 0) {
+    constexpr int j64 = (J * (64 / N)) & 63;
+    if constexpr (j64 == 0) {
         return psub(a, b);
-    } else if constexpr (j32 == 8) {            // -i (a - b)
+    } else if constexpr (j64 == 16) {           // -i (a - b)
         return mk<float>(a.y - b.y, b.x - a.x);
-    } else if constexpr (j32 == 16) {
+    } else if constexpr (j64 == 32) {
         return psub(b, a);
-    } else if constexpr (j32 == 24) {           // +i (a - b)
+    } else if constexpr (j64 == 48) {           // +i (a - b)
         return mk<float>(b.y - a.y, a.x - b.x);
-    } else if constexpr (j32 == 4) {
+    } else if constexpr (j64 == 8) {
         const cx<float> d = psub(a, b);
         return pscale(mk<float>(d.x + d.y, d.y - d.x), 0.70710678118654752440f);
-    } else if constexpr (j32 == 12) {
+    } else if constexpr (j64 == 24) {
         const cx<float> d = psub(a, b);
         return pscale(mk<float>(d.y - d.x, -d.x - d.y), 0.70710678118654752440f);
     } else {
         const cx<float> d = psub(a, b);
-        constexpr float c = (float)cos32(j32);
-        constexpr float s = (float)(-sin32(j32));
+        constexpr float c = (float)cos64(j64);
+        constexpr float s = (float)(-sin64(j64));
         return mk<float>(d.x * c - d.y * s, d.x * s + d.y * c);
     }
 }

@@ -103,27 +103,29 @@ __global__ void __launch_bounds__(256) fbk_channel_mean(const cx<T>* __restrict_
 constexpr int kNW1 = 8, kNW2 = 8;                    // warps per CTA of K1 / K2
 // K3: lines (= GT tile rows) per CTA for T lanes per line; CTA = T * R threads, 512 threads per SM
 template <int T> constexpr int kR3() { return 8; }
+// CTAs per SM the register budget allows: a lane holds E complex points (E = 64: 128 data registers, one CTA)
+template <int E> constexpr int kOcc(int full) { return E > 32 ? 1 : full; }
 template <int E, int T, typename TI, bool PRUNED>
-__global__ void __launch_bounds__(32 * kNW1, 16 / kNW1) fbk_fast_rows_forward(const __grid_constant__ FastParams fp)
+__global__ void __launch_bounds__(32 * kNW1, kOcc<E>(16 / kNW1)) fbk_fast_rows_forward(const __grid_constant__ FastParams fp)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     kfast_rows_forward<E, T, kNW1, TI, PRUNED>(fp, smem);
 }
 template <int E, int T, bool PRUNED>
-__global__ void __launch_bounds__(32 * kNW2, 16 / kNW2) fbk_fast_columns(const __grid_constant__ FastParams fp)
+__global__ void __launch_bounds__(32 * kNW2, kOcc<E>(16 / kNW2)) fbk_fast_columns(const __grid_constant__ FastParams fp)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     kfast_columns<E, T, kNW2, PRUNED>(fp, smem);
 }
 template <int E, int T, int R, int RB = R>
-__global__ void __launch_bounds__(T * R, 512 / (T * R)) fbk_fast_rows_inverse(const __grid_constant__ FastParams fp)
+__global__ void __launch_bounds__(T * R, kOcc<E>(512 / (T * R))) fbk_fast_rows_inverse(const __grid_constant__ FastParams fp)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     kfast_rows_inverse<E, T, R, RB>(fp, smem);
 }
 
 template <int E, int T, int R, bool MIRROR>
-__global__ void __launch_bounds__(T * R, 512 / (T * R)) fbk_fast_rows_inverse_tma(const __grid_constant__ FastParams fp)
+__global__ void __launch_bounds__(T * R, kOcc<E>(512 / (T * R))) fbk_fast_rows_inverse_tma(const __grid_constant__ FastParams fp)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     kfast_rows_inverse_tma<E, T, R, MIRROR>(fp, smem);
@@ -258,6 +260,7 @@ static int set_attrs(int device)
     RSF(16, 16);
     RSF(32, 16);
     RSF(32, 32);
+    RSF(64, 32);
     RS((fbk_fast_rows_inverse<32, 32, 4>));
     RS((fbk_fast_rows_inverse<32, 32, 4, 8>));
 #undef RSF
@@ -284,7 +287,7 @@ struct Problem {
     fb_xcorr_ext ext;
 };
 
-static bool fast_size(int n) { return n == 256 || n == 512 || n == 1024; }
+static bool fast_size(int n) { return n == 256 || n == 512 || n == 1024 || n == 2048; }
 
 static int make_problem(Problem& q, int n, int h0, int w0, int h1, int w1, int in_dtype, int fft_h, int fft_w, int flags,
                         const fb_xcorr_ext* ext = nullptr)
@@ -380,7 +383,7 @@ static void launch_fast_k2(const FastParams& fp, bool pruned, int grid, size_t s
 }
 static void fast_et(int n, int& E, int& T)
 {
-    if (n == 256) { E = 16; T = 16; } else if (n == 512) { E = 32; T = 16; } else { E = 32; T = 32; }
+    if (n == 256) { E = 16; T = 16; } else if (n == 512) { E = 32; T = 16; } else if (n == 1024) { E = 32; T = 32; } else { E = 64; T = 32; }
 }
 static size_t fast_smem(int n, int nw)
 {
@@ -437,7 +440,7 @@ static int launch_fast(const Problem& q, StreamCtx& ctx, XcParams& p, int nb, cu
     fp.GT = reinterpret_cast<cx<float>*>(w + f0 + f1);
     p.part = reinterpret_cast<Partial*>(w + f0 + f1 + gg);
     fp.rblk = TX == 32 ? kR3<32>() : kR3<16>();          // rows per K3 tile
-    if (TX == 32 && (g_opt_fast_flags & 32)) fp.rblk = 4;
+    if (q.nx == 1024 && (g_opt_fast_flags & 32)) fp.rblk = 4;
     fp.flags = (int)(g_opt_fast_flags & ~(16 | 32));
     fp.use_tma = make_gt_map(&fp.gt_map, fp.GT, nb, q.ny, g.kp, fp.rblk) ? 1 : 0;
     p.G = fp.GT; p.gt_layout = fp.rblk; p.nrt = q.nrt; p.out_scale = p.scale;
@@ -447,33 +450,35 @@ static int launch_fast(const Problem& q, StreamCtx& ctx, XcParams& p, int nb, cu
     {
         const int lpw = 32 / TX, TR = 2 * lpw * kNW1;
         const int work = nb * (q.hp0 / TR + q.hp1 / TR);
-        const int cap = g_num_sms * (16 / kNW1);
+        const int cap = g_num_sms * (EX > 32 ? 1 : 16 / kNW1);
         const int grid = work < cap ? work : cap;
         const bool pruned = q.w0 <= q.nx / 2 && q.w1 <= q.nx / 2;
         ProfScope ps(ctx, st, SLOT_ROWS_FWD);
         if (q.nx == 256) launch_fast_k1<16, 16, TI>(fp, pruned, grid, fast_smem(256, kNW1), st);
         else if (q.nx == 512) launch_fast_k1<32, 16, TI>(fp, pruned, grid, fast_smem(512, kNW1), st);
-        else launch_fast_k1<32, 32, TI>(fp, pruned, grid, fast_smem(1024, kNW1), st);
+        else if (q.nx == 1024) launch_fast_k1<32, 32, TI>(fp, pruned, grid, fast_smem(1024, kNW1), st);
+        else launch_fast_k1<64, 32, TI>(fp, pruned, grid, fast_smem(2048, kNW1), st);
     }
     // K2
     {
         const int cpg = (32 / TY) * (kNW2 / 2);
         const int work = nb * ((g.kp + cpg - 1) / cpg);
-        const int cap = g_num_sms * (16 / kNW2);
+        const int cap = g_num_sms * (EY > 32 ? 1 : 16 / kNW2);
         const int grid = work < cap ? work : cap;
         const bool pruned = q.hp0 <= q.ny / 2 && q.hp1 <= q.ny / 2;
         ProfScope ps(ctx, st, SLOT_COLUMNS);
         if (q.ny == 256) launch_fast_k2<16, 16>(fp, pruned, grid, fast_smem(256, kNW2), st);
         else if (q.ny == 512) launch_fast_k2<32, 16>(fp, pruned, grid, fast_smem(512, kNW2), st);
-        else launch_fast_k2<32, 32>(fp, pruned, grid, fast_smem(1024, kNW2), st);
+        else if (q.ny == 1024) launch_fast_k2<32, 32>(fp, pruned, grid, fast_smem(1024, kNW2), st);
+        else launch_fast_k2<64, 32>(fp, pruned, grid, fast_smem(2048, kNW2), st);
     }
     // K3: TX * R threads own R lines (R <= rblk rows of a GT tile)
     {
         int R = fp.rblk;
-        if (TX == 32 && (g_opt_fast_flags & 16)) R = 4;          // experiment: half-tile CTAs
+        if (q.nx == 1024 && (g_opt_fast_flags & 16)) R = 4;          // experiment: half-tile CTAs
         const int nt = TX * R;
         const int work = nb * (q.nrt / R);
-        const int cap = g_num_sms * (512 / nt);
+        const int cap = g_num_sms * (EX > 32 ? 1 : 512 / nt);
         const int grid = work < cap ? work : cap;
         const int XS = TX * R + (R < 16 ? R : 0);
         const size_t sm3 = ((size_t)EX * XS + (kLaneTwiddles ? 0 : q.nx)) * sizeof(cx<float>) + (nt / 32) * R * 2 * (sizeof(float) + sizeof(double));
@@ -485,9 +490,11 @@ static int launch_fast(const Problem& q, StreamCtx& ctx, XcParams& p, int nb, cu
                          else fbk_fast_rows_inverse_tma<E_, T_, kR3<T_>(), false><<<grid, nt, sm3t, st>>>(fp); } while (0)
         if (tma3 && q.nx == 256) K3T(16, 16);
         else if (tma3 && q.nx == 512) K3T(32, 16);
-        else if (tma3) K3T(32, 32);
+        else if (tma3 && q.nx == 1024) K3T(32, 32);
+        else if (tma3) K3T(64, 32);
         else if (q.nx == 256) fbk_fast_rows_inverse<16, 16, kR3<16>()><<<grid, nt, sm3, st>>>(fp);
         else if (q.nx == 512) fbk_fast_rows_inverse<32, 16, kR3<16>()><<<grid, nt, sm3, st>>>(fp);
+        else if (q.nx == 2048) fbk_fast_rows_inverse<64, 32, kR3<32>()><<<grid, nt, sm3, st>>>(fp);
         else if (R == 4 && fp.rblk == 8) fbk_fast_rows_inverse<32, 32, 4, 8><<<grid, nt, sm3, st>>>(fp);
         else if (R == 4) fbk_fast_rows_inverse<32, 32, 4><<<grid, nt, sm3, st>>>(fp);
         else fbk_fast_rows_inverse<32, 32, kR3<32>()><<<grid, nt, sm3, st>>>(fp);

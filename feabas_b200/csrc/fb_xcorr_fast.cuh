@@ -384,19 +384,34 @@ __device__ void kfast_columns(const FastParams& fp, unsigned char* smem)
                 // next transform: a register permutation, no exchange needed
                 // unscaled: 1 / (ny nx) is applied once per pair by the finalize kernel (XcParams::out_scale);
                 // confidence and sub-pixel offsets are ratios
-                cx<float> u[E];
-                if (!roleB) {
+                if constexpr (E <= 32) {
+                    cx<float> u[E];
+                    if (!roleB) {
 #pragma unroll
-                    for (int j = 0; j < E; ++j) u[j] = cmulc(v[W::out_reg(j)], other[W::out_k(t, j)]);      // conj(P) = F0 conj(F1)
+                        for (int j = 0; j < E; ++j) u[j] = cmulc(v[W::out_reg(j)], other[W::out_k(t, j)]);      // conj(P) = F0 conj(F1)
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < E; ++j) {                                                         // conj(Q) = conj(F1 F0)
+                            const cx<float> o = other[W::out_k(t, j)], m = v[W::out_reg(j)];
+                            u[j] = mk<float>(m.x * o.x - m.y * o.y, -(m.x * o.y) - m.y * o.x);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < E; ++j) v[j] = u[j];
                 } else {
+                    // E = 64: no room for a second register file image -- the own spectrum is read back from
+                    // the region it was just written to (natural order) instead of being permuted in registers
+                    if (!roleB) {
 #pragma unroll
-                    for (int j = 0; j < E; ++j) {                                                         // conj(Q) = conj(F1 F0)
-                        const cx<float> o = other[W::out_k(t, j)], m = v[W::out_reg(j)];
-                        u[j] = mk<float>(m.x * o.x - m.y * o.y, -(m.x * o.y) - m.y * o.x);
+                        for (int j = 0; j < E; ++j) v[j] = cmulc(mine[W::out_k(t, j)], other[W::out_k(t, j)]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < E; ++j) {
+                            const cx<float> o = other[W::out_k(t, j)], m = mine[W::out_k(t, j)];
+                            v[j] = mk<float>(m.x * o.x - m.y * o.y, -(m.x * o.y) - m.y * o.x);
+                        }
                     }
                 }
-#pragma unroll
-                for (int j = 0; j < E; ++j) v[j] = u[j];
                 asm volatile("bar.sync %0, 64;" ::"r"(pw + 1) : "memory");
                 if (!second_phase) break;
             } else if (live && !(fp.flags & 64)) {

@@ -179,7 +179,7 @@ def test_full_size_ground_truth(fc):
 
 
 FAST_CASES = [
-    # (n, shape0, shape1, kwargs) -- every FFT grid here is a power of two in {256, 512, 1024}
+    # (n, shape0, shape1, kwargs) -- every FFT grid here is a power of two in {256, 512, 1024, 2048}
     (5, (128, 128), (128, 128), dict(subpixel=True)),                          # 256 x 256
     (3, (127, 127), (127, 127), dict(subpixel=True)),                          # 256 x 256, ragged rows
     (3, (110, 120), (147, 137), dict(subpixel=True)),                          # 256 x 256, different shapes
@@ -193,6 +193,11 @@ FAST_CASES = [
     (3, (256, 256), (256, 256), dict(subpixel=True, conf_mode=1)),             # STD
     (3, (255, 255), (255, 255), dict(subpixel=True, conf_mode=0, pad=False)),  # 256^2 odd rows, NONE pairs rows
     (2, (501, 512), (501, 512), dict(subpixel=True, conf_mode=1, pad=False)),  # 512 x 512 (odd rows)
+    (2, (1024, 1024), (1024, 1024), dict(subpixel=True)),                      # 2048 x 2048 (64 points per lane)
+    (2, (1024, 128), (1024, 128), dict(subpixel=True)),                        # 2048 x 256
+    (2, (256, 2048), (256, 2048), dict(subpixel=True, pad=False)),             # 256 x 2048, no pruning
+    (2, (1020, 1017), (1020, 1017), dict(subpixel=True, conf_mode=1)),         # 2048 x 2048 ragged, STD
+    (2, (2048, 512), (2048, 512), dict(subpixel=False, conf_mode=0, pad=False)),  # 2048 x 512, unpruned columns, NONE
 ]
 
 
