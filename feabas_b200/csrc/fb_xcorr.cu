@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(256) fbk_channel_mean(const cx<T>* __restrict_
 // ---- register-resident fast path (power-of-two grids, float32 compute) ----
 constexpr int kNW1 = 8, kNW2 = 8;                    // warps per CTA of K1 / K2
 // K3: lines (= GT tile rows) per CTA for T lanes per line; CTA = T * R threads, 512 threads per SM
-template <int T> constexpr int kR3() { return 8; }
+template <int T> constexpr int kR3() { return T > 32 ? 4 : 8; }
 // CTAs per SM the register budget allows: a lane holds E complex points (E = 64: 128 data registers, one CTA)
 template <int E> constexpr int kOcc(int full) { return E > 32 ? 1 : full; }
 template <int E, int T, typename TI, bool PRUNED>
@@ -261,6 +261,7 @@ static int set_attrs(int device)
     RSF(32, 16);
     RSF(32, 32);
     RSF(64, 32);
+    RSF(64, 64);
     RS((fbk_fast_rows_inverse<32, 32, 4>));
     RS((fbk_fast_rows_inverse<32, 32, 4, 8>));
 #undef RSF
@@ -287,7 +288,7 @@ struct Problem {
     fb_xcorr_ext ext;
 };
 
-static bool fast_size(int n) { return n == 256 || n == 512 || n == 1024 || n == 2048; }
+static bool fast_size(int n) { return n == 256 || n == 512 || n == 1024 || n == 2048 || n == 4096; }
 
 static int make_problem(Problem& q, int n, int h0, int w0, int h1, int w1, int in_dtype, int fft_h, int fft_w, int flags,
                         const fb_xcorr_ext* ext = nullptr)
@@ -383,12 +384,13 @@ static void launch_fast_k2(const FastParams& fp, bool pruned, int grid, size_t s
 }
 static void fast_et(int n, int& E, int& T)
 {
-    if (n == 256) { E = 16; T = 16; } else if (n == 512) { E = 32; T = 16; } else if (n == 1024) { E = 32; T = 32; } else { E = 64; T = 32; }
+    if (n == 256) { E = 16; T = 16; } else if (n == 512) { E = 32; T = 16; } else if (n == 1024) { E = 32; T = 32; } else if (n == 2048) { E = 64; T = 32; } else { E = 64; T = 64; }
 }
 static size_t fast_smem(int n, int nw)
 {
     int E, T; fast_et(n, E, T);
-    return ((size_t)nw * (32 / T) * (n + E + 16) + (kLaneTwiddles ? 0 : n)) * sizeof(cx<float>);
+    const int lines = T > 32 ? nw / (T / 32) : nw * (32 / T);
+    return ((size_t)lines * (n + E + 16) + (kLaneTwiddles ? 0 : n)) * sizeof(cx<float>);
 }
 
 static int g_num_sms = 0;
@@ -413,10 +415,12 @@ static bool make_gt_map(CUtensorMap* map, void* gt, int nb, int ny, int kp, int 
             g_encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
         cudaGetLastError();
     }
-    if (!g_encode_tiled || ny / rblk > 256) return false;
+    if (!g_encode_tiled) return false;
+    const int tiles = ny / rblk, boxt = tiles > 256 ? 256 : tiles;      // a box dimension is at most 256: K2 stores long columns in pieces
+    if (tiles % boxt) return false;
     const cuuint64_t dims[4] = {(cuuint64_t)rblk, (cuuint64_t)kp, 2, (cuuint64_t)nb * (ny / rblk)};
     const cuuint64_t strides[3] = {(cuuint64_t)rblk * 8, (cuuint64_t)kp * rblk * 8, (cuuint64_t)2 * kp * rblk * 8};
-    const cuuint32_t box[4] = {(cuuint32_t)rblk, 1, 1, (cuuint32_t)(ny / rblk)};
+    const cuuint32_t box[4] = {(cuuint32_t)rblk, 1, 1, (cuuint32_t)boxt};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     return g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, gt, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -439,16 +443,18 @@ static int launch_fast(const Problem& q, StreamCtx& ctx, XcParams& p, int nb, cu
     fp.FT1 = reinterpret_cast<cx<float>*>(w + f0);
     fp.GT = reinterpret_cast<cx<float>*>(w + f0 + f1);
     p.part = reinterpret_cast<Partial*>(w + f0 + f1 + gg);
-    fp.rblk = TX == 32 ? kR3<32>() : kR3<16>();          // rows per K3 tile
+    fp.rblk = TX == 64 ? kR3<64>() : (TX == 32 ? kR3<32>() : kR3<16>());          // rows per K3 tile
     if (q.nx == 1024 && (g_opt_fast_flags & 32)) fp.rblk = 4;
     fp.flags = (int)(g_opt_fast_flags & ~(16 | 32));
     fp.use_tma = make_gt_map(&fp.gt_map, fp.GT, nb, q.ny, g.kp, fp.rblk) ? 1 : 0;
+    fp.gt_tiles = q.ny / fp.rblk;
+    fp.gt_pieces = fp.gt_tiles > 256 ? fp.gt_tiles / 256 : 1;
     p.G = fp.GT; p.gt_layout = fp.rblk; p.nrt = q.nrt; p.out_scale = p.scale;
     fp.hp0 = q.hp0; fp.hp1 = q.hp1;
     fp.x = p;
     // K1
     {
-        const int lpw = 32 / TX, TR = 2 * lpw * kNW1;
+        const int TR = 2 * (TX > 32 ? kNW1 / (TX / 32) : (32 / TX) * kNW1);
         const int work = nb * (q.hp0 / TR + q.hp1 / TR);
         const int cap = g_num_sms * (EX > 32 ? 1 : 16 / kNW1);
         const int grid = work < cap ? work : cap;
@@ -457,11 +463,12 @@ static int launch_fast(const Problem& q, StreamCtx& ctx, XcParams& p, int nb, cu
         if (q.nx == 256) launch_fast_k1<16, 16, TI>(fp, pruned, grid, fast_smem(256, kNW1), st);
         else if (q.nx == 512) launch_fast_k1<32, 16, TI>(fp, pruned, grid, fast_smem(512, kNW1), st);
         else if (q.nx == 1024) launch_fast_k1<32, 32, TI>(fp, pruned, grid, fast_smem(1024, kNW1), st);
-        else launch_fast_k1<64, 32, TI>(fp, pruned, grid, fast_smem(2048, kNW1), st);
+        else if (q.nx == 2048) launch_fast_k1<64, 32, TI>(fp, pruned, grid, fast_smem(2048, kNW1), st);
+        else launch_fast_k1<64, 64, TI>(fp, pruned, grid, fast_smem(4096, kNW1), st);
     }
     // K2
     {
-        const int cpg = (32 / TY) * (kNW2 / 2);
+        const int cpg = (TY > 32 ? kNW2 / (TY / 32) : (32 / TY) * kNW2) / 2;
         const int work = nb * ((g.kp + cpg - 1) / cpg);
         const int cap = g_num_sms * (EY > 32 ? 1 : 16 / kNW2);
         const int grid = work < cap ? work : cap;
@@ -470,7 +477,8 @@ static int launch_fast(const Problem& q, StreamCtx& ctx, XcParams& p, int nb, cu
         if (q.ny == 256) launch_fast_k2<16, 16>(fp, pruned, grid, fast_smem(256, kNW2), st);
         else if (q.ny == 512) launch_fast_k2<32, 16>(fp, pruned, grid, fast_smem(512, kNW2), st);
         else if (q.ny == 1024) launch_fast_k2<32, 32>(fp, pruned, grid, fast_smem(1024, kNW2), st);
-        else launch_fast_k2<64, 32>(fp, pruned, grid, fast_smem(2048, kNW2), st);
+        else if (q.ny == 2048) launch_fast_k2<64, 32>(fp, pruned, grid, fast_smem(2048, kNW2), st);
+        else launch_fast_k2<64, 64>(fp, pruned, grid, fast_smem(4096, kNW2), st);
     }
     // K3: TX * R threads own R lines (R <= rblk rows of a GT tile)
     {
@@ -491,10 +499,12 @@ static int launch_fast(const Problem& q, StreamCtx& ctx, XcParams& p, int nb, cu
         if (tma3 && q.nx == 256) K3T(16, 16);
         else if (tma3 && q.nx == 512) K3T(32, 16);
         else if (tma3 && q.nx == 1024) K3T(32, 32);
-        else if (tma3) K3T(64, 32);
+        else if (tma3 && q.nx == 2048) K3T(64, 32);
+        else if (tma3) K3T(64, 64);
         else if (q.nx == 256) fbk_fast_rows_inverse<16, 16, kR3<16>()><<<grid, nt, sm3, st>>>(fp);
         else if (q.nx == 512) fbk_fast_rows_inverse<32, 16, kR3<16>()><<<grid, nt, sm3, st>>>(fp);
         else if (q.nx == 2048) fbk_fast_rows_inverse<64, 32, kR3<32>()><<<grid, nt, sm3, st>>>(fp);
+        else if (q.nx == 4096) fbk_fast_rows_inverse<64, 64, kR3<64>()><<<grid, nt, sm3, st>>>(fp);
         else if (R == 4 && fp.rblk == 8) fbk_fast_rows_inverse<32, 32, 4, 8><<<grid, nt, sm3, st>>>(fp);
         else if (R == 4) fbk_fast_rows_inverse<32, 32, 4><<<grid, nt, sm3, st>>>(fp);
         else fbk_fast_rows_inverse<32, 32, kR3<32>()><<<grid, nt, sm3, st>>>(fp);

@@ -108,12 +108,29 @@ template <int E, int T> struct StageTw {
     static constexpr __host__ __device__ int smem_entries() { return kLaneTwiddles ? 0 : E * T; }
 };
 
+// named barrier over `nthreads` threads (a multiple of 32); id 0 is __syncthreads
+__device__ __forceinline__ void named_barrier(int id, int nthreads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 template <int E, int T> struct WarpFFT {
-    static_assert(T == 16 || T == 32, "lanes per line");
+    static_assert(T == 16 || T == 32 || T == 64, "lanes per line");
     static_assert(E % T == 0 && E / T <= 2, "E/T stage-B transforms per lane");
     static constexpr int N = E * T;
-    static constexpr int LPW = 32 / T;        // lines per warp
+    static constexpr int WPL = T > 32 ? T / 32 : 1;   // warps per line (T = 64: the line's lanes span two adjacent warps)
+    static constexpr int LPW = T >= 32 ? 1 : 32 / T;  // lines per warp
     static constexpr int M = E / T;           // stage-B transforms per lane
+    // lines a CTA of NW warps works on at a time
+    static constexpr __host__ __device__ int lines_per_cta(int nw) { return WPL > 1 ? nw / WPL : nw * LPW; }
+    // lane within the line / line within the CTA of this thread
+    static __device__ __forceinline__ int lane_in_line(int warp, int lane) { return WPL > 1 ? (warp % WPL) * 32 + lane : lane % T; }
+    static __device__ __forceinline__ int line_in_cta(int warp, int lane) { return WPL > 1 ? warp / WPL : warp * LPW + lane / T; }
+    // all lanes of a line (bar: a named barrier id private to the line, used only when the line spans warps)
+    static __device__ __forceinline__ void line_sync(int bar)
+    {
+        if constexpr (WPL > 1) named_barrier(bar, 32 * WPL); else __syncwarp();
+    }
     static constexpr int RS = N + E + 1;      // minimum slots per line region
     // smallest region stride >= RS with stride % 16 == m: makes accesses by (line-minor, slot-major)
     // thread groups of 16/m lines conflict free
@@ -130,7 +147,7 @@ template <int E, int T> struct WarpFFT {
     // runs ONE butterfly body (instruction-cache footprint).
     template <bool PRUNED>
     static __device__ __forceinline__ void run(cx<float>* v, cx<float>* region, const StageTw<E, T>& tw, int t,
-                                               bool pruned_now = true)
+                                               bool pruned_now = true, int bar = 1)
     {
         // first radix-2 level: skipped arithmetic when the upper half of the input is zero; the
         // remaining levels are one shared body
@@ -138,13 +155,13 @@ template <int E, int T> struct WarpFFT {
         PRegFFT<E / 2>::run(v);
         PRegFFT<E / 2>::run(v + E / 2);
         tw.apply_all(v, [&](int k1, cx<float> a) { region[k1 * (T + 1) + t] = a; });
-        __syncwarp();
+        line_sync(bar);
 #pragma unroll
         for (int m = 0; m < M; ++m) {
 #pragma unroll
             for (int n2 = 0; n2 < T; ++n2) v[m * T + n2] = region[(t + T * m) * (T + 1) + n2];
         }
-        __syncwarp();
+        line_sync(bar);
 #pragma unroll
         for (int m = 0; m < M; ++m) PRegFFT<T>::run(v + m * T);
     }
@@ -217,6 +234,7 @@ struct FastParams {
     int hp0, hp1;
     int rblk;               // rows per K3 tile, a power of two <= 16
     int use_tma;            // K2 stores its columns with gt_map (cp.async.bulk.tensor)
+    int gt_tiles, gt_pieces; // ny / rblk; TMA stores per column (a box holds at most 256 tiles)
     alignas(64) CUtensorMap gt_map;   // G^T as a 4-D tensor of 8-byte elements: [n * ny / rblk][P|Q][kp][rblk], box = one column
     int flags;              // experiment switches (fb_set_option "fast_flags"): 1/2/4 = no L2 prefetch in
                             // K1/K2/K3, 8 = K2 partners are warps (w, w + NW/2) instead of (2w, 2w+1)
@@ -236,12 +254,12 @@ template <int E, int T, int NW, typename TI, bool PRUNED>
 __device__ void kfast_rows_forward(const FastParams& fp, unsigned char* smem)
 {
     using W = WarpFFT<E, T>;
-    constexpr int N = W::N, LPW = W::LPW, LPC = LPW * NW, TR = 2 * LPC, NT = 32 * NW;
+    constexpr int N = W::N, LPC = W::lines_per_cta(NW), TR = 2 * LPC, NT = 32 * NW;
     constexpr int RS = W::stride_mod16(LPC >= 16 ? 1 : 16 / LPC);
     const XcParams& p = fp.x;
     cx<float>* regions = reinterpret_cast<cx<float>*>(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int t = lane % T, lw = lane / T;                 // lane within line, line within warp
+    const int t = W::lane_in_line(warp, lane);             // lane within line
     StageTw<E, T> tw;
     tw.init(fp.twx, regions + LPC * RS, t, tid, NT);
     const int tiles0 = fp.hp0 / TR, tiles1 = fp.hp1 / TR, tpp = tiles0 + tiles1;
@@ -273,7 +291,7 @@ __device__ void kfast_rows_forward(const FastParams& fp, unsigned char* smem)
                 }
             }
         }
-        const int line = warp * LPW + lw;                  // line within the tile
+        const int line = W::line_in_cta(warp, lane);       // line within the tile
         const int rA = row0 + 2 * line, rB = rA + 1;
         cx<float>* region = regions + line * RS;
         cx<float> v[E];
@@ -292,7 +310,7 @@ __device__ void kfast_rows_forward(const FastParams& fp, unsigned char* smem)
 #pragma unroll
             for (int n1 = 0; n1 < E; ++n1) v[n1] = mk<float>(0.f, 0.f);
         }
-        W::template run<PRUNED>(v, region, tw, t);
+        W::template run<PRUNED>(v, region, tw, t, true, 1 + line);
 #pragma unroll
         for (int j = 0; j < E; ++j) region[W::out_k(t, j)] = v[W::out_reg(j)];
         __syncthreads();
@@ -327,24 +345,28 @@ template <int E, int T, int NW, bool PRUNED0>
 __device__ void kfast_columns(const FastParams& fp, unsigned char* smem)
 {
     using W = WarpFFT<E, T>;
-    constexpr int N = W::N, LPW = W::LPW, RS = (W::RS + 15) & ~15, CPG = LPW * (NW / 2), NT = 32 * NW;   // CPG columns per CTA;
-                                                                  // regions are 128-byte aligned (TMA source)
+    constexpr int N = W::N, LPW = W::LPW, WPL = W::WPL, RS = (W::RS + 15) & ~15, NT = 32 * NW;
+    constexpr int CPG = W::lines_per_cta(NW) / 2;           // columns per CTA; regions are 128-byte aligned (TMA source)
+    constexpr int PT = 64 * WPL;                            // threads of a pair of partner lines
     const XcParams& p = fp.x;
     cx<float>* regions = reinterpret_cast<cx<float>*>(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int t = lane % T, lw = lane / T;
+    const int t = W::lane_in_line(warp, lane), lw = WPL > 1 ? 0 : lane / T;
     StageTw<E, T> tw;
-    tw.init(fp.twy, regions + NW * LPW * RS, t, tid, NT);
+    tw.init(fp.twy, regions + W::lines_per_cta(NW) * RS, t, tid, NT);
     // partners are ADJACENT warps (2 pw, 2 pw + 1): they sit on different SM sub-partitions, so the
     // four warps an SMSP schedules belong to four different pairs and drift through the
-    // FP-only and shared-memory-only phases independently
-    const bool split = fp.flags & 8;
-    const bool roleB = split ? warp >= NW / 2 : (warp & 1);
-    const int pw = split ? (roleB ? warp - NW / 2 : warp) : warp >> 1;   // pair-of-warps index
+    // FP-only and shared-memory-only phases independently.  (T = 64: a line spans two warps, partners
+    // are adjacent warp pairs.)
+    const bool split = WPL == 1 && (fp.flags & 8);
+    const int wl = warp / WPL;                              // "line warp": index of the warp group that owns a line set
+    const bool roleB = split ? warp >= NW / 2 : (wl & 1);
+    const int pw = split ? (roleB ? warp - NW / 2 : warp) : wl >> 1;     // pair-of-lines index
+    const int lbar = 1 + NW / 2 + wl;                       // named barrier of this line (used when WPL > 1)
     const bool mirror = p.conf_mode == CONF_MIRROR;
     const int kp = p.kp, groups = (kp + CPG - 1) / CPG;
-    cx<float>* mine = regions + (warp * LPW + lw) * RS;
-    cx<float>* other = regions + ((split ? (roleB ? pw : pw + NW / 2) : (warp ^ 1)) * LPW + lw) * RS;
+    cx<float>* mine = regions + (wl * LPW + lw) * RS;
+    cx<float>* other = regions + ((split ? (roleB ? pw : pw + NW / 2) : (wl ^ 1)) * LPW + lw) * RS;
     const int hp = roleB ? fp.hp1 : fp.hp0;
     const bool second_phase = !roleB || mirror;
     const bool tma = fp.use_tma && !(fp.flags & 2048);
@@ -354,9 +376,9 @@ __device__ void kfast_columns(const FastParams& fp, unsigned char* smem)
         const bool live = col < kp;
         if (tma) {                                         // the previous column's TMA store has read `mine`
             if (t == 0) tma_store_wait_read();
-            __syncwarp();
+            W::line_sync(lbar);
         }
-        if (lane == 0 && pw == 0 && !(fp.flags & 2)) {     // the CTA's next column group (contiguous in FT) -> L2
+        if ((WPL > 1 ? t == 0 : lane == 0) && pw == 0 && !(fp.flags & 2)) {     // the CTA's next column group (contiguous in FT) -> L2
             const int nw_ = work + gridDim.x;
             if (nw_ < p.n * groups) {
                 const int np = nw_ / groups, ng = nw_ - np * groups;
@@ -375,11 +397,11 @@ __device__ void kfast_columns(const FastParams& fp, unsigned char* smem)
         }
 #pragma unroll 1
         for (int phase = 0; phase < 2; ++phase) {
-            W::template run<PRUNED0>(v, mine, tw, t, phase == 0);
+            W::template run<PRUNED0>(v, mine, tw, t, phase == 0, lbar);
             if (phase == 0) {
 #pragma unroll
                 for (int j = 0; j < E; ++j) mine[W::out_k(t, j)] = v[W::out_reg(j)];
-                asm volatile("bar.sync %0, 64;" ::"r"(pw + 1) : "memory");
+                named_barrier(pw + 1, PT);
                 // the output of lane t, k = t + T j, is exactly the input element n1 = j of the
                 // next transform: a register permutation, no exchange needed
                 // unscaled: 1 / (ny nx) is applied once per pair by the finalize kernel (XcParams::out_scale);
@@ -412,7 +434,7 @@ __device__ void kfast_columns(const FastParams& fp, unsigned char* smem)
                         }
                     }
                 }
-                asm volatile("bar.sync %0, 64;" ::"r"(pw + 1) : "memory");
+                named_barrier(pw + 1, PT);
                 if (!second_phase) break;
             } else if (live && !(fp.flags & 64)) {
                 if (tma) {
@@ -422,8 +444,14 @@ __device__ void kfast_columns(const FastParams& fp, unsigned char* smem)
                     for (int j = 0; j < E; ++j) mine[W::out_k(t, j)] = v[W::out_reg(j)];
                     // only the lanes of this line: with two lines per warp (T = 16) `live` can differ between them
                     fence_proxy_async_smem();
-                    __syncwarp(T == 32 ? 0xffffffffu : (0xffffu << (16 * lw)));
-                    if (t == 0) tma_store_4d(&fp.gt_map, mine, 0, col, roleB ? 1 : 0, pair * (N / fp.rblk));
+                    if constexpr (WPL > 1) W::line_sync(lbar);
+                    else __syncwarp(T == 32 ? 0xffffffffu : (0xffffu << (16 * lw)));
+                    if (t == 0) {
+                        // the box of the tensor map holds at most 256 tiles: long columns leave in several pieces
+                        tma_store_4d(&fp.gt_map, mine, 0, col, roleB ? 1 : 0, pair * fp.gt_tiles);
+                        for (int i = 1; i < fp.gt_pieces; ++i)
+                            tma_store_4d(&fp.gt_map, mine + i * 256 * fp.rblk, 0, col, roleB ? 1 : 0, pair * fp.gt_tiles + i * 256);
+                    }
                 } else {
                     // y = t + c, c a multiple of T >= rblk: the tile index advances by c / rblk
                     const int R = fp.rblk;
@@ -437,7 +465,7 @@ __device__ void kfast_columns(const FastParams& fp, unsigned char* smem)
     }
     if (tma) {                                             // shared memory must outlive the last store's read
         if (t == 0) tma_store_wait_read();
-        __syncwarp();
+        W::line_sync(lbar);
     }
 }
 
@@ -588,7 +616,7 @@ __device__ void kfast_rows_inverse(const FastParams& fp, unsigned char* smem)
 template <int E, int T, int R, bool MIRROR>
 __device__ void kfast_rows_inverse_tma(const FastParams& fp, unsigned char* smem)
 {
-    static_assert(R == 8 || R == 16, "lines per CTA = rows per GT tile");
+    static_assert(R == 4 || R == 8 || R == 16, "lines per CTA = rows per GT tile");
     constexpr int N = E * T, M = E / T, NT = T * R, NWARP = NT / 32, KP = N / 2 + 1;
     constexpr int XS = T * R + (R < 16 ? R : 0);              // k1 stride of the exchange tile (conflict free)
     static_assert(E * XS >= 2 * KP * R, "the exchange tile covers the landing buffer");

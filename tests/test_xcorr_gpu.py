@@ -179,7 +179,7 @@ def test_full_size_ground_truth(fc):
 
 
 FAST_CASES = [
-    # (n, shape0, shape1, kwargs) -- every FFT grid here is a power of two in {256, 512, 1024, 2048}
+    # (n, shape0, shape1, kwargs) -- every FFT grid here is a power of two in {256, 512, 1024, 2048, 4096}
     (5, (128, 128), (128, 128), dict(subpixel=True)),                          # 256 x 256
     (3, (127, 127), (127, 127), dict(subpixel=True)),                          # 256 x 256, ragged rows
     (3, (110, 120), (147, 137), dict(subpixel=True)),                          # 256 x 256, different shapes
@@ -198,6 +198,10 @@ FAST_CASES = [
     (2, (256, 2048), (256, 2048), dict(subpixel=True, pad=False)),             # 256 x 2048, no pruning
     (2, (1020, 1017), (1020, 1017), dict(subpixel=True, conf_mode=1)),         # 2048 x 2048 ragged, STD
     (2, (2048, 512), (2048, 512), dict(subpixel=False, conf_mode=0, pad=False)),  # 2048 x 512, unpruned columns, NONE
+    (1, (2048, 2048), (2048, 2048), dict(subpixel=True)),                      # 4096 x 4096 (a line spans two warps)
+    (2, (2040, 128), (2040, 128), dict(subpixel=True)),                        # 4096 x 256 (ragged), column pieces
+    (2, (128, 2048), (128, 2048), dict(subpixel=True, conf_mode=1)),           # 256 x 4096, STD
+    (2, (4096, 256), (4096, 256), dict(subpixel=True, conf_mode=0, pad=False)),  # 4096 x 256 unpruned, NONE
 ]
 
 
