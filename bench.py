@@ -35,6 +35,7 @@ WORKLOADS = {
     'xcorr2048': dict(h=2048, w=2048, pad=True, batch=16),
     'stitch_fine': dict(h=74, w=67, pad=True, batch=16384),       # config 1/2 finest level, FFT 150x135
     'thumb150': dict(h=150, w=150, pad=True, batch=4096),         # config 3, FFT 300x300
+    'align280': dict(h=280, w=280, pad=True, batch=1024),         # default fine alignment (spacing 400, shrink 0.7), FFT 576x576
 }
 
 
@@ -218,6 +219,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--fast-flags', type=int, default=0, help='kernel experiment switches (fb_set_option fast_flags)')
+    ap.add_argument('--force', default=None, choices=['generic', 'staged', 'fused'], help='force an execution shape (comparison runs)')
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.batch:
@@ -280,14 +282,14 @@ def main():
     flags = 0x2 | (2 << 2) | (1 if pad else 0)
     info = L.plan_info(h, w, h, w, L.FB_F32, ny, nx, flags)
     fused = info['path'] == 'fused'
-    config['path'] = info['path']
+    config['path'] = info['path'] if not args.force else 'forced ' + args.force
 
     a, b, shifts = make_pairs(batch, h, w, seed=100 + rank, device=dev, max_shift=min(32, min(h, w) // 8))
     out = torch.empty((5, batch), dtype=torch.float64, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
 
     def step():
-        fc.xcorr_fft_device(a, b, subpixel=True, pad=pad, out=out)
+        fc.xcorr_fft_device(a, b, subpixel=True, pad=pad, out=out, force=args.force)
 
     def barrier():
         torch.cuda.synchronize()

@@ -100,6 +100,8 @@ __global__ void __launch_bounds__(256) fbk_channel_mean(const cx<T>* __restrict_
 }
 
 // ---- register-resident fast path (power-of-two grids, float32 compute) ----
+// fast-path line lengths: N = E * T (E points per lane, T lanes per line).  X(n, E, T)
+#define FB_FAST_SIZES(X) X(256, 16, 16) X(512, 32, 16) X(1024, 32, 32) X(2048, 64, 32) X(4096, 64, 64) X(576, 24, 24) X(288, 24, 12)
 constexpr int kNW1 = 8, kNW2 = 8;                    // warps per CTA of K1 / K2
 // K3: lines (= GT tile rows) per CTA for T lanes per line; CTA = T * R threads, 512 threads per SM
 template <int T> constexpr int kR3() { return T > 32 ? 4 : 8; }
@@ -257,11 +259,9 @@ static int set_attrs(int device)
     RS((fbk_fast_rows_inverse<E, T, kR3<T>()>));             \
     RS((fbk_fast_rows_inverse_tma<E, T, kR3<T>(), true>));   \
     RS((fbk_fast_rows_inverse_tma<E, T, kR3<T>(), false>))
-    RSF(16, 16);
-    RSF(32, 16);
-    RSF(32, 32);
-    RSF(64, 32);
-    RSF(64, 64);
+#define X(N_, E_, T_) RSF(E_, T_);
+    FB_FAST_SIZES(X)
+#undef X
     RS((fbk_fast_rows_inverse<32, 32, 4>));
     RS((fbk_fast_rows_inverse<32, 32, 4, 8>));
 #undef RSF
@@ -288,7 +288,13 @@ struct Problem {
     fb_xcorr_ext ext;
 };
 
-static bool fast_size(int n) { return n == 256 || n == 512 || n == 1024 || n == 2048 || n == 4096; }
+static bool fast_size(int n)
+{
+#define X(N_, E_, T_) if (n == N_) return true;
+    FB_FAST_SIZES(X)
+#undef X
+    return false;
+}
 
 static int make_problem(Problem& q, int n, int h0, int w0, int h1, int w1, int in_dtype, int fft_h, int fft_w, int flags,
                         const fb_xcorr_ext* ext = nullptr)
@@ -384,12 +390,16 @@ static void launch_fast_k2(const FastParams& fp, bool pruned, int grid, size_t s
 }
 static void fast_et(int n, int& E, int& T)
 {
-    if (n == 256) { E = 16; T = 16; } else if (n == 512) { E = 32; T = 16; } else if (n == 1024) { E = 32; T = 32; } else if (n == 2048) { E = 64; T = 32; } else { E = 64; T = 64; }
+    E = T = 0;
+#define X(N_, E_, T_) if (n == N_) { E = E_; T = T_; }
+    FB_FAST_SIZES(X)
+#undef X
 }
+static int fast_lines(int T, int nw) { return T > 32 ? nw / (T / 32) : nw * (32 / T); }   // WarpFFT::lines_per_cta
 static size_t fast_smem(int n, int nw)
 {
     int E, T; fast_et(n, E, T);
-    const int lines = T > 32 ? nw / (T / 32) : nw * (32 / T);
+    const int lines = fast_lines(T, nw);
     return ((size_t)lines * (n + E + 16) + (kLaneTwiddles ? 0 : n)) * sizeof(cx<float>);
 }
 
@@ -454,31 +464,29 @@ static int launch_fast(const Problem& q, StreamCtx& ctx, XcParams& p, int nb, cu
     fp.x = p;
     // K1
     {
-        const int TR = 2 * (TX > 32 ? kNW1 / (TX / 32) : (32 / TX) * kNW1);
+        const int TR = 2 * fast_lines(TX, kNW1);
         const int work = nb * (q.hp0 / TR + q.hp1 / TR);
         const int cap = g_num_sms * (EX > 32 ? 1 : 16 / kNW1);
         const int grid = work < cap ? work : cap;
         const bool pruned = q.w0 <= q.nx / 2 && q.w1 <= q.nx / 2;
         ProfScope ps(ctx, st, SLOT_ROWS_FWD);
-        if (q.nx == 256) launch_fast_k1<16, 16, TI>(fp, pruned, grid, fast_smem(256, kNW1), st);
-        else if (q.nx == 512) launch_fast_k1<32, 16, TI>(fp, pruned, grid, fast_smem(512, kNW1), st);
-        else if (q.nx == 1024) launch_fast_k1<32, 32, TI>(fp, pruned, grid, fast_smem(1024, kNW1), st);
-        else if (q.nx == 2048) launch_fast_k1<64, 32, TI>(fp, pruned, grid, fast_smem(2048, kNW1), st);
-        else launch_fast_k1<64, 64, TI>(fp, pruned, grid, fast_smem(4096, kNW1), st);
+        if (false) {}
+#define X(N_, E_, T_) else if (q.nx == N_) launch_fast_k1<E_, T_, TI>(fp, pruned, grid, fast_smem(N_, kNW1), st);
+        FB_FAST_SIZES(X)
+#undef X
     }
     // K2
     {
-        const int cpg = (TY > 32 ? kNW2 / (TY / 32) : (32 / TY) * kNW2) / 2;
+        const int cpg = fast_lines(TY, kNW2) / 2;
         const int work = nb * ((g.kp + cpg - 1) / cpg);
         const int cap = g_num_sms * (EY > 32 ? 1 : 16 / kNW2);
         const int grid = work < cap ? work : cap;
         const bool pruned = q.hp0 <= q.ny / 2 && q.hp1 <= q.ny / 2;
         ProfScope ps(ctx, st, SLOT_COLUMNS);
-        if (q.ny == 256) launch_fast_k2<16, 16>(fp, pruned, grid, fast_smem(256, kNW2), st);
-        else if (q.ny == 512) launch_fast_k2<32, 16>(fp, pruned, grid, fast_smem(512, kNW2), st);
-        else if (q.ny == 1024) launch_fast_k2<32, 32>(fp, pruned, grid, fast_smem(1024, kNW2), st);
-        else if (q.ny == 2048) launch_fast_k2<64, 32>(fp, pruned, grid, fast_smem(2048, kNW2), st);
-        else launch_fast_k2<64, 64>(fp, pruned, grid, fast_smem(4096, kNW2), st);
+        if (false) {}
+#define X(N_, E_, T_) else if (q.ny == N_) launch_fast_k2<E_, T_>(fp, pruned, grid, fast_smem(N_, kNW2), st);
+        FB_FAST_SIZES(X)
+#undef X
     }
     // K3: TX * R threads own R lines (R <= rblk rows of a GT tile)
     {
@@ -496,18 +504,11 @@ static int launch_fast(const Problem& q, StreamCtx& ctx, XcParams& p, int nb, cu
         const size_t sm3t = sm3 + 16;                                         // + mbarrier
 #define K3T(E_, T_) do { if (mir) fbk_fast_rows_inverse_tma<E_, T_, kR3<T_>(), true><<<grid, nt, sm3t, st>>>(fp); \
                          else fbk_fast_rows_inverse_tma<E_, T_, kR3<T_>(), false><<<grid, nt, sm3t, st>>>(fp); } while (0)
-        if (tma3 && q.nx == 256) K3T(16, 16);
-        else if (tma3 && q.nx == 512) K3T(32, 16);
-        else if (tma3 && q.nx == 1024) K3T(32, 32);
-        else if (tma3 && q.nx == 2048) K3T(64, 32);
-        else if (tma3) K3T(64, 64);
-        else if (q.nx == 256) fbk_fast_rows_inverse<16, 16, kR3<16>()><<<grid, nt, sm3, st>>>(fp);
-        else if (q.nx == 512) fbk_fast_rows_inverse<32, 16, kR3<16>()><<<grid, nt, sm3, st>>>(fp);
-        else if (q.nx == 2048) fbk_fast_rows_inverse<64, 32, kR3<32>()><<<grid, nt, sm3, st>>>(fp);
-        else if (q.nx == 4096) fbk_fast_rows_inverse<64, 64, kR3<64>()><<<grid, nt, sm3, st>>>(fp);
-        else if (R == 4 && fp.rblk == 8) fbk_fast_rows_inverse<32, 32, 4, 8><<<grid, nt, sm3, st>>>(fp);
-        else if (R == 4) fbk_fast_rows_inverse<32, 32, 4><<<grid, nt, sm3, st>>>(fp);
-        else fbk_fast_rows_inverse<32, 32, kR3<32>()><<<grid, nt, sm3, st>>>(fp);
+        if (R == 4 && q.nx == 1024 && fp.rblk == 8) fbk_fast_rows_inverse<32, 32, 4, 8><<<grid, nt, sm3, st>>>(fp);
+        else if (R == 4 && q.nx == 1024) fbk_fast_rows_inverse<32, 32, 4><<<grid, nt, sm3, st>>>(fp);
+#define X(N_, E_, T_) else if (q.nx == N_) { if (tma3) K3T(E_, T_); else fbk_fast_rows_inverse<E_, T_, kR3<T_>()><<<grid, nt, sm3, st>>>(fp); }
+        FB_FAST_SIZES(X)
+#undef X
 #undef K3T
     }
     {

@@ -57,7 +57,7 @@ template <int E, int T> struct SmemTw {
     // out(k1, value) stores the twiddled value of output k1
     template <typename F> __device__ __forceinline__ void apply_all(const cx<float>* v, F out) const
     {
-        constexpr int TB = 4, NB = E / 2 / TB;
+        constexpr int H = E / 2, TB = H % 4 == 0 ? 4 : (H % 3 == 0 ? 3 : (H % 5 == 0 ? 5 : 1)), NB = H / TB;
         float4 wq[2][TB];
 #pragma unroll
         for (int i = 0; i < TB; ++i) wq[0][i] = tw4[i * T];
@@ -71,7 +71,7 @@ template <int E, int T> struct SmemTw {
             for (int i = 0; i < TB; ++i) {
                 const int k1 = 2 * (b * TB + i);
                 const float4 w = wq[b & 1][i];
-                cx<float> a0 = v[brev<E>(k1)], a1 = v[brev<E>(k1 + 1)];
+                cx<float> a0 = v[gpos<E>(k1)], a1 = v[gpos<E>(k1 + 1)];
                 if (k1) a0 = cmul(a0, mk<float>(w.x, w.y));
                 a1 = cmul(a1, mk<float>(w.z, w.w));
                 out(k1, a0);
@@ -100,7 +100,7 @@ template <int E, int T> struct StageTw {
     {
         if constexpr (kLaneTwiddles) {
 #pragma unroll
-            for (int k1 = 0; k1 < E; ++k1) out(k1, lane.apply(v[brev<E>(k1)], k1));
+            for (int k1 = 0; k1 < E; ++k1) out(k1, lane.apply(v[gpos<E>(k1)], k1));
         } else {
             sm.apply_all(v, out);
         }
@@ -115,17 +115,26 @@ __device__ __forceinline__ void named_barrier(int id, int nthreads)
 }
 
 template <int E, int T> struct WarpFFT {
-    static_assert(T == 16 || T == 32 || T == 64, "lanes per line");
-    static_assert(E % T == 0 && E / T <= 2, "E/T stage-B transforms per lane");
+    static_assert(T <= 32 || T == 64, "lanes per line");
+    static_assert(E % T == 0 && E / T <= 4 && E % 2 == 0, "E/T stage-B transforms per lane");
     static constexpr int N = E * T;
     static constexpr int WPL = T > 32 ? T / 32 : 1;   // warps per line (T = 64: the line's lanes span two adjacent warps)
     static constexpr int LPW = T >= 32 ? 1 : 32 / T;  // lines per warp
     static constexpr int M = E / T;           // stage-B transforms per lane
+    // T not a divisor of 32 (24, 12, 10, ...): the lanes >= AL SHADOW the first lanes of the warp -- same line,
+    // same t, same loads and (duplicate, identical) stores -- so no code path diverges on them; only
+    // one-per-line actions (TMA issue) and sums must skip them
+    static constexpr int AL = T >= 32 ? 32 : LPW * T;
+    static __device__ __forceinline__ bool is_shadow(int lane) { return lane >= AL; }
     // lines a CTA of NW warps works on at a time
     static constexpr __host__ __device__ int lines_per_cta(int nw) { return WPL > 1 ? nw / WPL : nw * LPW; }
     // lane within the line / line within the CTA of this thread
-    static __device__ __forceinline__ int lane_in_line(int warp, int lane) { return WPL > 1 ? (warp % WPL) * 32 + lane : lane % T; }
-    static __device__ __forceinline__ int line_in_cta(int warp, int lane) { return WPL > 1 ? warp / WPL : warp * LPW + lane / T; }
+    static __device__ __forceinline__ int lane_in_line(int warp, int lane)
+    {
+        return WPL > 1 ? (warp % WPL) * 32 + lane : (lane >= AL ? lane - AL : lane) % T;
+    }
+    static __device__ __forceinline__ int line_in_warp(int lane) { return WPL > 1 ? 0 : (lane >= AL ? lane - AL : lane) / T; }
+    static __device__ __forceinline__ int line_in_cta(int warp, int lane) { return WPL > 1 ? warp / WPL : warp * LPW + line_in_warp(lane); }
     // all lanes of a line (bar: a named barrier id private to the line, used only when the line spans warps)
     static __device__ __forceinline__ void line_sync(int bar)
     {
@@ -139,7 +148,7 @@ template <int E, int T> struct WarpFFT {
     // k (natural index) of register j after run(): see out_index()
     static __device__ __forceinline__ int out_k(int t, int j) { return t + T * (j % M) + E * (j / M); }
     // register that holds output j (j-th in increasing k for this lane)
-    static constexpr __host__ __device__ int out_reg(int j) { return (j % M) * T + brev<T>(j / M); }
+    static constexpr __host__ __device__ int out_reg(int j) { return (j % M) * T + gpos<T>(j / M); }
 
     // v: E registers; in: v[n1] = x[n1 T + t]; out: X[out_k(t, j)] = v[out_reg(j)].
     // Forward transform only: inverse transforms are taken as conj(fft(conj(.))) with the
@@ -151,9 +160,7 @@ template <int E, int T> struct WarpFFT {
     {
         // first radix-2 level: skipped arithmetic when the upper half of the input is zero; the
         // remaining levels are one shared body
-        if (PRUNED && pruned_now) DifLevelPruned<float, E, false>::run(v); else PDifLevel<E>::run(v);
-        PRegFFT<E / 2>::run(v);
-        PRegFFT<E / 2>::run(v + E / 2);
+        LaneFFT<E>::template run_first<PRUNED>(v, pruned_now);
         tw.apply_all(v, [&](int k1, cx<float> a) { region[k1 * (T + 1) + t] = a; });
         line_sync(bar);
 #pragma unroll
@@ -163,7 +170,7 @@ template <int E, int T> struct WarpFFT {
         }
         line_sync(bar);
 #pragma unroll
-        for (int m = 0; m < M; ++m) PRegFFT<T>::run(v + m * T);
+        for (int m = 0; m < M; ++m) LaneFFT<T>::run(v + m * T);
     }
 };
 
@@ -317,11 +324,11 @@ __device__ void kfast_rows_forward(const FastParams& fp, unsigned char* smem)
         // separation + transposed store: thread -> (line l minor, k major); both rows of a line are
         // adjacent in FT, so one 16-byte store writes the pair (A[k], B[k])
         {
-            constexpr int KSTEP = NT / LPC;
+            constexpr int KSTEP = NT / LPC;                // (threads beyond KSTEP * LPC idle when LPC does not divide NT)
             const int l = tid % LPC;
             const cx<float>* reg = regions + l * RS;
             float4* dst = reinterpret_cast<float4*>(FT + row0 + 2 * l);
-            for (int k = tid / LPC; k < ((fp.flags & 1024) ? 0 : kp); k += KSTEP) {
+            for (int k = tid / LPC; k < ((fp.flags & 1024) || tid >= KSTEP * LPC ? 0 : kp); k += KSTEP) {
                 const cx<float> zk = reg[k], zm = reg[k ? N - k : 0];
                 float4 o;
                 o.x = 0.5f * (zk.x + zm.x); o.y = 0.5f * (zk.y - zm.y);      // row 2l   : (Z[k] + conj Z[N-k]) / 2
@@ -351,7 +358,8 @@ __device__ void kfast_columns(const FastParams& fp, unsigned char* smem)
     const XcParams& p = fp.x;
     cx<float>* regions = reinterpret_cast<cx<float>*>(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int t = W::lane_in_line(warp, lane), lw = WPL > 1 ? 0 : lane / T;
+    const int t = W::lane_in_line(warp, lane), lw = W::line_in_warp(lane);
+    const bool leader = t == 0 && !W::is_shadow(lane);     // one thread per line
     StageTw<E, T> tw;
     tw.init(fp.twy, regions + W::lines_per_cta(NW) * RS, t, tid, NT);
     // partners are ADJACENT warps (2 pw, 2 pw + 1): they sit on different SM sub-partitions, so the
@@ -375,7 +383,7 @@ __device__ void kfast_columns(const FastParams& fp, unsigned char* smem)
         const int col = grp * CPG + pw * LPW + lw;
         const bool live = col < kp;
         if (tma) {                                         // the previous column's TMA store has read `mine`
-            if (t == 0) tma_store_wait_read();
+            if (leader) tma_store_wait_read();
             W::line_sync(lbar);
         }
         if ((WPL > 1 ? t == 0 : lane == 0) && pw == 0 && !(fp.flags & 2)) {     // the CTA's next column group (contiguous in FT) -> L2
@@ -436,35 +444,32 @@ __device__ void kfast_columns(const FastParams& fp, unsigned char* smem)
                 }
                 named_barrier(pw + 1, PT);
                 if (!second_phase) break;
-            } else if (live && !(fp.flags & 64)) {
+            } else if (!(fp.flags & 64)) {
                 if (tma) {
                     // natural y order into the (free) transpose region, then one bulk tensor store scatters
-                    // the column into its ny / rblk tiles
+                    // the column into its ny / rblk tiles.  Every lane takes this path (columns past kp write
+                    // their region too, nothing is stored for them): no divergence around the line barrier.
 #pragma unroll
                     for (int j = 0; j < E; ++j) mine[W::out_k(t, j)] = v[W::out_reg(j)];
-                    // only the lanes of this line: with two lines per warp (T = 16) `live` can differ between them
                     fence_proxy_async_smem();
-                    if constexpr (WPL > 1) W::line_sync(lbar);
-                    else __syncwarp(T == 32 ? 0xffffffffu : (0xffffu << (16 * lw)));
-                    if (t == 0) {
+                    W::line_sync(lbar);
+                    if (leader && live) {
                         // the box of the tensor map holds at most 256 tiles: long columns leave in several pieces
                         tma_store_4d(&fp.gt_map, mine, 0, col, roleB ? 1 : 0, pair * fp.gt_tiles);
                         for (int i = 1; i < fp.gt_pieces; ++i)
                             tma_store_4d(&fp.gt_map, mine + i * 256 * fp.rblk, 0, col, roleB ? 1 : 0, pair * fp.gt_tiles + i * 256);
                     }
-                } else {
-                    // y = t + c, c a multiple of T >= rblk: the tile index advances by c / rblk
+                } else if (live) {
                     const int R = fp.rblk;
-                    cx<float>* dst = fp.GT + (size_t)pair * 2 * kp * N + gt_row_offset(t, kp, R) + ((size_t)(roleB ? kp : 0) + col) * R;
-                    const size_t cs = (size_t)2 * kp;
+                    cx<float>* dst = fp.GT + (size_t)pair * 2 * kp * N + ((size_t)(roleB ? kp : 0) + col) * R;
 #pragma unroll
-                    for (int j = 0; j < E; ++j) dst[(W::out_k(t, j) - t) * cs] = v[W::out_reg(j)];
+                    for (int j = 0; j < E; ++j) dst[gt_row_offset(W::out_k(t, j), kp, R)] = v[W::out_reg(j)];
                 }
             }
         }
     }
     if (tma) {                                             // shared memory must outlive the last store's read
-        if (t == 0) tma_store_wait_read();
+        if (leader) tma_store_wait_read();
         W::line_sync(lbar);
     }
 }
@@ -544,7 +549,7 @@ __device__ void kfast_rows_inverse(const FastParams& fp, unsigned char* smem)
                 }
                 v[n1] = z;
             }
-            PRegFFT<E>::run(v);
+            LaneFFT<E>::run(v);
             tw.apply_all(v, [&](int k1, cx<float> a) { X[k1 * XS + t * R + r] = a; });
         }
         __syncthreads();
@@ -559,7 +564,7 @@ __device__ void kfast_rows_inverse(const FastParams& fp, unsigned char* smem)
                 for (int n2 = 0; n2 < T; ++n2) u[m * T + n2] = X[k1 * XS + n2 * R + r];
             }
 #pragma unroll
-            for (int m = 0; m < M; ++m) PRegFFT<T>::run(u + m * T);
+            for (int m = 0; m < M; ++m) LaneFFT<T>::run(u + m * T);
             best = u[0].x; second = mirror ? fabsf(u[0].y) : -u[0].y;
 #pragma unroll
             for (int j = 1; j < E; ++j) {
@@ -697,7 +702,7 @@ __device__ void kfast_rows_inverse_tma(const FastParams& fp, unsigned char* smem
             }
         }
         __syncthreads();                                       // every input is in registers: X may be overwritten
-        PRegFFT<E>::run(v);
+        LaneFFT<E>::run(v);
         tw.apply_all(v, [&](int k1, cx<float> a) { X[k1 * XS + tq * R + r] = a; });
         __syncthreads();
         float best, second;
@@ -716,7 +721,7 @@ __device__ void kfast_rows_inverse_tma(const FastParams& fp, unsigned char* smem
                 if (nw_ < total) { issue(nw_); prefetch(nw_ + gridDim.x); }
             }
 #pragma unroll
-            for (int m = 0; m < M; ++m) PRegFFT<T>::run(u + m * T);
+            for (int m = 0; m < M; ++m) LaneFFT<T>::run(u + m * T);
             best = u[0].x; second = MIRROR ? fabsf(u[0].y) : -u[0].y;
 #pragma unroll
             for (int j = 1; j < E; ++j) {

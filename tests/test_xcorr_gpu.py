@@ -202,6 +202,14 @@ FAST_CASES = [
     (2, (2040, 128), (2040, 128), dict(subpixel=True)),                        # 4096 x 256 (ragged), column pieces
     (2, (128, 2048), (128, 2048), dict(subpixel=True, conf_mode=1)),           # 256 x 4096, STD
     (2, (4096, 256), (4096, 256), dict(subpixel=True, conf_mode=0, pad=False)),  # 4096 x 256 unpruned, NONE
+    # 5-smooth grids with a radix-3 factor: 576 = 24 x 24 and 288 = 24 x 12 points (lanes 24..31 shadow lanes 0..7)
+    (3, (280, 280), (280, 280), dict(subpixel=True)),                          # 576 x 576: default fine-alignment blocks
+    (3, (140, 140), (140, 140), dict(subpixel=True)),                          # 288 x 288
+    (2, (285, 281), (285, 281), dict(subpixel=True, conf_mode=1)),             # 576 x 576 ragged, STD
+    (2, (288, 576), (288, 576), dict(subpixel=True, pad=False)),               # 288 x 576 unpruned
+    (2, (280, 512), (280, 512), dict(subpixel=True, conf_mode=0)),             # 576 x 1024, NONE
+    (2, (512, 140), (512, 140), dict(subpixel=False)),                         # 1024 x 288
+    (3, (130, 130), (150, 150), dict(subpixel=True)),                          # 288 x 288, different shapes
 ]
 
 
@@ -225,7 +233,7 @@ def test_fast_path_against_oracle(fc, n, shape0, shape1, kw):
     np.testing.assert_allclose(got[1], gen[1], atol=2e-3)
 
 
-@pytest.mark.parametrize('size,n', [(128, 48), (256, 20)])
+@pytest.mark.parametrize('size,n', [(128, 48), (256, 20), (140, 60), (280, 16)])
 def test_fast_path_many_work_items_per_cta(fc, size, n):
     """More (pair, column group) / (pair, tile) work items than resident CTAs: the persistent loops of the
     fast-path kernels (TMA store / load recycling, odd last column group) run several iterations."""
