@@ -101,10 +101,10 @@ __global__ void __launch_bounds__(256) fbk_channel_mean(const cx<T>* __restrict_
 
 // ---- register-resident fast path (power-of-two grids, float32 compute) ----
 // fast-path line lengths: N = E * T (E points per lane, T lanes per line).  X(n, E, T)
-#define FB_FAST_SIZES(X) X(256, 16, 16) X(512, 32, 16) X(1024, 32, 32) X(2048, 64, 32) X(4096, 64, 64) X(576, 24, 24) X(288, 24, 12)
+#define FB_FAST_SIZES(X) X(256, 16, 16) X(512, 32, 16) X(1024, 32, 32) X(2048, 64, 32) X(4096, 64, 64) X(576, 24, 24) X(288, 24, 12) X(300, 30, 10)
 constexpr int kNW1 = 8, kNW2 = 8;                    // warps per CTA of K1 / K2
 // K3: lines (= GT tile rows) per CTA for T lanes per line; CTA = T * R threads, 512 threads per SM
-template <int T> constexpr int kR3() { return T > 32 ? 4 : 8; }
+template <int T> constexpr int kR3() { return T > 32 || T == 10 ? 4 : 8; }     // (300 = 4 * 75 rows: tiles of 4)
 // CTAs per SM the register budget allows: a lane holds E complex points (E = 64: 128 data registers, one CTA)
 template <int E> constexpr int kOcc(int full) { return E > 32 ? 1 : full; }
 template <int E, int T, typename TI, bool PRUNED>
@@ -120,14 +120,14 @@ __global__ void __launch_bounds__(32 * kNW2, kOcc<E>(16 / kNW2)) fbk_fast_column
     kfast_columns<E, T, kNW2, PRUNED>(fp, smem);
 }
 template <int E, int T, int R, int RB = R>
-__global__ void __launch_bounds__(T * R, kOcc<E>(512 / (T * R))) fbk_fast_rows_inverse(const __grid_constant__ FastParams fp)
+__global__ void __launch_bounds__(k3_threads(T, R), kOcc<E>(512 / k3_threads(T, R))) fbk_fast_rows_inverse(const __grid_constant__ FastParams fp)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     kfast_rows_inverse<E, T, R, RB>(fp, smem);
 }
 
 template <int E, int T, int R, bool MIRROR>
-__global__ void __launch_bounds__(T * R, kOcc<E>(512 / (T * R))) fbk_fast_rows_inverse_tma(const __grid_constant__ FastParams fp)
+__global__ void __launch_bounds__(k3_threads(T, R), kOcc<E>(512 / k3_threads(T, R))) fbk_fast_rows_inverse_tma(const __grid_constant__ FastParams fp)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     kfast_rows_inverse_tma<E, T, R, MIRROR>(fp, smem);
@@ -288,6 +288,7 @@ struct Problem {
     fb_xcorr_ext ext;
 };
 
+static int fast_rblk_of(int nx);
 static bool fast_size(int n)
 {
 #define X(N_, E_, T_) if (n == N_) return true;
@@ -337,6 +338,11 @@ static int make_problem(Problem& q, int n, int h0, int w0, int h1, int w1, int i
                             : ((size_t)(h0 + h1) * g.fpitch * q.nchan + (size_t)fft_h * 2 * g.fpitch * (q.nchan + (q.nchan > 1 ? 1 : 0))) * g.esize +
                                   (size_t)q.nrt * sizeof(Partial);
     q.fast = !q.fused && !q.f64 && fast_size(fft_h) && fast_size(fft_w) && !(flags & FB_FLAG_FORCE_GENERIC);
+    if (q.fast) {
+        // K3 owns whole GT tiles of rblk rows (rblk follows the x size); without the mirror term a line is two rows
+        const int rb = fast_rblk_of(fft_w);
+        if (fft_h % (g.mirror ? rb : 2 * rb)) q.fast = false;
+    }
     if (q.fast) {
         q.hp0 = (h0 + 31) & ~31; q.hp1 = (h1 + 31) & ~31;
         q.nrt = g.mirror ? fft_h : (fft_h + 1) / 2;
@@ -395,7 +401,9 @@ static void fast_et(int n, int& E, int& T)
     FB_FAST_SIZES(X)
 #undef X
 }
+static int fast_rblk(int T) { return T > 32 || T == 10 ? 4 : 8; }                         // == kR3<T>()
 static int fast_lines(int T, int nw) { return T > 32 ? nw / (T / 32) : nw * (32 / T); }   // WarpFFT::lines_per_cta
+static int fast_rblk_of(int nx) { int E, T; fast_et(nx, E, T); return fast_rblk(T); }
 static size_t fast_smem(int n, int nw)
 {
     int E, T; fast_et(n, E, T);
@@ -453,7 +461,7 @@ static int launch_fast(const Problem& q, StreamCtx& ctx, XcParams& p, int nb, cu
     fp.FT1 = reinterpret_cast<cx<float>*>(w + f0);
     fp.GT = reinterpret_cast<cx<float>*>(w + f0 + f1);
     p.part = reinterpret_cast<Partial*>(w + f0 + f1 + gg);
-    fp.rblk = TX == 64 ? kR3<64>() : (TX == 32 ? kR3<32>() : kR3<16>());          // rows per K3 tile
+    fp.rblk = fast_rblk(TX);                             // rows per K3 tile
     if (q.nx == 1024 && (g_opt_fast_flags & 32)) fp.rblk = 4;
     fp.flags = (int)(g_opt_fast_flags & ~(16 | 32));
     fp.use_tma = make_gt_map(&fp.gt_map, fp.GT, nb, q.ny, g.kp, fp.rblk) ? 1 : 0;
@@ -465,7 +473,7 @@ static int launch_fast(const Problem& q, StreamCtx& ctx, XcParams& p, int nb, cu
     // K1
     {
         const int TR = 2 * fast_lines(TX, kNW1);
-        const int work = nb * (q.hp0 / TR + q.hp1 / TR);
+        const int work = nb * ((q.hp0 + TR - 1) / TR + (q.hp1 + TR - 1) / TR);
         const int cap = g_num_sms * (EX > 32 ? 1 : 16 / kNW1);
         const int grid = work < cap ? work : cap;
         const bool pruned = q.w0 <= q.nx / 2 && q.w1 <= q.nx / 2;
@@ -481,7 +489,7 @@ static int launch_fast(const Problem& q, StreamCtx& ctx, XcParams& p, int nb, cu
         const int work = nb * ((g.kp + cpg - 1) / cpg);
         const int cap = g_num_sms * (EY > 32 ? 1 : 16 / kNW2);
         const int grid = work < cap ? work : cap;
-        const bool pruned = q.hp0 <= q.ny / 2 && q.hp1 <= q.ny / 2;
+        const bool pruned = q.h0 <= q.ny / 2 && q.h1 <= q.ny / 2;     // (rows >= h of the row spectra are zero)
         ProfScope ps(ctx, st, SLOT_COLUMNS);
         if (false) {}
 #define X(N_, E_, T_) else if (q.ny == N_) launch_fast_k2<E_, T_>(fp, pruned, grid, fast_smem(N_, kNW2), st);
@@ -492,7 +500,7 @@ static int launch_fast(const Problem& q, StreamCtx& ctx, XcParams& p, int nb, cu
     {
         int R = fp.rblk;
         if (q.nx == 1024 && (g_opt_fast_flags & 16)) R = 4;          // experiment: half-tile CTAs
-        const int nt = TX * R;
+        const int nt = k3_threads(TX, R);
         const int work = nb * (q.nrt / R);
         const int cap = g_num_sms * (EX > 32 ? 1 : 512 / nt);
         const int grid = work < cap ? work : cap;

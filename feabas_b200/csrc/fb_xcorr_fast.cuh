@@ -230,6 +230,9 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, un
                    "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
 }
 
+// threads of a K3 CTA: T * R rounded up to whole warps
+constexpr __host__ __device__ int k3_threads(int T, int R) { return (T * R + 31) / 32 * 32; }
+
 struct FastParams {
     XcParams x;
     const cx<float>* twx;   // [EX / 2][TX][2]: w_nx^(k1 t) with rows (k1, k1 + 1) paired per lane
@@ -269,7 +272,7 @@ __device__ void kfast_rows_forward(const FastParams& fp, unsigned char* smem)
     const int t = W::lane_in_line(warp, lane);             // lane within line
     StageTw<E, T> tw;
     tw.init(fp.twx, regions + LPC * RS, t, tid, NT);
-    const int tiles0 = fp.hp0 / TR, tiles1 = fp.hp1 / TR, tpp = tiles0 + tiles1;
+    const int tiles0 = (fp.hp0 + TR - 1) / TR, tiles1 = (fp.hp1 + TR - 1) / TR, tpp = tiles0 + tiles1;   // last tile may be partial
     const int kp = p.kp;
     for (int work = blockIdx.x; work < p.n * tpp; work += gridDim.x) {
         const int pair = work / tpp;
@@ -328,7 +331,7 @@ __device__ void kfast_rows_forward(const FastParams& fp, unsigned char* smem)
             const int l = tid % LPC;
             const cx<float>* reg = regions + l * RS;
             float4* dst = reinterpret_cast<float4*>(FT + row0 + 2 * l);
-            for (int k = tid / LPC; k < ((fp.flags & 1024) || tid >= KSTEP * LPC ? 0 : kp); k += KSTEP) {
+            for (int k = tid / LPC; k < ((fp.flags & 1024) || tid >= KSTEP * LPC || row0 + 2 * l >= hp ? 0 : kp); k += KSTEP) {
                 const cx<float> zk = reg[k], zm = reg[k ? N - k : 0];
                 float4 o;
                 o.x = 0.5f * (zk.x + zm.x); o.y = 0.5f * (zk.y - zm.y);      // row 2l   : (Z[k] + conj Z[N-k]) / 2
@@ -490,17 +493,19 @@ __device__ void kfast_rows_inverse(const FastParams& fp, unsigned char* smem)
 {
     static_assert(R == 4 || R == 8 || R == 16, "lines per CTA");
     static_assert(RB % R == 0, "a CTA owns a whole GT tile (RB rows) or an aligned part of one");
-    constexpr int N = E * T, M = E / T, NT = T * R, NWARP = NT / 32;   // RB == fp.rblk
+    constexpr int N = E * T, M = E / T, NT = k3_threads(T, R), NWARP = NT / 32;   // RB == fp.rblk
     constexpr int XS = T * R + (R < 16 ? R : 0);              // k1 stride of the exchange tile (conflict free)
     const XcParams& p = fp.x;
     cx<float>* X = reinterpret_cast<cx<float>*>(smem);
     cx<float>* twsm = X + E * XS;
     float* red = reinterpret_cast<float*>(twsm + StageTw<E, T>::smem_entries());   // [NWARP][R][2] floats + doubles after
     double* redd = reinterpret_cast<double*>(red + NWARP * R * 2);
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int warp = threadIdx.x >> 5;
+    const bool shadow = (int)threadIdx.x >= T * R;            // T * R not a multiple of 32: the surplus threads repeat the
+    const int tid = shadow ? threadIdx.x - T * R : threadIdx.x;   // first ones (identical loads / stores; sums skip them)
     const int r = tid % R, tq = tid / R;                      // stage A: t = tq; stage B: k1 = tq + T m
     StageTw<E, T> tw;
-    tw.init(fp.twx, twsm, tq, tid, NT);
+    tw.init(fp.twx, twsm, tq, threadIdx.x, NT);            // (the table copy strides over ALL threads, shadows included)
     const bool mirror = p.conf_mode == CONF_MIRROR, want_std = p.conf_mode == CONF_STD;
     const int ny = p.ny, kp = p.kp;
     const int lines_pp = mirror ? ny : (ny + 1) / 2;          // lines per pair
@@ -512,7 +517,7 @@ __device__ void kfast_rows_inverse(const FastParams& fp, unsigned char* smem)
         const int y0 = mirror ? gl : 2 * gl;                   //  R divides the power-of-two line count)
         const cx<float>* A = fp.GT + (size_t)pair * 2 * plane + gt_row_offset(y0, kp, RB);
         const cx<float>* B = mirror ? A + (size_t)kp * RB : A + 1;
-        if (tid == 0 && !(fp.flags & 4)) {                     // the GT tile of the CTA's next work item is one
+        if (threadIdx.x == 0 && !(fp.flags & 4)) {             // the GT tile of the CTA's next work item is one
             const int nw_ = work + gridDim.x;                  // contiguous chunk -> L2 (once per GT tile)
             const int rows = mirror ? R : 2 * R;               // surface rows per work item
             if (nw_ < p.n * tiles && (nw_ * rows) % RB == 0) {
@@ -579,6 +584,7 @@ __device__ void kfast_rows_inverse(const FastParams& fp, unsigned char* smem)
                 }
             }
         }
+        if (shadow) { sum = 0.0; sumsq = 0.0; }
         // lanes with equal r inside the warp, then the warps through shared memory
 #pragma unroll
         for (int off = R; off < 32; off <<= 1) {
@@ -589,12 +595,12 @@ __device__ void kfast_rows_inverse(const FastParams& fp, unsigned char* smem)
                 sumsq += __shfl_xor_sync(0xffffffffu, sumsq, off);
             }
         }
-        if ((tid & 31) < R) {
+        if ((threadIdx.x & 31) < R) {
             red[(warp * R + r) * 2] = best; red[(warp * R + r) * 2 + 1] = second;
             if (want_std) { redd[(warp * R + r) * 2] = sum; redd[(warp * R + r) * 2 + 1] = sumsq; }
         }
         __syncthreads();
-        if (tid < R) {
+        if (threadIdx.x < R) {
             for (int w = 1; w < NWARP; ++w) {
                 best = fmaxf(best, red[(w * R + r) * 2]); second = fmaxf(second, red[(w * R + r) * 2 + 1]);
                 if (want_std) { sum += redd[(w * R + r) * 2]; sumsq += redd[(w * R + r) * 2 + 1]; }
@@ -622,7 +628,7 @@ template <int E, int T, int R, bool MIRROR>
 __device__ void kfast_rows_inverse_tma(const FastParams& fp, unsigned char* smem)
 {
     static_assert(R == 4 || R == 8 || R == 16, "lines per CTA = rows per GT tile");
-    constexpr int N = E * T, M = E / T, NT = T * R, NWARP = NT / 32, KP = N / 2 + 1;
+    constexpr int N = E * T, M = E / T, NT = k3_threads(T, R), NWARP = NT / 32, KP = N / 2 + 1;
     constexpr int XS = T * R + (R < 16 ? R : 0);              // k1 stride of the exchange tile (conflict free)
     static_assert(E * XS >= 2 * KP * R, "the exchange tile covers the landing buffer");
     constexpr unsigned TILE_BYTES = 2u * KP * R * 8u;
@@ -632,11 +638,13 @@ __device__ void kfast_rows_inverse_tma(const FastParams& fp, unsigned char* smem
     float* red = reinterpret_cast<float*>(twsm + StageTw<E, T>::smem_entries());   // [NWARP][R][2] floats, doubles, mbarrier
     double* redd = reinterpret_cast<double*>(red + NWARP * R * 2);
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(redd + NWARP * R * 2);
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int warp = threadIdx.x >> 5;
+    const bool shadow = (int)threadIdx.x >= T * R;            // T * R not a multiple of 32: the surplus threads repeat the
+    const int tid = shadow ? threadIdx.x - T * R : threadIdx.x;   // first ones (identical loads / stores; sums skip them)
     const int r = tid % R, tq = tid / R;                      // stage A: t = tq; stage B: k1 = tq + T m
-    if (tid == 0) mbar_init(bar, 1);
+    if (threadIdx.x == 0) mbar_init(bar, 1);
     StageTw<E, T> tw;
-    tw.init(fp.twx, twsm, tq, tid, NT);
+    tw.init(fp.twx, twsm, tq, threadIdx.x, NT);            // (the table copy strides over ALL threads, shadows included)
     fence_proxy_async_smem();
     __syncthreads();
     const bool want_std = !MIRROR && p.conf_mode == CONF_STD;
@@ -669,7 +677,7 @@ __device__ void kfast_rows_inverse_tma(const FastParams& fp, unsigned char* smem
             prefetch_l2_bulk(base + (size_t)(2 * nt + 1) * 2 * KP * R, TILE_BYTES / 2);
         }
     };
-    if (tid == 0 && (int)blockIdx.x < total) { issue(blockIdx.x); prefetch(blockIdx.x + gridDim.x); }
+    if (threadIdx.x == 0 && (int)blockIdx.x < total) { issue(blockIdx.x); prefetch(blockIdx.x + gridDim.x); }
     unsigned parity = 0;
     // this thread's inputs inside the landing buffer
     const int offA = MIRROR ? r : ((2 * r) / R) * KP * R + (2 * r) % R;
@@ -716,7 +724,7 @@ __device__ void kfast_rows_inverse_tma(const FastParams& fp, unsigned char* smem
                 for (int n2 = 0; n2 < T; ++n2) u[m * T + n2] = X[k1 * XS + n2 * R + r];
             }
             __syncthreads();                                   // X has been read: the next tile may land
-            if (tid == 0) {
+            if (threadIdx.x == 0) {
                 const int nw_ = work + gridDim.x;
                 if (nw_ < total) { issue(nw_); prefetch(nw_ + gridDim.x); }
             }
@@ -736,6 +744,7 @@ __device__ void kfast_rows_inverse_tma(const FastParams& fp, unsigned char* smem
                 }
             }
         }
+        if (shadow) { sum = 0.0; sumsq = 0.0; }
         // lanes with equal r inside the warp, then the warps through shared memory
 #pragma unroll
         for (int off = R; off < 32; off <<= 1) {
@@ -746,12 +755,12 @@ __device__ void kfast_rows_inverse_tma(const FastParams& fp, unsigned char* smem
                 sumsq += __shfl_xor_sync(0xffffffffu, sumsq, off);
             }
         }
-        if ((tid & 31) < R) {
+        if ((threadIdx.x & 31) < R) {
             red[(warp * R + r) * 2] = best; red[(warp * R + r) * 2 + 1] = second;
             if (want_std) { redd[(warp * R + r) * 2] = sum; redd[(warp * R + r) * 2 + 1] = sumsq; }
         }
         __syncthreads();
-        if (tid < R) {
+        if (threadIdx.x < R) {
             for (int w = 1; w < NWARP; ++w) {
                 best = fmaxf(best, red[(w * R + r) * 2]); second = fmaxf(second, red[(w * R + r) * 2 + 1]);
                 if (want_std) { sum += redd[(w * R + r) * 2]; sumsq += redd[(w * R + r) * 2 + 1]; }

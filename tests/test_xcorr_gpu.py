@@ -210,6 +210,10 @@ FAST_CASES = [
     (2, (280, 512), (280, 512), dict(subpixel=True, conf_mode=0)),             # 576 x 1024, NONE
     (2, (512, 140), (512, 140), dict(subpixel=False)),                         # 1024 x 288
     (3, (130, 130), (150, 150), dict(subpixel=True)),                          # 288 x 288, different shapes
+    # 300 = 30 x 10 points (radix 5; three lines per warp, K3 tiles of 4 rows with shadow threads)
+    (4, (150, 150), (150, 150), dict(subpixel=True)),                          # 300 x 300: thumbnail blocks
+    (3, (300, 300), (300, 300), dict(subpixel=True, pad=False)),               # 300 x 300 unpruned
+    (2, (141, 150), (141, 150), dict(subpixel=False)),                         # 288 x 300 (ragged rows)
 ]
 
 
@@ -217,7 +221,8 @@ FAST_CASES = [
 def test_fast_path_against_oracle(fc, n, shape0, shape1, kw):
     from feabas_b200.cuda import _lib
     ny, nx = fc.fft_shape(shape0, shape1, kw.get('pad', True))
-    info = _lib.plan_info(*shape0, *shape1, _lib.FB_F32, ny, nx, 0)
+    from feabas_b200.cuda.xcorr import _flags
+    info = _lib.plan_info(*shape0, *shape1, _lib.FB_F32, ny, nx, _flags(kw.get('conf_mode', 2), kw.get('subpixel', False), kw.get('pad', True)))
     assert info['path'] == 'staged-fast', (ny, nx, info)
     if shape0 == shape1:
         a, b, _ = synth.block_pairs(n, shape0, seed=shape0[0] + shape0[1], max_shift=min(shape0) // 8)
@@ -233,7 +238,7 @@ def test_fast_path_against_oracle(fc, n, shape0, shape1, kw):
     np.testing.assert_allclose(got[1], gen[1], atol=2e-3)
 
 
-@pytest.mark.parametrize('size,n', [(128, 48), (256, 20), (140, 60), (280, 16)])
+@pytest.mark.parametrize('size,n', [(128, 48), (256, 20), (140, 60), (280, 16), (150, 80)])
 def test_fast_path_many_work_items_per_cta(fc, size, n):
     """More (pair, column group) / (pair, tile) work items than resident CTAs: the persistent loops of the
     fast-path kernels (TMA store / load recycling, odd last column group) run several iterations."""
