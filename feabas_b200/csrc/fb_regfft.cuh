@@ -291,15 +291,93 @@ template <> struct PRegFFT<1> {
     static __device__ __forceinline__ void run(cx<float>*) {}
 };
 
+// ---------------------------------------------------------------------------------------------
+// Decimation-in-TIME variant of the packed radix-2 transform: same interface (natural order in,
+// X[k] in v[brev<N>(k)]), but the twiddle multiplies the odd branch BEFORE the butterfly, so a
+// general butterfly is x = e + w o (four FFMA with immediate constants), y = 2 e - x (two FFMA):
+// 6 FP32 lane operations instead of the 8 of the DIF form (2 FADD2 + 2 FMUL + 2 FFMA); the
+// sqrt(1/2) butterflies take 6 instead of 8.  388 instead of 456 lane operations per radix-32.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ cx<float> pfma(float s, cx<float> a, cx<float> b)      // s * a + b, packed
+{
+    const float2 r = __ffma2_rn(make_float2(s, s), make_float2(a.x, a.y), make_float2(b.x, b.y));
+    return mk<float>(r.x, r.y);
+}
+
+// e, o -> e + w o, e - w o with w = exp(-2 pi i J / N)
+template <int N, int J> __device__ __forceinline__ void dit_bfly(cx<float>& e, cx<float>& o)
+{
+    constexpr int j64 = (J * (64 / N)) & 63;
+    const cx<float> a = e, b = o;
+    if constexpr (j64 == 0) {
+        e = padd(a, b); o = psub(a, b);
+    } else if constexpr (j64 == 16) {           // w = -i: w b = (b.y, -b.x)
+        e = mk<float>(a.x + b.y, a.y - b.x); o = mk<float>(a.x - b.y, a.y + b.x);
+    } else if constexpr (j64 == 8) {            // w = h (1 - i): w b = h (b.x + b.y, b.y - b.x)
+        constexpr float h = 0.70710678118654752440f;
+        const cx<float> sd = mk<float>(b.x + b.y, b.y - b.x);
+        e = pfma(h, sd, a); o = pfma(-h, sd, a);
+    } else if constexpr (j64 == 24) {           // w = -h (1 + i): w b = h (b.y - b.x, -(b.x + b.y))
+        constexpr float h = 0.70710678118654752440f;
+        const cx<float> ds = mk<float>(b.y - b.x, -b.x - b.y);
+        e = pfma(h, ds, a); o = pfma(-h, ds, a);
+    } else {
+        constexpr float c = (float)cos64(j64);
+        constexpr float s = (float)sin64(j64);
+        // w b = (c b.x + s b.y, c b.y - s b.x)
+        const float xr = fmaf(c, b.x, fmaf(s, b.y, a.x));
+        const float xi = fmaf(c, b.y, fmaf(-s, b.x, a.y));
+        e = mk<float>(xr, xi);
+        o = mk<float>(fmaf(2.0f, a.x, -xr), fmaf(2.0f, a.y, -xi));
+    }
+}
+
+template <int N, int S, int K = 0> struct PDitCombine {
+    static __device__ __forceinline__ void run(cx<float>* v)
+    {
+        constexpr int pe = 2 * S * brev<N / 2>(K);
+        dit_bfly<N, K>(v[pe], v[pe + S]);
+        if constexpr (K + 1 < N / 2) PDitCombine<N, S, K + 1>::run(v);
+    }
+};
+
+// transforms v[0], v[S], ..., v[(N - 1) S] in place; X[k] ends at v[S * brev<N>(k)].
+// PR: the upper half of the (top-level) input is zero -- the size-2 leaves pair element i with i + N_top / 2,
+// so they degenerate to copies
+template <int N, int S = 1, bool PR = false> struct PDitFFT {
+    static __device__ __forceinline__ void run(cx<float>* v)
+    {
+        if constexpr (N == 2 && PR) {
+            v[S] = v[0];
+        } else {
+            PDitFFT<N / 2, 2 * S, PR>::run(v);
+            PDitFFT<N / 2, 2 * S, PR>::run(v + S);
+            PDitCombine<N, S>::run(v);
+        }
+    }
+};
+template <int S, bool PR> struct PDitFFT<1, S, PR> {
+    static __device__ __forceinline__ void run(cx<float>*) {}
+};
+
+#ifndef FB_DIT
+#define FB_DIT 1
+#endif
+constexpr bool kUseDit = FB_DIT != 0;
+
 // front end of the warp FFTs: packed radix-2 code for powers of two, the mixed-radix code otherwise
 template <int N> struct LaneFFT {
     static __device__ __forceinline__ void run(cx<float>* v)
     {
-        if constexpr (is_pow2(N)) PRegFFT<N>::run(v); else GRegFFT<N>::run(v);
+        if constexpr (is_pow2(N) && kUseDit) PDitFFT<N>::run(v);
+        else if constexpr (is_pow2(N)) PRegFFT<N>::run(v);
+        else GRegFFT<N>::run(v);
     }
     template <bool PRUNED> static __device__ __forceinline__ void run_first(cx<float>* v, bool pruned_now)
     {
-        if constexpr (is_pow2(N)) {
+        if constexpr (is_pow2(N) && kUseDit) {
+            if (PRUNED && pruned_now) PDitFFT<N, 1, true>::run(v); else PDitFFT<N>::run(v);
+        } else if constexpr (is_pow2(N)) {
             if (PRUNED && pruned_now) DifLevelPruned<float, N, false>::run(v); else PDifLevel<N>::run(v);
             PRegFFT<N / 2>::run(v);
             PRegFFT<N / 2>::run(v + N / 2);

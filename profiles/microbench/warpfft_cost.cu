@@ -4,6 +4,8 @@
 //   mode 1: + stage twiddles (shared-memory table)
 //   mode 2: + transpose through shared memory (= WarpFFT::run)
 //   mode 3: mode 2 with scalar (non-packed) butterflies
+//   mode 4: 2 x radix-32 butterflies, decimation in time with FMA-fused twiddles (PDitFFT)
+//   mode 5: mode 0 with the decimation-in-frequency packed butterflies (PRegFFT), for comparison when FB_DIT=1
 // nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I../../feabas_b200/csrc warpfft_cost.cu -o warpfft_cost
 #include <cstdio>
 #include <cuda_runtime.h>
@@ -36,15 +38,21 @@ __global__ void __launch_bounds__(32 * NW, 2) k(const cx<float>* table, cx<float
             for (int n2 = 0; n2 < T; ++n2) v[n2] = region[t * (T + 1) + n2];
             __syncwarp();
             RegFFT<float, T, false>::run(v);
-        } else {
+        } else if (MODE == 4) {
+            PDitFFT<E>::run(v);
+            PDitFFT<E>::run(v);
+        } else if (MODE == 5) {
             PRegFFT<E>::run(v);
+            PRegFFT<E>::run(v);
+        } else {
+            LaneFFT<E>::run(v);
             if (MODE == 1) {
                 cx<float> u[E];
                 tw.apply_all(v, [&](int k1, cx<float> a) { u[k1] = a; });
 #pragma unroll
                 for (int j = 0; j < E; ++j) v[j] = u[j];
             }
-            PRegFFT<E>::run(v);
+            LaneFFT<E>::run(v);
         }
 #pragma unroll
         for (int j = 0; j < E; ++j) v[j] = mk<float>(v[j].x * 0.03125f, v[j].y * 0.03125f);   // keep the values finite
@@ -80,9 +88,11 @@ int main()
     cx<float> h[1024];
     for (int i = 0; i < 1024; ++i) { h[i].x = 0.9f; h[i].y = 0.1f; }
     cudaMemcpy(table, h, sizeof(h), cudaMemcpyHostToDevice);
-    run<0>("2 x radix-32 butterflies (packed)", table, out);
+    run<0>("2 x radix-32 butterflies (LaneFFT default)", table, out);
     run<1>("+ stage twiddles (smem table)", table, out);
     run<2>("+ transpose via smem = WarpFFT::run", table, out);
     run<3>("WarpFFT with scalar butterflies", table, out);
+    run<4>("2 x radix-32 DIT butterflies (FMA twiddles)", table, out);
+    run<5>("2 x radix-32 DIF butterflies (packed)", table, out);
     return 0;
 }
