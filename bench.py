@@ -276,6 +276,9 @@ def main():
     import feabas_b200.cuda as fc
     L = fc._lib
     L.set_option('ws_bytes', int(args.ws_gib * (1 << 30)))
+    if os.environ.get('FB_MAX_RADIX'):
+        L.set_option('max_radix', int(os.environ['FB_MAX_RADIX']))
+        config['max_radix'] = int(os.environ['FB_MAX_RADIX'])
     if args.fast_flags:
         L.set_option('fast_flags', args.fast_flags)
         config['fast_flags'] = args.fast_flags

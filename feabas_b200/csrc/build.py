@@ -15,7 +15,7 @@ OBJ_DIR = os.path.join(HERE, 'build')
 HEADER = os.path.join('..', '..', 'include', 'feabas_cuda.h')
 # translation unit -> headers it includes
 UNITS = {
-    'fb_xcorr.cu': ['fb_xcorr.cuh', 'fb_xcorr_fast.cuh', 'fb_regfft.cuh', 'fb_fft.cuh', 'fb_host_plan.h', 'fb_common.h', HEADER],
+    'fb_xcorr.cu': ['fb_xcorr.cuh', 'fb_xcorr_fast.cuh', 'fb_regfft.cuh', 'fb_fft.cuh', 'fb_gfft.cuh', 'fb_host_plan.h', 'fb_common.h', HEADER],
     'fb_image.cu': ['fb_common.h', HEADER],
 }
 SOURCES = list(UNITS)

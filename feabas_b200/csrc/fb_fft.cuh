@@ -1,4 +1,4 @@
-// fb_fft.cuh -- in-place mixed-radix (2,3,4,5,8) FFT passes over shared-memory tiles.
+// fb_fft.cuh -- in-place mixed-radix (2,3,4,5,6,8,9,10,12,15,16) FFT passes over shared-memory tiles.
 //
 // The tile holds `nl` independent lines interleaved line-minor:
 //     element e of line l lives at  s[e * pitch + l]
@@ -128,6 +128,10 @@ template <typename T, bool INV> struct Bfly<T, 8, INV> {
     }
 };
 
+}  // namespace fb
+#include "fb_gfft.cuh"     // composite radices 6, 9, 10, 12, 15, 16 (mixed-radix register FFT)
+namespace fb {
+
 // ----------------------------------------------------------------------------
 // one pass over a tile.  L = current sub-transform length (N for the first
 // forward pass), m = L / R.  Thread i handles butterfly (line = i % nl,
@@ -169,8 +173,9 @@ FB_DEV void fft_pass(cx<T>* s, int pitch, int nl, int N, int L, const cx<T>* tw,
     }
 }
 
+// radices 2, 3, 4, 5, 8 only, inlined: the staged kernels (two 512-thread CTAs per SM need <= 64 registers)
 template <typename T, bool INV>
-FB_DEV void fft_pass_any(int R, cx<T>* s, int pitch, int nl, int N, int L, const cx<T>* tw, int tid, int nthr)
+FB_DEV void fft_pass_basic(int R, cx<T>* s, int pitch, int nl, int N, int L, const cx<T>* tw, int tid, int nthr)
 {
     switch (R) {
         case 2: fft_pass<T, 2, INV>(s, pitch, nl, N, L, tw, tid, nthr); break;
@@ -178,6 +183,35 @@ FB_DEV void fft_pass_any(int R, cx<T>* s, int pitch, int nl, int N, int L, const
         case 4: fft_pass<T, 4, INV>(s, pitch, nl, N, L, tw, tid, nthr); break;
         case 5: fft_pass<T, 5, INV>(s, pitch, nl, N, L, tw, tid, nthr); break;
         default: fft_pass<T, 8, INV>(s, pitch, nl, N, L, tw, tid, nthr); break;
+    }
+}
+
+// All radices (the fused kernel: one CTA per SM, registers are not the limit).
+// One out-of-line copy per (type, direction): the kernels call it from several places and the composite
+// radices unroll to a few hundred instructions each.
+#if defined(__CUDACC__)
+#define FB_NOINLINE __device__ __noinline__
+#else
+#define FB_NOINLINE inline
+#endif
+template <typename T, bool INV>
+FB_NOINLINE void fft_pass_any(int R, cx<T>* s, int pitch, int nl, int N, int L, const cx<T>* tw, int tid, int nthr)
+{
+#if defined(__CUDA_ARCH__)
+    __builtin_assume(__isShared(s));        // out of line: keep LDS / STS instead of generic loads and stores
+#endif
+    switch (R) {
+        case 2: fft_pass<T, 2, INV>(s, pitch, nl, N, L, tw, tid, nthr); break;
+        case 3: fft_pass<T, 3, INV>(s, pitch, nl, N, L, tw, tid, nthr); break;
+        case 4: fft_pass<T, 4, INV>(s, pitch, nl, N, L, tw, tid, nthr); break;
+        case 5: fft_pass<T, 5, INV>(s, pitch, nl, N, L, tw, tid, nthr); break;
+        case 6: fft_pass<T, 6, INV>(s, pitch, nl, N, L, tw, tid, nthr); break;
+        case 8: fft_pass<T, 8, INV>(s, pitch, nl, N, L, tw, tid, nthr); break;
+        case 9: fft_pass<T, 9, INV>(s, pitch, nl, N, L, tw, tid, nthr); break;
+        case 10: fft_pass<T, 10, INV>(s, pitch, nl, N, L, tw, tid, nthr); break;
+        case 12: fft_pass<T, 12, INV>(s, pitch, nl, N, L, tw, tid, nthr); break;
+        case 15: fft_pass<T, 15, INV>(s, pitch, nl, N, L, tw, tid, nthr); break;
+        default: fft_pass<T, 16, INV>(s, pitch, nl, N, L, tw, tid, nthr); break;
     }
 }
 

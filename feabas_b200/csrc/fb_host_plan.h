@@ -18,8 +18,8 @@ inline bool is_5smooth(int n)
     return n == 1;
 }
 
-// DIF radix sequence: 8s, then 4/2 for the rest of the power of two, then 5s and 3s.
-inline std::vector<int> radix_sequence(int n)
+// Basic DIF radix sequence (staged kernels): 8s, then 4/2 for the rest of the power of two, then 5s and 3s.
+inline std::vector<int> radix_sequence_basic(int n)
 {
     std::vector<int> r;
     int a = 0;
@@ -31,6 +31,36 @@ inline std::vector<int> radix_sequence(int n)
     while (n % 5 == 0) { r.push_back(5); n /= 5; }
     while (n % 3 == 0) { r.push_back(3); n /= 3; }
     return r;   // n == 1 expected; caller checks is_5smooth first
+}
+
+// Wide DIF radix sequence (fused kernel) over the pass radices {2,3,4,5,6,8,9,10,12,15,16}: the fewest passes, and among
+// those the most balanced factorisation (smallest largest radix, then smallest sum), largest radix first.
+inline void radix_search(int n, int max_r, std::vector<int>& cur, std::vector<int>& best)
+{
+    static const int kR[] = {16, 15, 12, 10, 9, 8, 6, 5, 4, 3, 2};
+    if (n == 1) {
+        auto key = [](const std::vector<int>& v) {
+            long long mx = 0, sum = 0;
+            for (int r : v) { mx = r > mx ? r : mx; sum += r; }
+            return ((long long)v.size() << 40) | (mx << 20) | sum;
+        };
+        if (best.empty() || key(cur) < key(best)) best = cur;
+        return;
+    }
+    if (!best.empty() && cur.size() + 1 > best.size()) return;
+    for (int r : kR) {
+        if (r > max_r || n % r) continue;
+        cur.push_back(r);
+        radix_search(n / r, r, cur, best);
+        cur.pop_back();
+    }
+}
+inline std::vector<int> radix_sequence(int n, int max_radix = 16)
+{
+    std::vector<int> cur, best;
+    if (n == 1) return best;
+    radix_search(n, max_radix, cur, best);
+    return best;   // empty if n is not 5-smooth; caller checks is_5smooth first
 }
 
 // pos[k]: where natural frequency k sits after the DIF passes.

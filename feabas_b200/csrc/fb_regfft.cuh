@@ -95,129 +95,7 @@ template <typename T, bool INV> struct RegFFT<T, 1, INV> {
     static FB_HD void run(cx<T>*) {}
 };
 
-// ---------------------------------------------------------------------------------------------
-// Mixed-radix (2, 3, 5) register FFT for 5-smooth N that are not powers of two (24, 12, 30, 10, ...):
-// decimation in frequency, one radix-R level (R = 2 while N is even, then 3, then 5) followed by
-// R transforms of length N / R on the contiguous sub-blocks.  X[k] ends up in v[gpos<N>(k)];
-// for powers of two gpos == brev.  Twiddles are compile-time constants.
-// ---------------------------------------------------------------------------------------------
-FB_HD constexpr int first_radix(int n) { return n % 2 == 0 ? 2 : (n % 3 == 0 ? 3 : (n % 5 == 0 ? 5 : n)); }
-
-template <int N> FB_HD constexpr int gpos(int k)
-{
-    if constexpr (N == 1) {
-        return 0;
-    } else {
-        constexpr int R = first_radix(N);
-        return (k % R) * (N / R) + gpos<N / R>(k / R);
-    }
-}
-
-// sin / cos of 2 pi m / n at compile time: octant reduction (exact at multiples of pi / 4), Taylor series inside
-FB_HD constexpr double series_sin(double x)
-{
-    double term = x, sum = x;
-    for (int i = 1; i < 12; ++i) { term *= -x * x / ((2 * i) * (2 * i + 1)); sum += term; }
-    return sum;
-}
-FB_HD constexpr double series_cos(double x)
-{
-    double term = 1.0, sum = 1.0;
-    for (int i = 1; i < 12; ++i) { term *= -x * x / ((2 * i - 1) * (2 * i)); sum += term; }
-    return sum;
-}
-// cos(2 pi m / n), 0 <= m < n
-FB_HD constexpr double cos_frac(int m, int n)
-{
-    constexpr double kPi = 3.14159265358979323846264338327950288;
-    m %= n;
-    if (m < 0) m += n;
-    if (2 * m > n) m = n - m;                     // cos is even around pi
-    // now 0 <= m / n <= 1/2
-    if (4 * m > n) return -cos_frac(n - 2 * m, 2 * n);      // cos(pi - y) = -cos(y):  2 pi m / n = pi - 2 pi (n - 2m) / (2n)
-    // 0 <= m / n <= 1/4
-    if (m == 0) return 1.0;
-    if (4 * m == n) return 0.0;
-    if (8 * m == n) return 0.70710678118654752440;
-    if (8 * m > n) return series_sin(kPi * (n - 4 * m) / (2.0 * n));       // cos(x) = sin(pi/2 - x), pi/2 - x = 2 pi (n - 4m) / (4n)
-    return series_cos(2.0 * kPi * m / n);
-}
-FB_HD constexpr double sin_frac(int m, int n) { return cos_frac(4 * m - n, 4 * n); }   // sin(x) = cos(x - pi/2)
-
-// v * exp(-2 pi i M / N)  (forward twiddle), trivial rotations special-cased
-template <int N, int M> FB_HD cx<float> gtwiddle(cx<float> v)
-{
-    constexpr int m = ((M % N) + N) % N;
-    if constexpr (m == 0) {
-        return v;
-    } else if constexpr (4 * m == N) {
-        return mk<float>(v.y, -v.x);
-    } else if constexpr (2 * m == N) {
-        return mk<float>(-v.x, -v.y);
-    } else if constexpr (4 * m == 3 * N) {
-        return mk<float>(-v.y, v.x);
-    } else {
-        constexpr float c = (float)cos_frac(m, N);
-        constexpr float s = (float)sin_frac(m, N);
-        return mk<float>(v.x * c + v.y * s, v.y * c - v.x * s);
-    }
-}
-
-template <int N, int R, int J, int S = 1> struct GTwLevel {      // y[S] *= w_N^(J S), S = 1..R-1
-    static FB_HD void run(cx<float>* y)
-    {
-        y[S] = gtwiddle<N, J * S>(y[S]);
-        if constexpr (S + 1 < R) GTwLevel<N, R, J, S + 1>::run(y);
-    }
-};
-
-template <int N, int R, bool PRUNED, int J = 0> struct GDifLevel {
-    static FB_HD void run(cx<float>* v)
-    {
-        constexpr int Q = N / R;
-        cx<float> y[R];
-#pragma unroll
-        for (int q = 0; q < R; ++q) y[q] = v[J + q * Q];
-        if constexpr (PRUNED && R == 2) {
-            y[1] = y[0];                             // upper half of the input is zero
-        } else {
-            Bfly<float, R, false>::run(y);
-        }
-        GTwLevel<N, R, J>::run(y);
-#pragma unroll
-        for (int q = 0; q < R; ++q) v[J + q * Q] = y[q];
-        if constexpr (J + 1 < Q) GDifLevel<N, R, PRUNED, J + 1>::run(v);
-    }
-};
-
-template <int N, int B = 0> struct GSub {             // the R sub-transforms of length N / R
-    static FB_HD void run(cx<float>* v);
-};
-
-template <int N> struct GRegFFT {
-    static FB_HD void run(cx<float>* v)
-    {
-        if constexpr (N > 1) {
-            constexpr int R = first_radix(N);
-            GDifLevel<N, R, false>::run(v);
-            GSub<N>::run(v);
-        }
-    }
-    // upper half of the input is zero (N even)
-    static FB_HD void run_pruned(cx<float>* v)
-    {
-        static_assert(N % 2 == 0, "pruned first level is radix 2");
-        GDifLevel<N, 2, true>::run(v);
-        GSub<N>::run(v);
-    }
-};
-template <int N, int B> FB_HD void GSub<N, B>::run(cx<float>* v)
-{
-    constexpr int R = first_radix(N);
-    GRegFFT<N / R>::run(v + B * (N / R));
-    if constexpr (B + 1 < R) GSub<N, B + 1>::run(v);
-}
-
+// (the mixed-radix register FFT GRegFFT / gpos lives in fb_gfft.cuh, shared with the shared-memory passes)
 FB_HD constexpr bool is_pow2(int n) { return (n & (n - 1)) == 0; }
 
 #if defined(__CUDACC__)
@@ -371,7 +249,7 @@ template <int N> struct LaneFFT {
     {
         if constexpr (is_pow2(N) && kUseDit) PDitFFT<N>::run(v);
         else if constexpr (is_pow2(N)) PRegFFT<N>::run(v);
-        else GRegFFT<N>::run(v);
+        else GRegFFT<float, N, false>::run(v);
     }
     template <bool PRUNED> static __device__ __forceinline__ void run_first(cx<float>* v, bool pruned_now)
     {
@@ -382,7 +260,7 @@ template <int N> struct LaneFFT {
             PRegFFT<N / 2>::run(v);
             PRegFFT<N / 2>::run(v + N / 2);
         } else {
-            if (PRUNED && pruned_now) GRegFFT<N>::run_pruned(v); else GRegFFT<N>::run(v);
+            if (PRUNED && pruned_now) GRegFFT<float, N, false>::run_pruned(v); else GRegFFT<float, N, false>::run(v);
         }
     }
 };

@@ -163,22 +163,23 @@ struct StreamCtx {
 };
 
 static std::mutex g_mu;
-static std::map<std::tuple<int, int, int>, DevTables> g_tables;      // (device, n, is_double)
+static std::map<std::tuple<int, int, int>, DevTables> g_tables;      // (device, n, is_double + 2 * wide radices)
 static std::map<std::pair<int, void*>, StreamCtx> g_ctx;              // (device, stream)
 static std::map<int, bool> g_attr_done;
 static long long g_opt_ws_bytes = 2LL << 30;
 static long long g_opt_host_chunk = 64LL << 20;
 static long long g_opt_profile = 0;
+static long long g_opt_max_radix = 16;         // largest radix of the shared-memory passes (experiment switch; set before first use)
 static long long g_opt_fast_flags = 0;       // experiment switches, see FastParams::flags (+16: K2 unbatched twiddles, +32: K3 8 lines)
 
 template <typename T>
-static int get_tables(int device, int n, Plan1D& out)
+static int get_tables(int device, int n, Plan1D& out, bool wide = false)
 {
-    auto key = std::make_tuple(device, n, (int)(sizeof(T) == 8));
+    auto key = std::make_tuple(device, n, (int)(sizeof(T) == 8) + (wide ? 2 : 0));
     auto it = g_tables.find(key);
     if (it == g_tables.end()) {
         DevTables t;
-        t.radix = radix_sequence(n);
+        t.radix = wide ? radix_sequence(n, (int)g_opt_max_radix) : radix_sequence_basic(n);
         if ((int)t.radix.size() > kMaxPass) return fail(FB_ESIZE, "fft length %d needs too many passes", n);
         auto pos = digit_positions(n, t.radix);
         auto tw = twiddle_table<T>(n);
@@ -537,8 +538,8 @@ static int launch_chunk(const Problem& q, StreamCtx& ctx, const void* img0, cons
 {
     XcParams p{};
     int rc;
-    if ((rc = get_tables<T>(ctx.device, q.nx, p.px)) != FB_OK) return rc;
-    if ((rc = get_tables<T>(ctx.device, q.ny, p.py)) != FB_OK) return rc;
+    if ((rc = get_tables<T>(ctx.device, q.nx, p.px, q.fused)) != FB_OK) return rc;     // fused kernel: wide pass radices
+    if ((rc = get_tables<T>(ctx.device, q.ny, p.py, q.fused)) != FB_OK) return rc;
     const Geometry& g = q.g;
     p.img0 = img0; p.img1 = img1; p.n = nb;
     p.h0 = q.h0; p.w0 = q.w0; p.h1 = q.h1; p.w1 = q.w1; p.ny = q.ny; p.nx = q.nx; p.kp = g.kp;
@@ -814,6 +815,7 @@ extern "C" int fb_set_option(const char* name, long long value)
 {
     if (!name) return fail(FB_EINVAL, "null option name");
     std::lock_guard<std::mutex> lk(g_mu);
+    if (!strcmp(name, "max_radix")) { if (value < 5 || value > 16) return fail(FB_EINVAL, "max_radix out of range"); g_opt_max_radix = value; return FB_OK; }
     if (!strcmp(name, "ws_bytes")) { if (value < (1 << 20)) return fail(FB_EINVAL, "ws_bytes too small"); g_opt_ws_bytes = value; return FB_OK; }
     if (!strcmp(name, "profile")) { g_opt_profile = value ? 1 : 0; return FB_OK; }
     if (!strcmp(name, "fast_flags")) { g_opt_fast_flags = value; return FB_OK; }

@@ -142,14 +142,16 @@ FB_DEV Acc<T> block_reduce(Acc<T> a, Acc<T>* red, int tid, int nthr)
 #endif
 }
 
-template <typename T, bool INV>
+// MAXR: largest pass radix the plan may contain (8: basic inlined passes; 16: all radices, out of line)
+template <typename T, bool INV, int MAXR = 8>
 FB_DEV void fft_lines(const Plan1D& pl, cx<T>* s, int pitch, int nl, int tid, int nthr)
 {
     const cx<T>* tw = reinterpret_cast<const cx<T>*>(pl.tw);
     if (!INV) {
         int L = pl.n;
         for (int p = 0; p < pl.npass; ++p) {
-            fft_pass_any<T, false>(pl.radix[p], s, pitch, nl, pl.n, L, tw, tid, nthr);
+            if constexpr (MAXR > 8) fft_pass_any<T, false>(pl.radix[p], s, pitch, nl, pl.n, L, tw, tid, nthr);
+            else fft_pass_basic<T, false>(pl.radix[p], s, pitch, nl, pl.n, L, tw, tid, nthr);
             L /= pl.radix[p];
             FB_SYNC();
         }
@@ -157,7 +159,8 @@ FB_DEV void fft_lines(const Plan1D& pl, cx<T>* s, int pitch, int nl, int tid, in
         int L = 1;
         for (int p = pl.npass - 1; p >= 0; --p) {
             L *= pl.radix[p];
-            fft_pass_any<T, true>(pl.radix[p], s, pitch, nl, pl.n, L, tw, tid, nthr);
+            if constexpr (MAXR > 8) fft_pass_any<T, true>(pl.radix[p], s, pitch, nl, pl.n, L, tw, tid, nthr);
+            else fft_pass_basic<T, true>(pl.radix[p], s, pitch, nl, pl.n, L, tw, tid, nthr);
             FB_SYNC();
         }
     }
@@ -170,7 +173,7 @@ FB_DEV void fft_lines(const Plan1D& pl, cx<T>* s, int pitch, int nl, int tid, in
 // the two half spectra are separated and written in natural k order to
 // dst[row * dpitch + k].
 // ----------------------------------------------------------------------------
-template <typename T, typename TI>
+template <typename T, typename TI, int MAXR = 8>
 FB_DEV void rows_forward_tile(const XcParams& p, const TI* img, int H, int W, int line0, int nl,
                               cx<T>* dst, int dpitch, cx<T>* s, int pitch, int tid, int nthr)
 {
@@ -186,7 +189,7 @@ FB_DEV void rows_forward_tile(const XcParams& p, const TI* img, int H, int W, in
         s[(size_t)x * pitch + l] = mk<T>(a, b);
     }
     FB_SYNC();
-    fft_lines<T, false>(p.px, s, pitch, nl, tid, nthr);
+    fft_lines<T, false, MAXR>(p.px, s, pitch, nl, tid, nthr);
     const int kp = p.kp;
     const int* pos = p.px.pos;
     for (int idx = tid; idx < kp * nl; idx += nthr) {
@@ -207,10 +210,10 @@ FB_DEV void rows_forward_tile(const XcParams& p, const TI* img, int H, int W, in
 // Forward both, P = conj(F0) F1 (matcher.py:65), Q = F0 F1 (matcher.py:114),
 // scaled by 1/(ny nx), inverse both (only P unless mirror).
 // ----------------------------------------------------------------------------
-template <typename T>
+template <typename T, int MAXR = 8>
 FB_DEV void cols_stage(const XcParams& p, cx<T>* S, int pitch, int half, bool mirror, int tid, int nthr)
 {
-    fft_lines<T, false>(p.py, S, pitch, 2 * half, tid, nthr);
+    fft_lines<T, false, MAXR>(p.py, S, pitch, 2 * half, tid, nthr);
     const T sc = (T)p.scale;
     for (int idx = tid; idx < p.ny * half; idx += nthr) {
         int e = idx / half, c = idx - e * half;
@@ -220,7 +223,7 @@ FB_DEV void cols_stage(const XcParams& p, cx<T>* S, int pitch, int half, bool mi
         if (mirror) q[half] = cscale(cmul(a, b), sc);
     }
     FB_SYNC();
-    fft_lines<T, true>(p.py, S, pitch, mirror ? 2 * half : half, tid, nthr);
+    fft_lines<T, true, MAXR>(p.py, S, pitch, mirror ? 2 * half : half, tid, nthr);
 }
 
 // ----------------------------------------------------------------------------
@@ -250,7 +253,7 @@ FB_DEV void rows_inverse_fill(const XcParams& p, const cx<T>* X, const cx<T>* Y,
     }
 }
 
-template <typename T>
+template <typename T, int MAXR = 8>
 FB_DEV void rows_inverse_tile(const XcParams& p, const cx<T>* Pb, const cx<T>* Qb, int rpitch, int row0, int nl,
                               bool mirror, Acc<T>& acc, cx<T>* s, int pitch, int tid, int nthr, int pair = 0)
 {
@@ -268,7 +271,7 @@ FB_DEV void rows_inverse_tile(const XcParams& p, const cx<T>* Pb, const cx<T>* Q
         rows_inverse_fill<T>(p, X, Y, s, pitch, l, k, kp);   // one k per call
     }
     FB_SYNC();
-    fft_lines<T, true>(p.px, s, pitch, nl, tid, nthr);
+    fft_lines<T, true, MAXR>(p.px, s, pitch, nl, tid, nthr);
     const bool want_std = p.conf_mode == CONF_STD;
     const float inv_nl = 1.0f / (float)nl;
     const T* norm = reinterpret_cast<const T*>(p.norm);
@@ -313,7 +316,7 @@ FB_DEV void rows_inverse_tile(const XcParams& p, const cx<T>* Pb, const cx<T>* Q
 // (:107-110) and confidence (:111-134) for one pair.  Recomputes the three
 // surface rows around the peak from the P (and Q) rows.
 // ----------------------------------------------------------------------------
-template <typename T>
+template <typename T, int MAXR = 8>
 FB_DEV void finalize_pair(const XcParams& p, int pair, const Acc<T>& best, const cx<T>* Pb, const cx<T>* Qb,
                           int rpitch, bool mirror, cx<T>* s, int tid, int nthr, size_t ks = 1)
 {
@@ -332,7 +335,7 @@ FB_DEV void finalize_pair(const XcParams& p, int pair, const Acc<T>& best, const
             rows_inverse_fill<T>(p, Pb + ro, mirror ? Qb + ro : nullptr, s, pitch, l, k, kp, ks);
         }
         FB_SYNC();
-        fft_lines<T, true>(p.px, s, pitch, 3, tid, nthr);
+        fft_lines<T, true, MAXR>(p.px, s, pitch, 3, tid, nthr);
         if (p.norm) {                                        // sub-pixel fit runs on the normalised surface
             const T* norm = reinterpret_cast<const T*>(p.norm);
             for (int idx = tid; idx < nx * 3; idx += nthr) {
@@ -525,7 +528,7 @@ FB_DEV void kf_fused(const XcParams& p, int bid, int tid, int nthr, unsigned cha
         const int lines = (H + 1) / 2;
         for (int line0 = 0; line0 < lines; line0 += tl) {
             int nl = lines - line0 < tl ? lines - line0 : tl;
-            rows_forward_tile<T, TI>(p, img, H, W, line0, nl, dst, sp, s, pitch, tid, nthr);
+            rows_forward_tile<T, TI, 16>(p, img, H, W, line0, nl, dst, sp, s, pitch, tid, nthr);
         }
         for (int idx = tid; idx < (ny - H) * kp; idx += nthr) {
             int y = idx / kp, k = idx - y * kp;
@@ -533,16 +536,16 @@ FB_DEV void kf_fused(const XcParams& p, int bid, int tid, int nthr, unsigned cha
         }
     }
     FB_SYNC();
-    cols_stage<T>(p, S, sp, kp, mirror, tid, nthr);
+    cols_stage<T, 16>(p, S, sp, kp, mirror, tid, nthr);
     Acc<T> acc; acc_init(acc);
     const int rpt = mirror ? tl : 2 * tl;
     for (int row0 = 0; row0 < ny; row0 += rpt) {
         int rows = ny - row0 < rpt ? ny - row0 : rpt;
         int nl = mirror ? rows : (rows + 1) / 2;
-        rows_inverse_tile<T>(p, S, S + kp, sp, row0, nl, mirror, acc, s, pitch, tid, nthr, pair);
+        rows_inverse_tile<T, 16>(p, S, S + kp, sp, row0, nl, mirror, acc, s, pitch, tid, nthr, pair);
     }
     Acc<T> best = block_reduce<T>(acc, red, tid, nthr);
-    finalize_pair<T>(p, pair, best, S, S + kp, sp, mirror, s, tid, nthr);
+    finalize_pair<T, 16>(p, pair, best, S, S + kp, sp, mirror, s, tid, nthr);
 }
 
 }  // namespace fb

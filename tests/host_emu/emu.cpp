@@ -42,9 +42,9 @@ template <typename T> struct HostPlan {
     std::vector<cx<T>> tw;
     std::vector<int> pos;
     Plan1D p;
-    explicit HostPlan(int n)
+    HostPlan(int n, bool wide)
     {
-        auto r = radix_sequence(n);
+        auto r = wide ? radix_sequence(n) : radix_sequence_basic(n);
         pos = digit_positions(n, r);
         tw = twiddle_table<T>(n);
         p.n = n; p.npass = (int)r.size();
@@ -62,12 +62,12 @@ static int run(const void* img0, const void* img1, int n, int h0, int w0, int h1
     g.h0 = h0; g.w0 = w0; g.h1 = h1; g.w1 = w1; g.ny = ny; g.nx = nx;
     g.esize = (int)sizeof(cx<T>); g.mirror = conf_mode == CONF_MIRROR;
     if (!choose_tiles(g)) return -3;
-    HostPlan<T> px(nx), py(ny);
+    const bool fused = path == 1 || (path == 0 && g.fused);
+    HostPlan<T> px(nx, fused), py(ny, fused);
     XcParams p{};
     p.img0 = img0; p.img1 = img1; p.n = n; p.h0 = h0; p.w0 = w0; p.h1 = h1; p.w1 = w1;
     p.ny = ny; p.nx = nx; p.kp = g.kp; p.px = px.p; p.py = py.p; p.fpitch = g.fpitch;
     p.dx = out; p.dy = out + n; p.conf = out + 2 * n; p.peak = out + 3 * n; p.mir = out + 4 * n; p.conf_mode = conf_mode; p.subpixel = subpixel; p.scale = 1.0 / ((double)ny * nx);
-    bool fused = path == 1 || (path == 0 && g.fused);
     if (fused) {
         if (!g.fused) return -4;
         p.tl = g.tl_fused; p.spitch = g.spitch;

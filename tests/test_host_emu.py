@@ -22,7 +22,7 @@ _DT = {np.dtype('float32'): 0, np.dtype('uint8'): 1, np.dtype('float64'): 2}
 def emu():
     so = os.path.join(EMU_DIR, 'libfb_emu.so')
     src = os.path.join(EMU_DIR, 'emu.cpp')
-    deps = [src] + [os.path.join(ROOT, 'feabas_b200', 'csrc', f) for f in ('fb_xcorr.cuh', 'fb_fft.cuh', 'fb_host_plan.h')]
+    deps = [src] + [os.path.join(ROOT, 'feabas_b200', 'csrc', f) for f in ('fb_xcorr.cuh', 'fb_fft.cuh', 'fb_gfft.cuh', 'fb_host_plan.h')]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.run(['g++', '-std=c++20', '-O2', '-fPIC', '-shared', '-pthread', '-o', so, src], check=True)
     lib = ctypes.CDLL(so)
