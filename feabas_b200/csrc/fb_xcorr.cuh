@@ -143,6 +143,10 @@ FB_DEV Acc<T> block_reduce(Acc<T> a, Acc<T>* red, int tid, int nthr)
 }
 
 // MAXR: largest pass radix the plan may contain (8: basic inlined passes; 16: all radices, out of line)
+// floor(i / d) for 0 <= i < 2^22 through the rounded reciprocal inv = 1.0f / d (exact in that range: the
+// true quotient of i + 0.5 is at least 0.5 / d away from an integer, the float error is below that)
+FB_HD int fdiv(int i, float inv) { return (int)(((float)i + 0.5f) * inv); }
+
 template <typename T, bool INV, int MAXR = 8>
 FB_DEV void fft_lines(const Plan1D& pl, cx<T>* s, int pitch, int nl, int tid, int nthr)
 {
@@ -178,8 +182,9 @@ FB_DEV void rows_forward_tile(const XcParams& p, const TI* img, int H, int W, in
                               cx<T>* dst, int dpitch, cx<T>* s, int pitch, int tid, int nthr)
 {
     const int nx = p.nx;
+    const float inv_nx = 1.0f / (float)nx;
     for (int idx = tid; idx < nx * nl; idx += nthr) {
-        int l = idx / nx, x = idx - l * nx;
+        int l = fdiv(idx, inv_nx), x = idx - l * nx;
         int r0 = 2 * (line0 + l), r1 = r0 + 1;
         T a = T(0), b = T(0);
         if (x < W) {
@@ -192,8 +197,9 @@ FB_DEV void rows_forward_tile(const XcParams& p, const TI* img, int H, int W, in
     fft_lines<T, false, MAXR>(p.px, s, pitch, nl, tid, nthr);
     const int kp = p.kp;
     const int* pos = p.px.pos;
+    const float inv_kp = 1.0f / (float)kp;
     for (int idx = tid; idx < kp * nl; idx += nthr) {
-        int l = idx / kp, k = idx - l * kp;
+        int l = fdiv(idx, inv_kp), k = idx - l * kp;
         int km = k ? nx - k : 0;
         cx<T> zk = s[(size_t)FB_LDG(pos + k) * pitch + l];
         cx<T> zm = s[(size_t)FB_LDG(pos + km) * pitch + l];
@@ -215,8 +221,9 @@ FB_DEV void cols_stage(const XcParams& p, cx<T>* S, int pitch, int half, bool mi
 {
     fft_lines<T, false, MAXR>(p.py, S, pitch, 2 * half, tid, nthr);
     const T sc = (T)p.scale;
+    const float inv_half = 1.0f / (float)half;
     for (int idx = tid; idx < p.ny * half; idx += nthr) {
-        int e = idx / half, c = idx - e * half;
+        int e = fdiv(idx, inv_half), c = idx - e * half;
         cx<T>* q = S + (size_t)e * pitch + c;
         cx<T> a = q[0], b = q[half];
         q[0] = cscale(cmulc(b, a), sc);
@@ -258,8 +265,9 @@ FB_DEV void rows_inverse_tile(const XcParams& p, const cx<T>* Pb, const cx<T>* Q
                               bool mirror, Acc<T>& acc, cx<T>* s, int pitch, int tid, int nthr, int pair = 0)
 {
     const int nx = p.nx, ny = p.ny, kp = p.kp;
+    const float inv_kp = 1.0f / (float)kp;
     for (int idx = tid; idx < kp * nl; idx += nthr) {
-        int l = idx / kp, k = idx - l * kp;
+        int l = fdiv(idx, inv_kp), k = idx - l * kp;
         const cx<T>* X; const cx<T>* Y;
         if (mirror) {
             int y = row0 + l;
@@ -443,8 +451,9 @@ FB_DEV void k2_columns(const XcParams& p, int bid, int tid, int nthr, unsigned c
     const cx<T>* F0 = reinterpret_cast<const cx<T>*>(p.F0) + (size_t)pair * p.h0 * p.fpitch;
     const cx<T>* F1 = reinterpret_cast<const cx<T>*>(p.F1) + (size_t)pair * p.h1 * p.fpitch;
     const int w2 = 2 * tc;
+    const float inv_w2 = 1.0f / (float)w2;
     for (int idx = tid; idx < ny * w2; idx += nthr) {
-        int y = idx / w2, c2 = idx - y * w2;
+        int y = fdiv(idx, inv_w2), c2 = idx - y * w2;
         int second = c2 >= tc;
         int col = ct * tc + (second ? c2 - tc : c2);
         cx<T> v = mk<T>(T(0), T(0));
@@ -455,8 +464,9 @@ FB_DEV void k2_columns(const XcParams& p, int bid, int tid, int nthr, unsigned c
     cols_stage<T>(p, S, pitch, tc, mirror, tid, nthr);
     cx<T>* G = reinterpret_cast<cx<T>*>(p.G) + (size_t)pair * ny * 2 * p.fpitch;
     const int wout = mirror ? w2 : tc;
+    const float inv_wout = 1.0f / (float)wout;
     for (int idx = tid; idx < ny * wout; idx += nthr) {
-        int y = idx / wout, c2 = idx - y * wout;
+        int y = fdiv(idx, inv_wout), c2 = idx - y * wout;
         int second = c2 >= tc;
         int col = ct * tc + (second ? c2 - tc : c2);
         if (col < p.kp) G[(size_t)y * 2 * p.fpitch + (second ? p.fpitch : 0) + col] = S[(size_t)y * pitch + c2];
@@ -521,6 +531,16 @@ FB_DEV void kf_fused(const XcParams& p, int bid, int tid, int nthr, unsigned cha
     cx<T>* s = S + (size_t)ny * sp;
     Acc<T>* red = reinterpret_cast<Acc<T>*>(s + (size_t)nx * pitch);
     const int pair = bid;
+#if defined(__CUDA_ARCH__)
+    if (tid < 2) {                                  // both images of the pair -> L2 ahead of the row tiles that read them
+        const int H = tid ? p.h1 : p.h0, W = tid ? p.w1 : p.w0;
+        size_t a = reinterpret_cast<size_t>(reinterpret_cast<const TI*>(tid ? p.img1 : p.img0) + (size_t)pair * H * W);
+        size_t e = (a + (size_t)H * W * sizeof(TI)) & ~(size_t)15;
+        a = (a + 15) & ~(size_t)15;
+        if (e > a) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(a), "r"((unsigned)(e - a)) : "memory");
+    }
+#endif
+    const float inv_kp = 1.0f / (float)kp;
     for (int second = 0; second < 2; ++second) {
         const int H = second ? p.h1 : p.h0, W = second ? p.w1 : p.w0;
         const TI* img = reinterpret_cast<const TI*>(second ? p.img1 : p.img0) + (size_t)pair * H * W;
@@ -531,7 +551,7 @@ FB_DEV void kf_fused(const XcParams& p, int bid, int tid, int nthr, unsigned cha
             rows_forward_tile<T, TI, 16>(p, img, H, W, line0, nl, dst, sp, s, pitch, tid, nthr);
         }
         for (int idx = tid; idx < (ny - H) * kp; idx += nthr) {
-            int y = idx / kp, k = idx - y * kp;
+            int y = fdiv(idx, inv_kp), k = idx - y * kp;
             dst[(size_t)(H + y) * sp + k] = mk<T>(T(0), T(0));
         }
     }
