@@ -10,7 +10,7 @@ tail -5 $OUT/pytest_gpu.log
 timeout 300 python __graft_entry__.py smoke > $OUT/smoke.log 2>&1; tail -2 $OUT/smoke.log
 timeout 900 python bench.py > $OUT/bench.json 2> $OUT/bench.err; tail -c 3000 $OUT/bench.json
 timeout 600 python bench.py --impl reference --steps 20 --warmup 3 > $OUT/bench_reference.json 2>> $OUT/bench.err; tail -c 600 $OUT/bench_reference.json
-for wl in xcorr512_nopad xcorr256 xcorr128 xcorr1024 xcorr2048 stitch_fine thumb150; do
+for wl in xcorr512_nopad xcorr256 xcorr128 xcorr1024 xcorr2048 stitch_fine thumb150 align280; do
   timeout 120 python bench.py --workload $wl --steps 30 --no-cpu-baseline > $OUT/bench_$wl.json 2>> $OUT/bench.err
 done
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:fbk -c 400 --csv \
