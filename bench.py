@@ -36,6 +36,9 @@ WORKLOADS = {
     'stitch_fine': dict(h=74, w=67, pad=True, batch=16384),       # config 1/2 finest level, FFT 150x135
     'thumb150': dict(h=150, w=150, pad=True, batch=4096),         # config 3, FFT 300x300
     'align280': dict(h=280, w=280, pad=True, batch=1024),         # default fine alignment (spacing 400, shrink 0.7), FFT 576x576
+    # config 4 through bboxes_mesh_renderer_matcher (matcher.py:781-861): a uint8 section pair, a dense grid of
+    # 512x512 blocks gathered + band-passed (sigma 3.5) + matched on the device; e2e uploads the two sections
+    'align512_blocks': dict(kind='blocks', h=512, w=512, pad=True, section=8192, sigma=3.5, batch=256),
 }
 
 
@@ -146,6 +149,234 @@ def cpu_pairs_per_worker(wl, target_cpu_seconds, cores):
     return max(1, int(round(target_cpu_seconds / cores / max(est, 1e-5))))
 
 
+
+# ----------------------------------------------------------------------------------------------
+# matcher-level workload: block grid of a section pair through bboxes_mesh_renderer_matcher
+# ----------------------------------------------------------------------------------------------
+def make_section_pair(size, seed, device, shift=(7, -5)):
+    """Two uint8 'sections' (size x size) cut from one band-limited canvas at a known integer offset
+    + independent noise.  A feature at p in img0 sits at p + shift in img1."""
+    import torch
+    import torch.nn.functional as F
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    m = 32
+    c = torch.randn((1, 1, size + 2 * m, size + 2 * m), generator=g, device=device)
+    t = torch.arange(-12, 13, device=device, dtype=torch.float32)
+    k = torch.exp(-0.5 * (t / 3.0) ** 2); k = k / k.sum()
+    c = F.conv2d(F.pad(c, (12, 12, 0, 0), mode='replicate'), k.view(1, 1, 1, -1))
+    c = F.conv2d(F.pad(c, (0, 0, 12, 12), mode='replicate'), k.view(1, 1, -1, 1))[0, 0]
+    c = c / c.std()
+    dx, dy = shift
+    a = c[m:m + size, m:m + size]
+    b = c[m - dy:m - dy + size, m - dx:m - dx + size]
+    def u8(x):
+        x = x + 0.2 * torch.randn(x.shape, generator=g, device=device)
+        return (x * 40 + 128).clamp_(0, 255).to(torch.uint8).contiguous()
+    return u8(a), u8(b)
+
+
+def _cpu_blocks_init(h, w, pad, per_worker, sigma, seed):
+    os.environ['OMP_NUM_THREADS'] = '1'
+    import numpy as np
+    rng = np.random.default_rng(seed + os.getpid())
+    side = int(np.ceil(np.sqrt(per_worker)))
+    img = rng.integers(0, 256, (side * h + 8, side * w + 8), dtype=np.uint8)
+    _W['img0'] = img
+    _W['img1'] = np.roll(img, (3, -5), axis=(0, 1))
+    _W['boxes'] = [(x * w, y * h, x * w + w, y * h + h) for y in range(side) for x in range(side)][:per_worker]
+    _W['pad'], _W['sigma'] = pad, sigma
+    from oracle import xcorr_oracle as xo
+    from oracle import matcher_oracle as mo
+    _W['f'], _W['dog'] = xo.xcorr_oracle, mo.masked_dog_oracle
+
+
+def _cpu_blocks_task(_):
+    """crop + masked DoG + xcorr_fft of this worker's blocks (renderer.py:601-648 -> matcher.py:846)."""
+    import numpy as np
+    t = time.perf_counter()
+    st0 = np.stack([_W['img0'][y0:y1, x0:x1] for x0, y0, x1, y1 in _W['boxes']])
+    st1 = np.stack([_W['img1'][y0:y1, x0:x1] for x0, y0, x1, y1 in _W['boxes']])
+    f0 = _W['dog'](st0, _W['sigma']).astype(np.float32)
+    f1 = _W['dog'](st1, _W['sigma']).astype(np.float32)
+    _W['f'](f0, f1, conf_mode=2, subpixel=True, pad=_W['pad'])
+    return time.perf_counter() - t
+
+
+def cpu_blocks_arm(wl, per_worker):
+    import psutil
+    from concurrent.futures import ProcessPoolExecutor
+    import multiprocessing as mp
+    cores = psutil.cpu_count(logical=False) or os.cpu_count() or 1
+    pool = ProcessPoolExecutor(cores, mp_context=mp.get_context('spawn'), initializer=_cpu_blocks_init,
+                               initargs=(wl['h'], wl['w'], wl['pad'], per_worker, wl['sigma'], 4321))
+    list(pool.map(_cpu_blocks_task, range(cores)))            # spawn + warm
+    return pool, cores
+
+
+def bench_blocks(args, wl, rank, world, local, warmup):
+    import numpy as np
+    h, w, pad, size, sigma = wl['h'], wl['w'], wl['pad'], wl['section'], wl['sigma']
+    nby, nbx = size // h, size // w
+    batch = nby * nbx
+    from oracle import xcorr_oracle as xo
+    ny, nx = xo.fft_shape((h, w), (h, w), pad)
+    config = {'workload': f'{args.workload}: bboxes_mesh_renderer_matcher on a {size}x{size} uint8 section pair, {nby}x{nbx} grid of '
+                          f'{h}x{w} blocks, sigma={sigma} (masked DoG), pad={pad} (FFT {ny}x{nx}), FFT_CONF_MIRROR, subpixel=True',
+              'pairs_per_step_per_gpu': batch, 'fft': [ny, nx], 'l2': 'inputs larger than L2 (no flush needed)'}
+    kw = dict(sigma=sigma, batch_size=batch, pad=pad, subpixel=True)
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        per_step_wall = min(3.0, max(0.3, 90.0 / (args.steps + warmup)))
+        pool, cores = None, 0
+        import psutil
+        cores = psutil.cpu_count(logical=False) or os.cpu_count() or 1
+        per_worker = max(1, int(round(per_step_wall / 0.085)))   # ~85 ms per 512^2 block pair per core (crop + 2 DoG + xcorr)
+        pool, cores = cpu_blocks_arm(wl, per_worker)
+        for _ in range(warmup):
+            list(pool.map(_cpu_blocks_task, range(cores)))
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            list(pool.map(_cpu_blocks_task, range(cores)))
+        secs = time.perf_counter() - t0
+        pool.shutdown()
+        val = cores * per_worker * args.steps / secs
+        sample = f'{per_worker} blocks per worker x {cores} single-thread workers per step (oracle port: crop + masked DoG + xcorr_fft)'
+        print(json.dumps({
+            'impl': 'reference', 'metric': 'xcorr_block_matches_per_sec', 'value': val, 'unit': 'matches/s', 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': warmup, 'ms_per_step': 1e3 * secs / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config,
+            'cpu_baseline': {'value': val, 'unit': 'matches/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': val, 'unit': 'matches/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+        return
+
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    config['numa_bound_cpus'] = bind_to_gpu_numa(local) if world > 1 else 0
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    import feabas_b200.cuda as fc
+    L = fc._lib
+    L.set_option('ws_bytes', int(args.ws_gib * (1 << 30)))
+    shift = (7, -5)
+    a, b = make_section_pair(size, 300 + rank, dev, shift)
+    m0, m1 = fc.AffineMesh((0, 0, size, size), uid=0), fc.AffineMesh((0, 0, size, size), uid=1)
+    boxes = np.array([(x * w, y * h, x * w + w, y * h + h) for y in range(nby) for x in range(nbx)], dtype=np.float64)
+    l0, l1 = fc.ArrayLoader(a, device=local), fc.ArrayLoader(b, device=local)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        return fc.bboxes_mesh_renderer_matcher(m0, m1, l0, l1, boxes, boxes, **kw)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        xy0, xy1, conf = step()
+    d = xy1 - xy0                                               # every block must recover the section offset
+    n_ok = int(np.sum((np.round(d[:, 0]) == shift[0]) & (np.round(d[:, 1]) == shift[1])))
+    assert n_ok >= 0.99 * batch, f'only {n_ok}/{batch} blocks recovered the offset {shift}: {d[:4]}'
+    config['ground_truth_recovered'] = n_ok / batch
+    L.profile_read(local, stream, reset=True) if L.launch_count() else None
+    L.set_option('profile', 1)
+    mon, mon_path = clocks_monitor_start(local) if rank == 0 else (None, None)
+    launches0 = L.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = L.launch_count() - launches0
+    clocks = clocks_monitor_stop(mon, mon_path) if rank == 0 else None
+    L.set_option('profile', 0)
+    prof = L.profile_read(local, stream, reset=True)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * batch * args.steps / (ms * 1e-3)
+
+    e2e = None
+    if not args.no_e2e:
+        ah, bh = a.cpu().pin_memory(), b.cpu().pin_memory()
+        e_steps = max(3, min(args.steps, 10))
+
+        def e_step():
+            # the call a user makes: host images in, matches out (upload of both sections inside)
+            return fc.bboxes_mesh_renderer_matcher(m0, m1, fc.ArrayLoader(ah, device=local), fc.ArrayLoader(bh, device=local),
+                                                   boxes, boxes, **kw)
+        for _ in range(2):
+            r = e_step()
+        assert np.array_equal(r[0], xy0) and np.array_equal(r[2], conf), 'host path and device path disagree'
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            r = e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {'value': world * batch * e_steps / dt, 'unit': 'matches/s',
+               'h2d_bytes_per_step': int(ah.numel() + bh.numel()), 'd2h_bytes_per_step': int(5 * 8 * batch), 'steps': e_steps,
+               'api': 'feabas_b200.cuda.bboxes_mesh_renderer_matcher(ArrayLoader(pinned uint8 host sections)) -> fb_crop_blocks + fb_masked_dog + fb_xcorr_batch_device'}
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_kind = peaks()
+    b_alg, b_min, b_pass = algorithmic_bytes(h, w, ny, nx, True, False)
+    kern = {k: {'ms_total': v[0], 'launches': v[1], 'ms_per_launch': (v[0] / v[1] if v[1] else None)} for k, v in prof.items() if v[1]}
+    dom = max(kern, key=lambda k: kern[k]['ms_total'])
+    pairs_per_launch = batch * args.steps / kern[dom]['launches']
+    bytes_per_pair = column_kernel_bytes(h, ny, nx, True) if dom == 'columns' else b_min
+    achieved = bytes_per_pair * pairs_per_launch / (kern[dom]['ms_per_launch'] * 1e-3) / 1e9
+    xcorr_ms = sum(v['ms_total'] for v in kern.values())
+    # image stage (fb_crop_blocks + fb_masked_dog, both sections): gather u8 -> f32 stack, two blur passes per stack
+    img_bytes = 2 * batch * h * w * (1 + 4 + 3 * 8)              # read u8, write f32; DoG: 2 x (read + write) + final read/write
+    roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                'traffic': None, 'peak_kind': peak_kind, 'algorithmic_bytes_per_pair': bytes_per_pair,
+                'pairs_per_launch': pairs_per_launch, 'ms_per_launch': kern[dom]['ms_per_launch'],
+                'kernel_share_of_step': kern[dom]['ms_total'] / ms if world == 1 else None,
+                'pipeline': {'bytes_per_pair': b_alg, 'b_min': b_min, 'b_pass': b_pass,
+                             'achieved': value / world * b_alg / 1e9, 'frac': value / world * b_alg / 1e9 / peak},
+                'image_stage': {'ms_per_step': (ms - xcorr_ms) / args.steps if world == 1 else None,
+                                'algorithmic_bytes_per_step': img_bytes,
+                                'note': 'crop (u8 gather -> f32) + masked DoG of both stacks + host control flow = step - xcorr kernels'},
+                'kernels': kern}
+    cpu = None
+    if not args.no_cpu_baseline:
+        per_worker = 16
+        pool, cores = cpu_blocks_arm(wl, per_worker)
+        t0 = time.perf_counter()
+        list(pool.map(_cpu_blocks_task, range(cores)))
+        s_ = time.perf_counter() - t0
+        pool.shutdown()
+        cpu = {'value': cores * per_worker / s_, 'unit': 'matches/s', 'cores': cores, 'kind': 'port',
+               'sample': f'{cores * per_worker} blocks ({per_worker} per single-thread worker, {cores} workers): crop + masked DoG + '
+                         f'xcorr_fft (oracle port), {s_:.1f} s wall'}
+    line = {'metric': 'xcorr_block_matches_per_sec', 'value': value, 'unit': 'matches/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config,
+            'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ----------------------------------------------------------------------------------------------
 def clocks_monitor_start(gpu_index):
     path = tempfile.mktemp(prefix='fb_clocks_', suffix='.csv')
@@ -199,6 +430,25 @@ def measured_traffic(workload, kernel):
         return None
 
 
+def bind_to_gpu_numa(local):
+    """Pin this rank to the CPUs next to its GPU (NVML affinity mask) BEFORE host buffers are allocated, so
+    that the pinned staging memory is first-touched on the GPU's NUMA node: with N ranks the end-to-end path
+    is bound by host memory / PCIe, not by the kernels."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        hnd = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(hnd, words)
+        cpus = [64 * i + b for i, wd in enumerate(mask) for b in range(64) if (wd >> b) & 1]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
@@ -228,6 +478,8 @@ def main():
     world = int(os.environ.get('WORLD_SIZE', 1))
     local = int(os.environ.get('LOCAL_RANK', 0))
     warmup = max(args.warmup, 3)
+    if wl.get('kind') == 'blocks':
+        return bench_blocks(args, wl, rank, world, local, warmup)
     h, w, pad, batch = wl['h'], wl['w'], wl['pad'], wl['batch']
 
     from oracle import xcorr_oracle as xo           # bench may execute oracle/ only for the CPU legs
@@ -271,6 +523,7 @@ def main():
     assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    config['numa_bound_cpus'] = bind_to_gpu_numa(local) if world > 1 else 0
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     import feabas_b200.cuda as fc

@@ -11,6 +11,7 @@
 // header says so (float64 accumulation of scipy.ndimage.correlate1d, OpenCV's fixed-point tables).
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -127,6 +128,122 @@ __global__ void __launch_bounds__(kNT) fbk_gauss2d(const __grid_constant__ Gauss
             float a = fmaxf(__fsub_rn(fabsf(f), mf), 0.f);
             if (!p.take_abs) a = f > 0.f ? a : (f < 0.f ? -a : __fmul_rn(a, 0.f));
             *o = a;
+        }
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// float32-accumulating variant (the default): same arithmetic, in the same order, as
+// fbk_gauss2d<.., float>, but register blocked -- a thread produces 8 consecutive outputs along the
+// filter direction from a sliding window (15 + 15 shared-memory loads per 8 taps x 8 outputs
+// instead of 2 per tap and output), on 64 x 64 tiles.  The tap list is padded to a multiple of 8
+// with zero weights: fmaf(x, 0, acc) == acc for finite x, and every padded read lands on
+// initialised (pixel or zeroed slack) shared memory.
+// ---------------------------------------------------------------------------------------------
+constexpr int kFT = 64, kFP = 8, kSlack = 8, kRowPitch = kFT + 1;
+
+struct GaussTapsF {
+    float wc;                          // centre weight
+    float wt[kMaxRadius + 8];          // wt[j] = weight at offset +-(radius - j), zero for j >= radius
+    int rpad;                          // radius rounded up to a multiple of 8
+};
+
+__host__ __device__ inline int gaussf_in_pitch(int r) { return (kFT + 2 * r + kFP) | 1; }
+
+template <typename TS, int MODE>
+__global__ void __launch_bounds__(kNT) fbk_gauss2d_f32(const __grid_constant__ GaussParams p, const __grid_constant__ GaussTapsF tf)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int r = p.taps.radius, rp = tf.rpad;
+    const int in_w = kFT + 2 * r, in_h = kFT + 2 * r, in_pitch = gaussf_in_pitch(r);
+    float* s_in_base = reinterpret_cast<float*>(smem_raw);                    // slack | [in_h][in_pitch] | slack
+    float* s_in = s_in_base + kSlack;
+    float* s_row_base = s_in + (size_t)in_h * in_pitch + kSlack;              // slack rows | [in_h][kRowPitch] | slack rows
+    float* s_row = s_row_base + kSlack * kRowPitch;
+    const int img = blockIdx.z, x0 = blockIdx.x * kFT, y0 = blockIdx.y * kFT, tid = threadIdx.x;
+    const TS* base = reinterpret_cast<const TS*>(p.src) + (size_t)img * p.src_stride;
+    float span = 0.f;
+    if (MODE == MODE_MASK) span = p.span ? (p.span[1] - p.span[0]) : p.span_value;
+    // input tile (+ zeroed pitch padding and slack)
+    {
+        const float inv_pitch = 1.0f / (float)in_pitch;
+        for (int i = tid; i < in_h * in_pitch; i += kNT) {
+            const int yy = (int)(((float)i + 0.5f) * inv_pitch), xx = i - yy * in_pitch;
+            s_in[i] = xx < in_w ? load_src<TS, MODE>(p, base, y0 + yy - r, x0 + xx - r, span) : 0.f;
+        }
+        for (int i = tid; i < kSlack; i += kNT) { s_in_base[i] = 0.f; s_in[(size_t)in_h * in_pitch + i] = 0.f; }
+        for (int i = tid; i < kSlack * kRowPitch; i += kNT) { s_row_base[i] = 0.f; s_row[(size_t)in_h * kRowPitch + i] = 0.f; }
+    }
+    __syncthreads();
+    // row pass: item = (row yy, strip of 8 outputs); consecutive threads take consecutive rows (odd pitch: no conflicts)
+    {
+        const float inv_h = 1.0f / (float)in_h;
+        for (int i = tid; i < in_h * (kFT / kFP); i += kNT) {
+            const int strip = (int)(((float)i + 0.5f) * inv_h), yy = i - strip * in_h;
+            const float* row = s_in + yy * in_pitch + strip * kFP;
+            float acc[kFP];
+#pragma unroll
+            for (int o = 0; o < kFP; ++o) acc[o] = row[r + o] * tf.wc;
+            for (int jb = 0; jb < rp; jb += 8) {
+                float a[15], b[15];
+                const float* pa = row + jb;
+                const float* pb = row + 2 * r - jb - 7;
+#pragma unroll
+                for (int k = 0; k < 15; ++k) { a[k] = pa[k]; b[k] = pb[k]; }
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                    const float wgt = tf.wt[jb + jj];
+#pragma unroll
+                    for (int o = 0; o < kFP; ++o) acc[o] = fmaf(a[jj + o] + b[7 - jj + o], wgt, acc[o]);
+                }
+            }
+            float* dst = s_row + yy * kRowPitch + strip * kFP;
+#pragma unroll
+            for (int o = 0; o < kFP; ++o) dst[o] = acc[o];
+        }
+    }
+    __syncthreads();
+    // column pass: item = (column xx, strip of 8 output rows); consecutive threads take consecutive columns
+    for (int i = tid; i < kFT * (kFT / kFP); i += kNT) {
+        const int ys = i / kFT, xx = i - ys * kFT;
+        const float* col = s_row + (ys * kFP) * kRowPitch + xx;
+        float acc[kFP];
+#pragma unroll
+        for (int o = 0; o < kFP; ++o) acc[o] = col[(r + o) * kRowPitch] * tf.wc;
+        for (int jb = 0; jb < rp; jb += 8) {
+            float a[15], b[15];
+            const float* pa = col + jb * kRowPitch;
+            const float* pb = col + (2 * r - jb - 7) * kRowPitch;
+#pragma unroll
+            for (int k = 0; k < 15; ++k) { a[k] = pa[k * kRowPitch]; b[k] = pb[k * kRowPitch]; }
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+                const float wgt = tf.wt[jb + jj];
+#pragma unroll
+                for (int o = 0; o < kFP; ++o) acc[o] = fmaf(a[jj + o] + b[7 - jj + o], wgt, acc[o]);
+            }
+        }
+        const int x = x0 + xx;
+        if (x >= p.w) continue;
+#pragma unroll
+        for (int o = 0; o < kFP; ++o) {
+            const int yy = ys * kFP + o, y = y0 + yy;
+            if (y >= p.h) break;
+            const float g = acc[o];
+            float* out = p.dst + ((size_t)img * p.h + y) * p.w + x;
+            if (MODE == MODE_BLUR) {
+                *out = g;
+            } else if (MODE == MODE_DOG) {
+                float f = __fsub_rn(s_in[(yy + r) * in_pitch + xx + r], g);     // img0f - img1f
+                *out = p.take_abs ? fabsf(f) : f;
+            } else {
+                const float mf = __fdiv_rn(__fmul_rn(g, p.sc2), p.s02);
+                const float f = *out;
+                float v = fmaxf(__fsub_rn(fabsf(f), mf), 0.f);
+                if (!p.take_abs) v = f > 0.f ? v : (f < 0.f ? -v : __fmul_rn(v, 0.f));
+                *out = v;
+            }
         }
     }
 }
@@ -292,6 +409,8 @@ int check_device(int device)
     return FB_OK;
 }
 
+bool g_gauss_legacy = false;      // FB_GAUSS_LEGACY=1: the unblocked float kernel (comparison runs)
+
 size_t gauss_smem(int r)
 {
     const int in_w = kTW + 2 * r, in_h = kTH + 2 * r;
@@ -310,10 +429,35 @@ int launch_gauss(const GaussParams& p, cudaStream_t st)
     return FB_OK;
 }
 
+size_t gaussf_smem(int r)
+{
+    const int in_h = kFT + 2 * r;
+    return ((size_t)in_h * gaussf_in_pitch(r) + 2 * kSlack + (size_t)(in_h + 2 * kSlack) * kRowPitch) * sizeof(float);
+}
+
+template <typename TS, int MODE>
+int launch_gauss_f32(const GaussParams& p, cudaStream_t st)
+{
+    GaussTapsF tf{};
+    const int r = p.taps.radius;
+    tf.wc = (float)p.taps.w[r];
+    tf.rpad = (r + 7) & ~7;
+    for (int j = 0; j < r; ++j) tf.wt[j] = (float)p.taps.w[j];
+    const size_t smem = gaussf_smem(r);
+    FB_CU(cudaFuncSetAttribute(fbk_gauss2d_f32<TS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((p.w + kFT - 1) / kFT, (p.h + kFT - 1) / kFT, p.n);
+    fbk_gauss2d_f32<TS, MODE><<<grid, kNT, smem, st>>>(p, tf);
+    fb_count_launches(1);
+    FB_CU(cudaGetLastError());
+    return FB_OK;
+}
+
 template <typename TS, int MODE>
 int launch_gauss_acc(const GaussParams& p, bool exact, cudaStream_t st)
 {
-    return exact ? launch_gauss<TS, MODE, double>(p, st) : launch_gauss<TS, MODE, float>(p, st);
+    if (exact) return launch_gauss<TS, MODE, double>(p, st);
+    if (g_gauss_legacy) return launch_gauss<TS, MODE, float>(p, st);
+    return launch_gauss_f32<TS, MODE>(p, st);
 }
 
 }  // namespace
@@ -329,6 +473,7 @@ extern "C" int fb_masked_dog(const void* img, const unsigned char* mask, int n, 
                              int device, void* stream)
 {
     if (n < 0 || h < 1 || w < 1) return fb_failf(FB_EINVAL, "bad shape n=%d %dx%d", n, h, w);
+    g_gauss_legacy = getenv("FB_GAUSS_LEGACY") != nullptr;
     if (in_dtype != FB_F32 && in_dtype != FB_U8) return fb_failf(FB_EINVAL, "masked_dog: dtype %d not supported (float32 / uint8)", in_dtype);
     if (mask && mask_n != 1 && mask_n != n) return fb_failf(FB_EINVAL, "mask_n must be 1 or n");
     if (n == 0) return FB_OK;
