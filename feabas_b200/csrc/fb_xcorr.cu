@@ -101,10 +101,13 @@ __global__ void __launch_bounds__(256) fbk_channel_mean(const cx<T>* __restrict_
 
 // ---- register-resident fast path (power-of-two grids, float32 compute) ----
 // fast-path line lengths: N = E * T (E points per lane, T lanes per line).  X(n, E, T)
-#define FB_FAST_SIZES(X) X(256, 16, 16) X(512, 32, 16) X(1024, 32, 32) X(2048, 64, 32) X(4096, 64, 64) X(576, 24, 24) X(288, 24, 12) X(300, 30, 10)
+#define FB_FAST_SIZES(X) X(256, 16, 16) X(512, 32, 16) X(1024, 32, 32) X(2048, 64, 32) X(4096, 64, 64) X(576, 24, 24) X(288, 24, 12) X(300, 30, 10) \
+    X(200, 20, 10) X(400, 40, 10) X(800, 40, 20) X(384, 48, 8) X(768, 48, 16) X(1152, 48, 24)
 constexpr int kNW1 = 8, kNW2 = 8;                    // warps per CTA of K1 / K2
 // K3: lines (= GT tile rows) per CTA for T lanes per line; CTA = T * R threads, 512 threads per SM
-template <int T> constexpr int kR3() { return T > 32 || T == 10 ? 4 : 8; }     // (300 = 4 * 75 rows: tiles of 4)
+// rows per GT tile = lines per K3 CTA: 8 when 8 divides the line length (square grids: the row count), else 4;
+// 4 for the two-warp lines of 4096 (shared memory)
+template <int E, int T> constexpr int kR3() { return T > 32 || (E * T) % 8 ? 4 : 8; }
 // CTAs per SM the register budget allows: a lane holds E complex points (E = 64: 128 data registers, one CTA)
 template <int E> constexpr int kOcc(int full) { return E > 32 ? 1 : full; }
 template <int E, int T, typename TI, bool PRUNED>
@@ -257,9 +260,9 @@ static int set_attrs(int device)
     RS((fbk_fast_rows_forward<E, T, unsigned char, false>)); \
     RS((fbk_fast_columns<E, T, true>));                      \
     RS((fbk_fast_columns<E, T, false>));                     \
-    RS((fbk_fast_rows_inverse<E, T, kR3<T>()>));             \
-    RS((fbk_fast_rows_inverse_tma<E, T, kR3<T>(), true>));   \
-    RS((fbk_fast_rows_inverse_tma<E, T, kR3<T>(), false>))
+    RS((fbk_fast_rows_inverse<E, T, kR3<E, T>()>));             \
+    RS((fbk_fast_rows_inverse_tma<E, T, kR3<E, T>(), true>));   \
+    RS((fbk_fast_rows_inverse_tma<E, T, kR3<E, T>(), false>))
 #define X(N_, E_, T_) RSF(E_, T_);
     FB_FAST_SIZES(X)
 #undef X
@@ -402,9 +405,9 @@ static void fast_et(int n, int& E, int& T)
     FB_FAST_SIZES(X)
 #undef X
 }
-static int fast_rblk(int T) { return T > 32 || T == 10 ? 4 : 8; }                         // == kR3<T>()
+static int fast_rblk(int n, int T) { return T > 32 || n % 8 ? 4 : 8; }                    // == kR3<E, T>()
 static int fast_lines(int T, int nw) { return T > 32 ? nw / (T / 32) : nw * (32 / T); }   // WarpFFT::lines_per_cta
-static int fast_rblk_of(int nx) { int E, T; fast_et(nx, E, T); return fast_rblk(T); }
+static int fast_rblk_of(int nx) { int E, T; fast_et(nx, E, T); return fast_rblk(nx, T); }
 static size_t fast_smem(int n, int nw)
 {
     int E, T; fast_et(n, E, T);
@@ -462,7 +465,7 @@ static int launch_fast(const Problem& q, StreamCtx& ctx, XcParams& p, int nb, cu
     fp.FT1 = reinterpret_cast<cx<float>*>(w + f0);
     fp.GT = reinterpret_cast<cx<float>*>(w + f0 + f1);
     p.part = reinterpret_cast<Partial*>(w + f0 + f1 + gg);
-    fp.rblk = fast_rblk(TX);                             // rows per K3 tile
+    fp.rblk = fast_rblk(q.nx, TX);                       // rows per K3 tile
     if (q.nx == 1024 && (g_opt_fast_flags & 32)) fp.rblk = 4;
     fp.flags = (int)(g_opt_fast_flags & ~(16 | 32));
     fp.use_tma = make_gt_map(&fp.gt_map, fp.GT, nb, q.ny, g.kp, fp.rblk) ? 1 : 0;
@@ -511,11 +514,11 @@ static int launch_fast(const Problem& q, StreamCtx& ctx, XcParams& p, int nb, cu
         const bool tma3 = R == fp.rblk && !(g_opt_fast_flags & 4096);      // TMA-fed variant (default)
         const bool mir = q.conf_mode == CONF_MIRROR;
         const size_t sm3t = sm3 + 16;                                         // + mbarrier
-#define K3T(E_, T_) do { if (mir) fbk_fast_rows_inverse_tma<E_, T_, kR3<T_>(), true><<<grid, nt, sm3t, st>>>(fp); \
-                         else fbk_fast_rows_inverse_tma<E_, T_, kR3<T_>(), false><<<grid, nt, sm3t, st>>>(fp); } while (0)
+#define K3T(E_, T_) do { if (mir) fbk_fast_rows_inverse_tma<E_, T_, kR3<E_, T_>(), true><<<grid, nt, sm3t, st>>>(fp); \
+                         else fbk_fast_rows_inverse_tma<E_, T_, kR3<E_, T_>(), false><<<grid, nt, sm3t, st>>>(fp); } while (0)
         if (R == 4 && q.nx == 1024 && fp.rblk == 8) fbk_fast_rows_inverse<32, 32, 4, 8><<<grid, nt, sm3, st>>>(fp);
         else if (R == 4 && q.nx == 1024) fbk_fast_rows_inverse<32, 32, 4><<<grid, nt, sm3, st>>>(fp);
-#define X(N_, E_, T_) else if (q.nx == N_) { if (tma3) K3T(E_, T_); else fbk_fast_rows_inverse<E_, T_, kR3<T_>()><<<grid, nt, sm3, st>>>(fp); }
+#define X(N_, E_, T_) else if (q.nx == N_) { if (tma3) K3T(E_, T_); else fbk_fast_rows_inverse<E_, T_, kR3<E_, T_>()><<<grid, nt, sm3, st>>>(fp); }
         FB_FAST_SIZES(X)
 #undef X
 #undef K3T

@@ -116,7 +116,7 @@ __device__ __forceinline__ void named_barrier(int id, int nthreads)
 
 template <int E, int T> struct WarpFFT {
     static_assert(T <= 32 || T == 64, "lanes per line");
-    static_assert(E % T == 0 && E / T <= 4 && E % 2 == 0, "E/T stage-B transforms per lane");
+    static_assert(E % T == 0 && E / T <= 8 && E % 2 == 0, "E/T stage-B transforms per lane");
     static constexpr int N = E * T;
     static constexpr int WPL = T > 32 ? T / 32 : 1;   // warps per line (T = 64: the line's lanes span two adjacent warps)
     static constexpr int LPW = T >= 32 ? 1 : 32 / T;  // lines per warp

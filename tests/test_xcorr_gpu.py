@@ -214,6 +214,15 @@ FAST_CASES = [
     (4, (150, 150), (150, 150), dict(subpixel=True)),                          # 300 x 300: thumbnail blocks
     (3, (300, 300), (300, 300), dict(subpixel=True, pad=False)),               # 300 x 300 unpruned
     (2, (141, 150), (141, 150), dict(subpixel=False)),                         # 288 x 300 (ragged rows)
+    # further 5-smooth lengths: 200 = 20 x 10, 400 = 40 x 10, 800 = 40 x 20, 384 = 48 x 8, 768 = 48 x 16, 1152 = 48 x 24
+    (3, (100, 100), (100, 100), dict(subpixel=True)),                          # 200 x 200
+    (2, (200, 200), (200, 200), dict(subpixel=True, conf_mode=1)),             # 400 x 400, STD
+    (2, (400, 400), (400, 400), dict(subpixel=True)),                          # 800 x 800
+    (2, (192, 192), (192, 192), dict(subpixel=True, conf_mode=0)),             # 384 x 384, NONE
+    (2, (384, 384), (384, 384), dict(subpixel=True)),                          # 768 x 768
+    (2, (576, 576), (576, 576), dict(subpixel=True)),                          # 1152 x 1152
+    (2, (100, 400), (100, 400), dict(subpixel=True)),                          # 200 x 800
+    (2, (400, 200), (400, 200), dict(subpixel=True, pad=False)),               # 400 x 200 unpruned
 ]
 
 
