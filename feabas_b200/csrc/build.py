@@ -13,9 +13,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, 'libfeabas_cuda.so')
 OBJ_DIR = os.path.join(HERE, 'build')
 HEADER = os.path.join('..', '..', 'include', 'feabas_cuda.h')
+FAST_DEPS = ['fb_fast_tu.inc', 'fb_fast_groups.h', 'fb_xcorr_fast.cuh', 'fb_xcorr.cuh', 'fb_regfft.cuh', 'fb_fft.cuh', 'fb_gfft.cuh', HEADER]
 # translation unit -> headers it includes
 UNITS = {
-    'fb_xcorr.cu': ['fb_xcorr.cuh', 'fb_xcorr_fast.cuh', 'fb_regfft.cuh', 'fb_fft.cuh', 'fb_gfft.cuh', 'fb_host_plan.h', 'fb_common.h', HEADER],
+    'fb_xcorr.cu': ['fb_xcorr.cuh', 'fb_xcorr_fast.cuh', 'fb_fast_groups.h', 'fb_regfft.cuh', 'fb_fft.cuh', 'fb_gfft.cuh', 'fb_host_plan.h', 'fb_common.h', HEADER],
+    # the register-resident fast path, one translation unit per group of line lengths (parallel build)
+    'fb_fast_pow2.cu': FAST_DEPS, 'fb_fast_big.cu': FAST_DEPS, 'fb_fast_r3.cu': FAST_DEPS, 'fb_fast_r5.cu': FAST_DEPS,
     'fb_image.cu': ['fb_common.h', HEADER],
 }
 SOURCES = list(UNITS)

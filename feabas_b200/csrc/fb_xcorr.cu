@@ -17,7 +17,7 @@
 #include "../../include/feabas_cuda.h"
 #include "fb_host_plan.h"
 #include "fb_xcorr.cuh"
-#include "fb_xcorr_fast.cuh"
+#include "fb_fast_groups.h"
 
 using namespace fb;
 
@@ -99,42 +99,7 @@ __global__ void __launch_bounds__(256) fbk_channel_mean(const cx<T>* __restrict_
     }
 }
 
-// ---- register-resident fast path (power-of-two grids, float32 compute) ----
-// fast-path line lengths: N = E * T (E points per lane, T lanes per line).  X(n, E, T)
-#define FB_FAST_SIZES(X) X(256, 16, 16) X(512, 32, 16) X(1024, 32, 32) X(2048, 64, 32) X(4096, 64, 64) X(576, 24, 24) X(288, 24, 12) X(300, 30, 10) \
-    X(200, 20, 10) X(400, 40, 10) X(800, 40, 20) X(384, 48, 8) X(768, 48, 16) X(1152, 48, 24)
-constexpr int kNW1 = 8, kNW2 = 8;                    // warps per CTA of K1 / K2
-// K3: lines (= GT tile rows) per CTA for T lanes per line; CTA = T * R threads, 512 threads per SM
-// rows per GT tile = lines per K3 CTA: 8 when 8 divides the line length (square grids: the row count), else 4;
-// 4 for the two-warp lines of 4096 (shared memory)
-template <int E, int T> constexpr int kR3() { return T > 32 || (E * T) % 8 ? 4 : 8; }
-// CTAs per SM the register budget allows: a lane holds E complex points (E = 64: 128 data registers, one CTA)
-template <int E> constexpr int kOcc(int full) { return E > 32 ? 1 : full; }
-template <int E, int T, typename TI, bool PRUNED>
-__global__ void __launch_bounds__(32 * kNW1, kOcc<E>(16 / kNW1)) fbk_fast_rows_forward(const __grid_constant__ FastParams fp)
-{
-    extern __shared__ __align__(16) unsigned char smem[];
-    kfast_rows_forward<E, T, kNW1, TI, PRUNED>(fp, smem);
-}
-template <int E, int T, bool PRUNED>
-__global__ void __launch_bounds__(32 * kNW2, kOcc<E>(16 / kNW2)) fbk_fast_columns(const __grid_constant__ FastParams fp)
-{
-    extern __shared__ __align__(128) unsigned char smem[];
-    kfast_columns<E, T, kNW2, PRUNED>(fp, smem);
-}
-template <int E, int T, int R, int RB = R>
-__global__ void __launch_bounds__(k3_threads(T, R), kOcc<E>(512 / k3_threads(T, R))) fbk_fast_rows_inverse(const __grid_constant__ FastParams fp)
-{
-    extern __shared__ __align__(16) unsigned char smem[];
-    kfast_rows_inverse<E, T, R, RB>(fp, smem);
-}
-
-template <int E, int T, int R, bool MIRROR>
-__global__ void __launch_bounds__(k3_threads(T, R), kOcc<E>(512 / k3_threads(T, R))) fbk_fast_rows_inverse_tma(const __grid_constant__ FastParams fp)
-{
-    extern __shared__ __align__(128) unsigned char smem[];
-    kfast_rows_inverse_tma<E, T, R, MIRROR>(fp, smem);
-}
+// ---- register-resident fast path: kernels live in fb_fast_<group>.cu (fb_fast_groups.h) ----
 
 // ---------------------------------------------------------------------------
 // caches
@@ -253,22 +218,8 @@ static int set_attrs(int device)
     RS((fbk_fused<float, unsigned char>));
     RS((fbk_fused<double, unsigned char>));
     RS((fbk_fused<double, double>));
-#define RSF(E, T)                                            \
-    RS((fbk_fast_rows_forward<E, T, float, true>));          \
-    RS((fbk_fast_rows_forward<E, T, float, false>));         \
-    RS((fbk_fast_rows_forward<E, T, unsigned char, true>));  \
-    RS((fbk_fast_rows_forward<E, T, unsigned char, false>)); \
-    RS((fbk_fast_columns<E, T, true>));                      \
-    RS((fbk_fast_columns<E, T, false>));                     \
-    RS((fbk_fast_rows_inverse<E, T, kR3<E, T>()>));             \
-    RS((fbk_fast_rows_inverse_tma<E, T, kR3<E, T>(), true>));   \
-    RS((fbk_fast_rows_inverse_tma<E, T, kR3<E, T>(), false>))
-#define X(N_, E_, T_) RSF(E_, T_);
-    FB_FAST_SIZES(X)
-#undef X
-    RS((fbk_fast_rows_inverse<32, 32, 4>));
-    RS((fbk_fast_rows_inverse<32, 32, 4, 8>));
-#undef RSF
+    if (fast_set_attrs_pow2(kMaxSmem) || fast_set_attrs_big(kMaxSmem) || fast_set_attrs_r3(kMaxSmem) || fast_set_attrs_r5(kMaxSmem))
+        return fail(FB_ECUDA, "cudaFuncSetAttribute failed for a fast-path kernel");
 #undef RS
     g_attr_done[device] = true;
     return FB_OK;
@@ -386,17 +337,13 @@ struct ProfScope {
 // ---------------------------------------------------------------------------
 // fast path launch
 // ---------------------------------------------------------------------------
-template <int E, int T, typename TI>
-static void launch_fast_k1(const FastParams& fp, bool pruned, int grid, size_t smem, cudaStream_t st)
+static bool fast_dispatch(int stage, const FastParams& fp, const FastLaunch& l)
 {
-    if (pruned) fbk_fast_rows_forward<E, T, TI, true><<<grid, 32 * kNW1, smem, st>>>(fp);
-    else fbk_fast_rows_forward<E, T, TI, false><<<grid, 32 * kNW1, smem, st>>>(fp);
-}
-template <int E, int T>
-static void launch_fast_k2(const FastParams& fp, bool pruned, int grid, size_t smem, cudaStream_t st)
-{
-    if (pruned) fbk_fast_columns<E, T, true><<<grid, 32 * kNW2, smem, st>>>(fp);
-    else fbk_fast_columns<E, T, false><<<grid, 32 * kNW2, smem, st>>>(fp);
+    switch (stage) {
+        case 1: return fast_k1_pow2(fp, l) || fast_k1_big(fp, l) || fast_k1_r3(fp, l) || fast_k1_r5(fp, l);
+        case 2: return fast_k2_pow2(fp, l) || fast_k2_big(fp, l) || fast_k2_r3(fp, l) || fast_k2_r5(fp, l);
+        default: return fast_k3_pow2(fp, l) || fast_k3_big(fp, l) || fast_k3_r3(fp, l) || fast_k3_r5(fp, l);
+    }
 }
 static void fast_et(int n, int& E, int& T)
 {
@@ -482,10 +429,8 @@ static int launch_fast(const Problem& q, StreamCtx& ctx, XcParams& p, int nb, cu
         const int grid = work < cap ? work : cap;
         const bool pruned = q.w0 <= q.nx / 2 && q.w1 <= q.nx / 2;
         ProfScope ps(ctx, st, SLOT_ROWS_FWD);
-        if (false) {}
-#define X(N_, E_, T_) else if (q.nx == N_) launch_fast_k1<E_, T_, TI>(fp, pruned, grid, fast_smem(N_, kNW1), st);
-        FB_FAST_SIZES(X)
-#undef X
+        FastLaunch l{q.nx, std::is_same<TI, float>::value ? FB_F32 : FB_U8, pruned, false, 0, grid, 32 * kNW1, fast_smem(q.nx, kNW1), st};
+        if (!fast_dispatch(1, fp, l)) return fail(FB_ESIZE, "no fast-path row kernel for %d points", q.nx);
     }
     // K2
     {
@@ -495,10 +440,8 @@ static int launch_fast(const Problem& q, StreamCtx& ctx, XcParams& p, int nb, cu
         const int grid = work < cap ? work : cap;
         const bool pruned = q.h0 <= q.ny / 2 && q.h1 <= q.ny / 2;     // (rows >= h of the row spectra are zero)
         ProfScope ps(ctx, st, SLOT_COLUMNS);
-        if (false) {}
-#define X(N_, E_, T_) else if (q.ny == N_) launch_fast_k2<E_, T_>(fp, pruned, grid, fast_smem(N_, kNW2), st);
-        FB_FAST_SIZES(X)
-#undef X
+        FastLaunch l{q.ny, 0, pruned, false, 0, grid, 32 * kNW2, fast_smem(q.ny, kNW2), st};
+        if (!fast_dispatch(2, fp, l)) return fail(FB_ESIZE, "no fast-path column kernel for %d points", q.ny);
     }
     // K3: TX * R threads own R lines (R <= rblk rows of a GT tile)
     {
@@ -514,14 +457,9 @@ static int launch_fast(const Problem& q, StreamCtx& ctx, XcParams& p, int nb, cu
         const bool tma3 = R == fp.rblk && !(g_opt_fast_flags & 4096);      // TMA-fed variant (default)
         const bool mir = q.conf_mode == CONF_MIRROR;
         const size_t sm3t = sm3 + 16;                                         // + mbarrier
-#define K3T(E_, T_) do { if (mir) fbk_fast_rows_inverse_tma<E_, T_, kR3<E_, T_>(), true><<<grid, nt, sm3t, st>>>(fp); \
-                         else fbk_fast_rows_inverse_tma<E_, T_, kR3<E_, T_>(), false><<<grid, nt, sm3t, st>>>(fp); } while (0)
-        if (R == 4 && q.nx == 1024 && fp.rblk == 8) fbk_fast_rows_inverse<32, 32, 4, 8><<<grid, nt, sm3, st>>>(fp);
-        else if (R == 4 && q.nx == 1024) fbk_fast_rows_inverse<32, 32, 4><<<grid, nt, sm3, st>>>(fp);
-#define X(N_, E_, T_) else if (q.nx == N_) { if (tma3) K3T(E_, T_); else fbk_fast_rows_inverse<E_, T_, kR3<E_, T_>()><<<grid, nt, sm3, st>>>(fp); }
-        FB_FAST_SIZES(X)
-#undef X
-#undef K3T
+        const int variant = (R == 4 && q.nx == 1024) ? (fp.rblk == 8 ? 3 : 2) : (tma3 ? 0 : 1);
+        FastLaunch l{q.nx, 0, false, mir, variant, grid, nt, variant == 0 ? sm3t : sm3, st};
+        if (!fast_dispatch(3, fp, l)) return fail(FB_ESIZE, "no fast-path inverse row kernel for %d points", q.nx);
     }
     {
         ProfScope ps(ctx, st, SLOT_FINALIZE);
