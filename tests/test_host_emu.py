@@ -83,3 +83,13 @@ def test_thread_count_independent(emu):
         got = emu(s0, s1, subpixel=True, nthr=nthr)
         for x, y in zip(ref[:3], got[:3]):
             np.testing.assert_array_equal(x, y)
+
+
+def test_register_fft_and_pass_planner(tmp_path):
+    """fb_gfft.cuh (compile-time mixed-radix register FFT: the fast path's per-lane transform for lengths with
+    factors 3 / 5 and the composite-radix butterfly of the fused kernel's passes) against a direct DFT, forward and
+    inverse, float and double; radix planner: products, radix bounds, digit-position tables are permutations."""
+    exe = tmp_path / 'gfft_check'
+    subprocess.run(['g++', '-std=c++17', '-O1', '-o', str(exe), os.path.join(EMU_DIR, 'gfft_check.cpp')], check=True)
+    res = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
