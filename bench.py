@@ -39,6 +39,9 @@ WORKLOADS = {
     # config 4 through bboxes_mesh_renderer_matcher (matcher.py:781-861): a uint8 section pair, a dense grid of
     # 512x512 blocks gathered + band-passed (sigma 3.5) + matched on the device; e2e uploads the two sections
     'align512_blocks': dict(kind='blocks', h=512, w=512, pad=True, section=8192, sigma=3.5, batch=256),
+    # config 1 (BASELINE.json configs[0]): stitching_matcher on every overlap of a 2x3 montage of 3000x4000 uint8 tiles,
+    # 10 % overlap, shipped stitching YAML kwargs; the unit counted is the block match (one xcorr of one block pair)
+    'stitch2x3': dict(kind='stitch', rows=2, cols=3, tile=(3000, 4000), overlap=0.1, margin=100, batch=0, h=74, w=67, pad=True),
 }
 
 
@@ -377,6 +380,196 @@ def bench_blocks(args, wl, rank, world, local, warmup):
         dist.destroy_process_group()
 
 
+
+# ----------------------------------------------------------------------------------------------
+# stitching workload: stitching_matcher over every overlap of a small montage (config 1)
+# ----------------------------------------------------------------------------------------------
+STITCH_KW = dict(spacings=None, conf_thresh=0.33, residue_mode='huber', residue_len=2, pad=True, sigma=2.5,
+                 coarse_downsample=0.5, fine_downsample=1.0, compute_photometric=False)   # default_stitching_configs.yaml:11-20
+
+
+def make_overlap_strips(wl, seed):
+    """Overlap strips (+ margin) of every pair of touching tiles, cut the way stitcher.py:556-568 does."""
+    import numpy as np
+    from feabas_b200 import synth
+    rows, cols, (th, tw), margin = wl['rows'], wl['cols'], wl['tile'], wl['margin']
+    tiles, nominal, _ = synth.tile_grid(rows, cols, tile_hw=(th, tw), overlap=wl['overlap'], jitter=10, seed=seed)
+    strips = []
+    for i in range(len(tiles)):
+        for j in range(i + 1, len(tiles)):
+            (x0, y0), (x1, y1) = nominal[i], nominal[j]
+            bx0, by0, bx1, by1 = max(x0, x1), max(y0, y1), min(x0, x1) + tw, min(y0, y1) + th
+            if bx1 - bx0 < 25 or by1 - by0 < 25:
+                continue
+            bx0, by0, bx1, by1 = bx0 - margin, by0 - margin, bx1 + margin, by1 + margin
+            def cut(t, ox, oy):
+                xa, ya, xb, yb = max(bx0 - ox, 0), max(by0 - oy, 0), min(bx1 - ox, tw), min(by1 - oy, th)
+                return np.ascontiguousarray(t[ya:yb, xa:xb])
+            strips.append((cut(tiles[i], x0, y0), cut(tiles[j], x1, y1)))
+    return strips
+
+
+def _cpu_stitch_init(seed, wl):
+    os.environ['OMP_NUM_THREADS'] = '1'
+    _W['strips'] = make_overlap_strips(wl, seed)
+    from oracle import matcher_oracle as mo
+    _W['f'] = mo.stitching_oracle
+
+
+def _cpu_stitch_task(k):
+    a, b = _W['strips'][k % len(_W['strips'])]
+    kw = {k_: v for k_, v in STITCH_KW.items() if k_ not in ('compute_photometric',)}
+    trace = []
+    out = _W['f'](a, b, trace=trace, **kw)
+    blocks = sum(t.get('nblocks', 0) + (1 if 'coarse' in t else 0) for t in trace)
+    return 0 if out[0] is None else len(out[0]), blocks
+
+
+def bench_stitch(args, wl, rank, world, local, warmup):
+    import numpy as np
+    config = {'workload': f"{args.workload}: stitching_matcher on every overlap of a {wl['rows']}x{wl['cols']} montage of "
+                          f"{wl['tile'][0]}x{wl['tile'][1]} uint8 tiles, {int(100 * wl['overlap'])} % overlap, margin {wl['margin']}, "
+                          'shipped YAML kwargs (sigma 2.5, coarse 0.5, pad, conf_thresh 0.33); unit = block match (one xcorr of one block pair)',
+              'l2': 'working set per overlap far below L2: latency bound, not HBM bound'}
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        import psutil
+        from concurrent.futures import ProcessPoolExecutor
+        import multiprocessing as mp
+        cores = psutil.cpu_count(logical=False) or os.cpu_count() or 1
+        pool = ProcessPoolExecutor(cores, mp_context=mp.get_context('spawn'), initializer=_cpu_stitch_init, initargs=(1, wl))
+        n_ov = len(make_overlap_strips(dict(wl, tile=(300, 400), margin=10), 1))     # overlap count only
+        list(pool.map(_cpu_stitch_task, range(cores)))
+        steps = max(1, min(args.steps, 3))
+        t0 = time.perf_counter()
+        res = []
+        for _ in range(steps):
+            res += list(pool.map(_cpu_stitch_task, range(n_ov)))
+        secs = time.perf_counter() - t0
+        pool.shutdown()
+        blocks = sum(r[1] for r in res) or sum(r[0] for r in res)
+        val = blocks / secs
+        sample = f'{steps} passes over the {n_ov} overlaps, one overlap per task on {cores} single-thread workers (oracle port of stitching_matcher)'
+        print(json.dumps({
+            'impl': 'reference', 'metric': 'xcorr_block_matches_per_sec', 'value': val, 'unit': 'matches/s', 'n_gpus': args.gpus,
+            'steps': steps, 'warmup': 1, 'ms_per_step': 1e3 * secs / steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': dict(config, overlaps_per_s=n_ov * steps / secs),
+            'cpu_baseline': {'value': val, 'unit': 'matches/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': val, 'unit': 'matches/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+        return
+
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    import feabas_b200.cuda as fc
+    L = fc._lib
+    strips = make_overlap_strips(wl, 1 + rank)
+    config['overlaps_per_step_per_gpu'] = len(strips)
+    dstrips = [(torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)) for a, b in strips]
+    hstrips = [(torch.from_numpy(a).pin_memory().numpy(), torch.from_numpy(b).pin_memory().numpy()) for a, b in strips]
+    stream = torch.cuda.current_stream().cuda_stream
+    lib = L.lib()
+
+    def run(pairs):
+        n = 0
+        x0 = lib.fb_pair_count() if hasattr(lib, 'fb_pair_count') else 0
+        for a, b in pairs:
+            out = fc.stitching_matcher(a, b, device=local, **STITCH_KW)
+            n += 0 if out[0] is None else len(out[0])
+        return n, (lib.fb_pair_count() - x0 if hasattr(lib, 'fb_pair_count') else 0)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        pts, pairs = run(dstrips)
+    assert pts > 0, 'no overlap produced matches'
+    config['match_points_per_step'] = pts
+    units = pairs or pts
+    L.profile_read(local, stream, reset=True) if L.launch_count() else None
+    L.set_option('profile', 1)
+    mon, mon_path = clocks_monitor_start(local) if rank == 0 else (None, None)
+    launches0 = L.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        run(dstrips)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = L.launch_count() - launches0
+    clocks = clocks_monitor_stop(mon, mon_path) if rank == 0 else None
+    L.set_option('profile', 0)
+    prof = L.profile_read(local, stream, reset=True)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * units * args.steps / (ms * 1e-3)
+    e_steps = max(2, min(args.steps, 5))
+    run(hstrips)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e_steps):
+        run(hstrips)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    e2e = {'value': world * units * e_steps / dt, 'unit': 'matches/s', 'h2d_bytes_per_step': int(sum(a.nbytes + b.nbytes for a, b in hstrips)),
+           'd2h_bytes_per_step': int(5 * 8 * units), 'steps': e_steps, 'overlaps_per_s': world * len(strips) * e_steps / dt,
+           'api': 'feabas_b200.cuda.stitching_matcher(uint8 host strips, shipped YAML kwargs), one call per overlap'}
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_kind = peaks()
+    kern = {k: {'ms_total': v[0], 'launches': v[1], 'ms_per_launch': (v[0] / v[1] if v[1] else None)} for k, v in prof.items() if v[1]}
+    dom = max(kern, key=lambda k: kern[k]['ms_total'])
+    xcorr_ms = sum(v['ms_total'] for v in kern.values())
+    b_min = 2 * wl['h'] * wl['w'] * 4 + 20
+    roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': units * args.steps * b_min / (kern[dom]['ms_total'] * 1e-3) / 1e9, 'peak': peak,
+                'unit': 'GB/s', 'frac': units * args.steps * b_min / (kern[dom]['ms_total'] * 1e-3) / 1e9 / peak, 'traffic': None, 'peak_kind': peak_kind,
+                'note': 'latency bound: one stitching_matcher call per overlap, batches of 5-270 small blocks; B_min of the finest-level block '
+                        'used as algorithmic bytes; xcorr kernels are %.0f %% of the step, the rest is host control flow + image kernels' % (100 * xcorr_ms / ms),
+                'kernel_share_of_step': kern[dom]['ms_total'] / ms if world == 1 else None, 'kernels': kern}
+    cpu = None
+    if not args.no_cpu_baseline:
+        import psutil
+        from concurrent.futures import ProcessPoolExecutor
+        import multiprocessing as mp
+        cores = psutil.cpu_count(logical=False) or os.cpu_count() or 1
+        pool = ProcessPoolExecutor(cores, mp_context=mp.get_context('spawn'), initializer=_cpu_stitch_init, initargs=(1, wl))
+        list(pool.map(_cpu_stitch_task, range(cores)))
+        t0 = time.perf_counter()
+        res = list(pool.map(_cpu_stitch_task, range(len(strips))))
+        s_ = time.perf_counter() - t0
+        pool.shutdown()
+        blocks = sum(r[1] for r in res) or sum(r[0] for r in res)
+        cpu = {'value': blocks / s_, 'unit': 'matches/s', 'cores': cores, 'kind': 'port', 'overlaps_per_s': len(strips) / s_,
+               'sample': f'one pass over the {len(strips)} overlaps, one overlap per task on {cores} single-thread workers '
+                         f'(oracle port of stitching_matcher), {s_:.1f} s wall'}
+    line = {'metric': 'xcorr_block_matches_per_sec', 'value': value, 'unit': 'matches/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic', 'config': dict(config, overlaps_per_s=world * len(strips) * args.steps / (ms * 1e-3),
+                                                                   unit_count='xcorr pairs (fb_pair_count)' if pairs else 'returned match points'),
+            'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ----------------------------------------------------------------------------------------------
 def clocks_monitor_start(gpu_index):
     path = tempfile.mktemp(prefix='fb_clocks_', suffix='.csv')
@@ -480,6 +673,8 @@ def main():
     warmup = max(args.warmup, 3)
     if wl.get('kind') == 'blocks':
         return bench_blocks(args, wl, rank, world, local, warmup)
+    if wl.get('kind') == 'stitch':
+        return bench_stitch(args, wl, rank, world, local, warmup)
     h, w, pad, batch = wl['h'], wl['w'], wl['pad'], wl['batch']
 
     from oracle import xcorr_oracle as xo           # bench may execute oracle/ only for the CPU legs

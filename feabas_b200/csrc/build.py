@@ -23,7 +23,7 @@ UNITS = {
 }
 SOURCES = list(UNITS)
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
-              '-Xcompiler', '-fPIC', '-diag-suppress', '68']
+              '-Xcompiler', '-fPIC', '-diag-suppress', '68'] + os.environ.get('FEABAS_NVCC_FLAGS', '').split()
 
 
 def _nvcc():

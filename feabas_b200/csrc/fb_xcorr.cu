@@ -26,6 +26,7 @@ using namespace fb;
 // ---------------------------------------------------------------------------
 static thread_local std::string g_err;
 static std::atomic<long long> g_launches{0};
+static std::atomic<long long> g_pairs{0};          // block pairs handed to the xcorr kernels (all entry points)
 
 static int fail(int code, const char* fmt, ...)
 {
@@ -530,6 +531,7 @@ static int launch_chunk(const Problem& q, StreamCtx& ctx, const void* img0, cons
 static int launch_chunk_any(const Problem& q, StreamCtx& ctx, const void* img0, const void* img1, int nb,
                             double* dx, double* dy, double* conf, double* peak, double* mir, cudaStream_t st)
 {
+    g_pairs += nb;
     if (q.in_dtype == FB_F32) return launch_chunk<float, float>(q, ctx, img0, img1, nb, dx, dy, conf, peak, mir, st);
     if (q.in_dtype == FB_U8) {
         if (q.f64) return launch_chunk<double, unsigned char>(q, ctx, img0, img1, nb, dx, dy, conf, peak, mir, st);
@@ -790,6 +792,7 @@ extern "C" int fb_profile_read(int device, void* stream, double* ms5, long long*
 }
 
 extern "C" long long fb_launch_count(void) { return g_launches.load(); }
+extern "C" long long fb_pair_count(void) { return g_pairs.load(); }
 
 extern "C" int fb_release(int device)
 {

@@ -82,13 +82,17 @@ template <int E, int T> struct SmemTw {
 };
 
 constexpr bool kLaneTwiddles = false;     // true: LaneTw (registers), false: SmemTw (shared-memory table)
-template <int E, int T> struct StageTw {
+#ifndef FB_LANE_TW_K2
+#define FB_LANE_TW_K2 0
+#endif
+// LANE: this kernel keeps the stage twiddles of a lane in registers (needs E % 8 == 0)
+template <int E, int T, bool LANE = kLaneTwiddles> struct StageTw {
     LaneTw<E> lane;
     SmemTw<E, T> sm;
     // table: global [E/2][T][2]; smem_table: room for E * T entries (unused with lane twiddles)
     __device__ __forceinline__ void init(const cx<float>* table, cx<float>* smem_table, int t, int tid, int nthr)
     {
-        if constexpr (kLaneTwiddles) {
+        if constexpr (LANE) {
             lane.template load<T>(table, t);
         } else {
             for (int i = tid; i < E * T; i += nthr) smem_table[i] = table[i];
@@ -98,7 +102,7 @@ template <int E, int T> struct StageTw {
     }
     template <typename F> __device__ __forceinline__ void apply_all(const cx<float>* v, F out) const
     {
-        if constexpr (kLaneTwiddles) {
+        if constexpr (LANE) {
 #pragma unroll
             for (int k1 = 0; k1 < E; ++k1) out(k1, lane.apply(v[gpos<E>(k1)], k1));
         } else {
@@ -154,8 +158,8 @@ template <int E, int T> struct WarpFFT {
     // Forward transform only: inverse transforms are taken as conj(fft(conj(.))) with the
     // conjugations folded into the neighbouring point-wise steps, so that every kernel
     // runs ONE butterfly body (instruction-cache footprint).
-    template <bool PRUNED>
-    static __device__ __forceinline__ void run(cx<float>* v, cx<float>* region, const StageTw<E, T>& tw, int t,
+    template <bool PRUNED, class TW>
+    static __device__ __forceinline__ void run(cx<float>* v, cx<float>* region, const TW& tw, int t,
                                                bool pruned_now = true, int bar = 1)
     {
         // first radix-2 level: skipped arithmetic when the upper half of the input is zero; the
@@ -363,7 +367,7 @@ __device__ void kfast_columns(const FastParams& fp, unsigned char* smem)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int t = W::lane_in_line(warp, lane), lw = W::line_in_warp(lane);
     const bool leader = t == 0 && !W::is_shadow(lane);     // one thread per line
-    StageTw<E, T> tw;
+    StageTw<E, T, (FB_LANE_TW_K2 != 0) && E % 8 == 0 && E <= 32> tw;
     tw.init(fp.twy, regions + W::lines_per_cta(NW) * RS, t, tid, NT);
     // partners are ADJACENT warps (2 pw, 2 pw + 1): they sit on different SM sub-partitions, so the
     // four warps an SMSP schedules belong to four different pairs and drift through the

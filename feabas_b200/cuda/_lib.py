@@ -47,6 +47,7 @@ SYMBOLS = {
     'fb_set_option': (_i, [ctypes.c_char_p, _ll]),
     'fb_profile_read': (_i, [_i, _vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_ll), _i]),
     'fb_launch_count': (_ll, []),
+    'fb_pair_count': (_ll, []),
     'fb_release': (_i, [_i]),
     'fb_device_count': (_i, []),
     'fb_last_error': (ctypes.c_char_p, []),

@@ -183,6 +183,9 @@ int fb_profile_read(int device, void* stream, double* ms5, long long* launches5,
 
 /* Number of kernels this library has launched in this process.              */
 long long fb_launch_count(void);
+/* Block pairs handed to the xcorr kernels since the library was loaded (every fb_xcorr_* entry point): the unit
+ * bench.py counts for workloads that call the matcher layers (stitching_matcher, ...). */
+long long fb_pair_count(void);
 
 /* Free cached tables / workspaces of `device` (-1: all).                     */
 int fb_release(int device);
