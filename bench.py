@@ -42,6 +42,9 @@ WORKLOADS = {
     # config 1 (BASELINE.json configs[0]): stitching_matcher on every overlap of a 2x3 montage of 3000x4000 uint8 tiles,
     # 10 % overlap, shipped stitching YAML kwargs; the unit counted is the block match (one xcorr of one block pair)
     'stitch2x3': dict(kind='stitch', rows=2, cols=3, tile=(3000, 4000), overlap=0.1, margin=100, batch=0, h=74, w=67, pad=True),
+    # config 3: section_matcher (coarse-to-fine block matching, spacings [150, 50]) on pairs of band-passed 2048^2 thumbnails,
+    # kwargs of default_thumbnail_configs.yaml:43-53 as thumbnail.py:509 passes them (sigma applied upstream -> 0 here)
+    'thumb_sections': dict(kind='sections', pairs=8, size=2048, batch=0, h=50, w=50, pad=True),
 }
 
 
@@ -409,28 +412,66 @@ def make_overlap_strips(wl, seed):
     return strips
 
 
+SECTION_KW = dict(sigma=0.0, spacings=[150, 50], conf_thresh=0.35, pad=True, distributor='cartesian_bbox',
+                  residue_mode='huber', residue_len=3, batch_size=300)                 # default_thumbnail_configs.yaml:43-53, thumbnail.py:509
+
+
+def make_section_thumbs(wl, seed):
+    """Pairs of float32 band-passed thumbnails (size x size) of neighbouring sections: one canvas, a small offset."""
+    import numpy as np
+    from feabas_b200 import synth
+    size, out = wl['size'], []
+    rng = np.random.default_rng(seed)
+    for k in range(wl['pairs']):
+        canvas = synth.dog_f32(synth.em_canvas(size + 40, size + 40, seed=seed * 100 + k), 3.5)
+        dx, dy = rng.integers(-9, 10, 2)
+        a = np.ascontiguousarray(canvas[20:20 + size, 20:20 + size])
+        b = np.ascontiguousarray(canvas[20 + dy:20 + dy + size, 20 + dx:20 + dx + size])
+        out.append((a, b + 0.05 * rng.standard_normal(b.shape).astype(np.float32)))
+    return out
+
+
+def make_jobs(wl, seed):
+    return make_overlap_strips(wl, seed) if wl['kind'] == 'stitch' else make_section_thumbs(wl, seed)
+
+
 def _cpu_stitch_init(seed, wl):
     os.environ['OMP_NUM_THREADS'] = '1'
-    _W['strips'] = make_overlap_strips(wl, seed)
+    _W['strips'] = make_jobs(wl, seed)
+    _W['kind'] = wl['kind']
     from oracle import matcher_oracle as mo
     _W['f'] = mo.stitching_oracle
+    _W['mo'] = mo
 
 
 def _cpu_stitch_task(k):
     a, b = _W['strips'][k % len(_W['strips'])]
-    kw = {k_: v for k_, v in STITCH_KW.items() if k_ not in ('compute_photometric',)}
     trace = []
-    out = _W['f'](a, b, trace=trace, **kw)
+    if _W['kind'] == 'stitch':
+        kw = {k_: v for k_, v in STITCH_KW.items() if k_ not in ('compute_photometric',)}
+        out = _W['f'](a, b, trace=trace, **kw)
+    else:
+        mo = _W['mo']
+        sec0 = mo._Section((0, 0, a.shape[1], a.shape[0]), locked=True)
+        sec1 = mo._Section((0, 0, b.shape[1], b.shape[0]))
+        out = mo.surrogate_loop_oracle(sec0, sec1, a, b, SECTION_KW['spacings'], conf_thresh=SECTION_KW['conf_thresh'],
+                                       residue_mode='huber', residue_len=SECTION_KW['residue_len'], pad=True, batch_size=SECTION_KW['batch_size'],
+                                       trace=trace)
     blocks = sum(t.get('nblocks', 0) + (1 if 'coarse' in t else 0) for t in trace)
     return 0 if out[0] is None else len(out[0]), blocks
 
 
 def bench_stitch(args, wl, rank, world, local, warmup):
     import numpy as np
-    config = {'workload': f"{args.workload}: stitching_matcher on every overlap of a {wl['rows']}x{wl['cols']} montage of "
-                          f"{wl['tile'][0]}x{wl['tile'][1]} uint8 tiles, {int(100 * wl['overlap'])} % overlap, margin {wl['margin']}, "
-                          'shipped YAML kwargs (sigma 2.5, coarse 0.5, pad, conf_thresh 0.33); unit = block match (one xcorr of one block pair)',
-              'l2': 'working set per overlap far below L2: latency bound, not HBM bound'}
+    stitch = wl['kind'] == 'stitch'
+    if stitch:
+        desc = (f"stitching_matcher on every overlap of a {wl['rows']}x{wl['cols']} montage of {wl['tile'][0]}x{wl['tile'][1]} uint8 tiles, "
+                f"{int(100 * wl['overlap'])} % overlap, margin {wl['margin']}, shipped YAML kwargs (sigma 2.5, coarse 0.5, pad, conf_thresh 0.33)")
+    else:
+        desc = (f"section_matcher on {wl['pairs']} pairs of {wl['size']}x{wl['size']} float32 band-passed thumbnails, spacings [150, 50], pad, "
+                'conf_thresh 0.35, huber residue 3 (affine surrogate mesh)')
+    config = {'workload': f'{args.workload}: {desc}; unit = block match (one xcorr of one block pair)',
+              'l2': 'working set per call far below L2: latency bound, not HBM bound'}
     if args.impl == 'reference':
         if rank != 0:
             return
@@ -439,18 +480,21 @@ def bench_stitch(args, wl, rank, world, local, warmup):
         import multiprocessing as mp
         cores = psutil.cpu_count(logical=False) or os.cpu_count() or 1
         pool = ProcessPoolExecutor(cores, mp_context=mp.get_context('spawn'), initializer=_cpu_stitch_init, initargs=(1, wl))
-        n_ov = len(make_overlap_strips(dict(wl, tile=(300, 400), margin=10), 1))     # overlap count only
+        n_ov = len(make_overlap_strips(dict(wl, tile=(300, 400), margin=10), 1)) if stitch else wl['pairs']     # job count only
         list(pool.map(_cpu_stitch_task, range(cores)))
         steps = max(1, min(args.steps, 3))
         t0 = time.perf_counter()
         res = []
+        n_tasks = max(n_ov, cores)                             # every worker busy: the job list is cycled
         for _ in range(steps):
-            res += list(pool.map(_cpu_stitch_task, range(n_ov)))
+            res += list(pool.map(_cpu_stitch_task, range(n_tasks)))
         secs = time.perf_counter() - t0
         pool.shutdown()
         blocks = sum(r[1] for r in res) or sum(r[0] for r in res)
         val = blocks / secs
-        sample = f'{steps} passes over the {n_ov} overlaps, one overlap per task on {cores} single-thread workers (oracle port of stitching_matcher)'
+        sample = (f'{steps} passes over {n_tasks} jobs (the {n_ov} of one step, cycled), one job per task on {cores} single-thread workers '
+                  f"(oracle port of {'stitching_matcher' if stitch else 'the section_matcher loop'})")
+        n_ov = n_tasks
         print(json.dumps({
             'impl': 'reference', 'metric': 'xcorr_block_matches_per_sec', 'value': val, 'unit': 'matches/s', 'n_gpus': args.gpus,
             'steps': steps, 'warmup': 1, 'ms_per_step': 1e3 * secs / steps, 'higher_is_better': True, 'scaling': 'weak',
@@ -468,8 +512,8 @@ def bench_stitch(args, wl, rank, world, local, warmup):
         dist.init_process_group('nccl', device_id=dev)
     import feabas_b200.cuda as fc
     L = fc._lib
-    strips = make_overlap_strips(wl, 1 + rank)
-    config['overlaps_per_step_per_gpu'] = len(strips)
+    strips = make_jobs(wl, 1 + rank)
+    config['overlaps_per_step_per_gpu' if stitch else 'section_pairs_per_step_per_gpu'] = len(strips)
     dstrips = [(torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)) for a, b in strips]
     hstrips = [(torch.from_numpy(a).pin_memory().numpy(), torch.from_numpy(b).pin_memory().numpy()) for a, b in strips]
     stream = torch.cuda.current_stream().cuda_stream
@@ -479,7 +523,12 @@ def bench_stitch(args, wl, rank, world, local, warmup):
         n = 0
         x0 = lib.fb_pair_count() if hasattr(lib, 'fb_pair_count') else 0
         for a, b in pairs:
-            out = fc.stitching_matcher(a, b, device=local, **STITCH_KW)
+            if stitch:
+                out = fc.stitching_matcher(a, b, device=local, **STITCH_KW)
+            else:
+                hh, ww = a.shape
+                out = fc.section_matcher(fc.AffineMesh((0, 0, ww, hh), uid=0), fc.AffineMesh((0, 0, ww, hh), uid=1),
+                                         fc.ArrayLoader(a, device=local), fc.ArrayLoader(b, device=local), **SECTION_KW)
             n += 0 if out[0] is None else len(out[0])
         return n, (lib.fb_pair_count() - x0 if hasattr(lib, 'fb_pair_count') else 0)
 
@@ -529,7 +578,8 @@ def bench_stitch(args, wl, rank, world, local, warmup):
         dt = float(t.item())
     e2e = {'value': world * units * e_steps / dt, 'unit': 'matches/s', 'h2d_bytes_per_step': int(sum(a.nbytes + b.nbytes for a, b in hstrips)),
            'd2h_bytes_per_step': int(5 * 8 * units), 'steps': e_steps, 'overlaps_per_s': world * len(strips) * e_steps / dt,
-           'api': 'feabas_b200.cuda.stitching_matcher(uint8 host strips, shipped YAML kwargs), one call per overlap'}
+           'api': 'feabas_b200.cuda.stitching_matcher(uint8 host strips, shipped YAML kwargs), one call per overlap' if stitch else
+                  'feabas_b200.cuda.section_matcher(AffineMesh, AffineMesh, ArrayLoader(host float32 thumbnail) x 2, ...), one call per section pair'}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -541,7 +591,7 @@ def bench_stitch(args, wl, rank, world, local, warmup):
     b_min = 2 * wl['h'] * wl['w'] * 4 + 20
     roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': units * args.steps * b_min / (kern[dom]['ms_total'] * 1e-3) / 1e9, 'peak': peak,
                 'unit': 'GB/s', 'frac': units * args.steps * b_min / (kern[dom]['ms_total'] * 1e-3) / 1e9 / peak, 'traffic': None, 'peak_kind': peak_kind,
-                'note': 'latency bound: one stitching_matcher call per overlap, batches of 5-270 small blocks; B_min of the finest-level block '
+                'note': 'latency bound: one matcher call per overlap / section pair, batches of 5-300 small blocks; B_min of the finest-level block '
                         'used as algorithmic bytes; xcorr kernels are %.0f %% of the step, the rest is host control flow + image kernels' % (100 * xcorr_ms / ms),
                 'kernel_share_of_step': kern[dom]['ms_total'] / ms if world == 1 else None, 'kernels': kern}
     cpu = None
@@ -553,13 +603,14 @@ def bench_stitch(args, wl, rank, world, local, warmup):
         pool = ProcessPoolExecutor(cores, mp_context=mp.get_context('spawn'), initializer=_cpu_stitch_init, initargs=(1, wl))
         list(pool.map(_cpu_stitch_task, range(cores)))
         t0 = time.perf_counter()
-        res = list(pool.map(_cpu_stitch_task, range(len(strips))))
+        n_tasks = max(len(strips), cores)                      # every worker busy: the job list is cycled
+        res = list(pool.map(_cpu_stitch_task, range(n_tasks)))
         s_ = time.perf_counter() - t0
         pool.shutdown()
         blocks = sum(r[1] for r in res) or sum(r[0] for r in res)
-        cpu = {'value': blocks / s_, 'unit': 'matches/s', 'cores': cores, 'kind': 'port', 'overlaps_per_s': len(strips) / s_,
-               'sample': f'one pass over the {len(strips)} overlaps, one overlap per task on {cores} single-thread workers '
-                         f'(oracle port of stitching_matcher), {s_:.1f} s wall'}
+        cpu = {'value': blocks / s_, 'unit': 'matches/s', 'cores': cores, 'kind': 'port', 'overlaps_per_s': n_tasks / s_,
+               'sample': f'{n_tasks} jobs (the {len(strips)} of one step, cycled), one job per task on {cores} single-thread workers '
+                         f"(oracle port of {'stitching_matcher' if stitch else 'the section_matcher loop'}), {s_:.1f} s wall"}
     line = {'metric': 'xcorr_block_matches_per_sec', 'value': value, 'unit': 'matches/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic', 'config': dict(config, overlaps_per_s=world * len(strips) * args.steps / (ms * 1e-3),
@@ -673,7 +724,7 @@ def main():
     warmup = max(args.warmup, 3)
     if wl.get('kind') == 'blocks':
         return bench_blocks(args, wl, rank, world, local, warmup)
-    if wl.get('kind') == 'stitch':
+    if wl.get('kind') in ('stitch', 'sections'):
         return bench_stitch(args, wl, rank, world, local, warmup)
     h, w, pad, batch = wl['h'], wl['w'], wl['pad'], wl['batch']
 
