@@ -48,6 +48,17 @@ def to_device(x, device=None, dtype=None):
     return t.contiguous()
 
 
+_UPLOAD_STREAMS = {}
+
+
+def upload_stream(dev):
+    """One side stream per device for host -> device copies of whole images (ArrayLoader)."""
+    key = dev.index
+    if key not in _UPLOAD_STREAMS:
+        _UPLOAD_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _UPLOAD_STREAMS[key]
+
+
 def _code(t):
     if t.dtype == torch.float32:
         return _lib.FB_F32

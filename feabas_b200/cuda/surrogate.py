@@ -28,25 +28,49 @@ class ArrayLoader:
 
     def __init__(self, img, fillval=0, resolution=DEFAULT_RESOLUTION, x0=0, y0=0, device=None):
         from . import image as _img
-        self.tensor = _img.to_device(img, device)
-        if self.tensor.dim() != 2:
+        self._ready = None
+        src = img if (torch is not None and isinstance(img, torch.Tensor)) else None
+        if src is None and torch is not None and isinstance(img, np.ndarray) and img.flags.c_contiguous and torch.cuda.is_available():
+            src = torch.from_numpy(img)
+        if src is not None and not src.is_cuda and src.dim() == 2 and torch.cuda.is_available() and src.is_pinned():
+            # page-locked host image: upload on a side stream, so that the copy of the NEXT section overlaps the
+            # block extraction / band-pass of this one; consumers wait on the event at first use of .tensor
+            dev = torch.device('cuda', torch.cuda.current_device() if device is None else int(device))
+            up = _img.upload_stream(dev)
+            with torch.cuda.stream(up):
+                self._tensor = src.to(dev, non_blocking=True)
+            self._ready = torch.cuda.Event()
+            self._ready.record(up)
+        else:
+            self._tensor = _img.to_device(img, device)
+        if self._tensor.dim() != 2:
             raise ValueError('ArrayLoader holds a single-channel 2-D image')
         self.default_fillval = fillval
         self.resolution = resolution
         self.x0, self.y0 = x0, y0
 
     @property
+    def tensor(self):
+        """The image on the GPU (the current stream is made to wait for a pending upload)."""
+        if self._ready is not None:
+            cur = torch.cuda.current_stream(self._tensor.device)
+            cur.wait_event(self._ready)
+            self._tensor.record_stream(cur)
+            self._ready = None
+        return self._tensor
+
+    @property
     def dtype(self):
-        return np.dtype(str(self.tensor.dtype).replace('torch.', ''))
+        return np.dtype(str(self._tensor.dtype).replace('torch.', ''))
 
     @property
     def bounds(self):
-        h, w = self.tensor.shape
+        h, w = self._tensor.shape
         return (self.x0, self.y0, self.x0 + w, self.y0 + h)
 
     def cover_rect(self):
         """Source-pixel rectangle a mesh built on ``bounds`` covers."""
-        h, w = self.tensor.shape
+        h, w = self._tensor.shape
         return (0.0, 0.0, float(w), float(h))
 
     def crop(self, bbox, return_empty=False, **kwargs):
