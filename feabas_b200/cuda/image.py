@@ -198,6 +198,8 @@ def crop_blocks_masked(img, blocks, block_shape, origin=None, fillval=0, cover=N
     if out is None:
         out = torch.empty((n, bh, bw), dtype=img.dtype, device=img.device)
     mask, cptr, mptr = None, None, None
+    if cover is not None and blk_host is not None and n and _blocks_inside(blk_host, bh, bw, cover):
+        cover = None            # every pixel of every block is covered: same stack, no mask to write / reduce / read back
     if cover is not None:
         import ctypes
         carr = (ctypes.c_double * 4)(*[float(v) for v in cover])
@@ -210,6 +212,19 @@ def crop_blocks_masked(img, blocks, block_shape, origin=None, fillval=0, cover=N
                                              float(origin[0]), float(origin[1]), float(fillval), out.data_ptr(),
                                              cptr, mptr, img.device.index, _stream(img)))
     return out, mask
+
+
+def _blocks_inside(b, bh, bw, cover, margin=0.0):
+    """True when the source positions of all four corners of every block lie inside ``cover``.  The corner
+    values are computed with the kernel's own operation order in float64, and every rounding step of the affine
+    coordinate field is monotone in the column and in the row index, so the corners bound all pixels exactly:
+    the coverage mask would be all ones."""
+    xe = np.stack((b[:, 0], b[:, 0] + (bw - 1) * b[:, 2]), axis=-1)[:, :, None]
+    ye = np.stack((b[:, 1], b[:, 1] + (bh - 1) * b[:, 3]), axis=-1)[:, None, :]
+    xs = xe * b[:, 4, None, None] + ye * b[:, 5, None, None] + b[:, 6, None, None]
+    ys = xe * b[:, 7, None, None] + ye * b[:, 8, None, None] + b[:, 9, None, None]
+    return bool(xs.min() >= cover[0] + margin and xs.max() < cover[2] - margin and
+                ys.min() >= cover[1] + margin and ys.max() < cover[3] - margin)
 
 
 def crop_blocks(img, blocks, block_shape, origin=None, fillval=0, out=None):
