@@ -1,10 +1,14 @@
-// fb_xcorr_fast.cuh -- register-resident fast path for power-of-two FFT grids (float32 compute).
+// fb_xcorr_fast.cuh -- register-resident fast path (float32 compute) for FFT grids whose line lengths
+// are in the size table of fb_fast_groups.h: powers of two 256 .. 4096 and 5-smooth lengths with
+// factors 3 / 5 (576, 288, 384, 768, 1152, 300, 200, 400, 800).
 //
-// A line of N = E * T points is transformed by T lanes of a warp holding E points each
-// (T = 16: two lines per warp, T = 32: one): radix-E in registers over the stride-T
-// elements, twiddle by w_N^(k1 t), one transpose through a private shared-memory region,
-// radix-T in registers.  Input and output are both in natural order, lane-contiguous, so
-// global loads / stores of whole lines are coalesced without staging.
+// A line of N = E * T points is transformed by T lanes holding E points each (T < 32: several lines per
+// warp, lanes beyond LPW * T shadow the first ones; T = 32: one line per warp; T = 64: a line spans two
+// warps): radix-E in registers over the stride-T elements, twiddle by w_N^(k1 t), one transpose
+// through a private shared-memory region, radix-T in registers (E / T transforms per lane).  Input and
+// output are both in natural order, lane-contiguous, so global loads / stores of whole lines are
+// coalesced without staging.  The per-lane transforms are the packed decimation-in-time radix-2 code of
+// fb_regfft.cuh for powers of two and the mixed-radix (2, 3, 5) code of fb_gfft.cuh otherwise.
 //
 //   n = n1 T + t,  k = k1 + E k2:
 //   A[k1][t]   = sum_n1 x[n1 T + t] w_E^(n1 k1)           (stage A, lane t)
@@ -12,9 +16,9 @@
 //   X[k1+E k2] = sum_t  A[k1][t] w_T^(t k2)               (stage B, lane k1 mod T)
 //
 // The three stages keep the HBM intermediates transposed so that every kernel reads and
-// writes whole lines:  K1 rows -> FT[img][pair][kx][y];  K2 columns: FT -> GT[pair][P|Q][kx][y];
+// writes whole lines:  K1 rows -> FT[img][pair][kx][y];  K2 columns: FT -> GT[pair][y / R][P|Q][kx][y % R];
 // K3 rows: GT -> per-row arg-max partials.  Same arithmetic as the generic path
-// (feabas/matcher.py:63-68,82,114-125).  CUDA only (warp shuffles, cp.async).
+// (feabas/matcher.py:63-68,82,114-125).  CUDA only (warp shuffles, cp.async.bulk, TMA tensor stores).
 #pragma once
 #include <cuda.h>          // CUtensorMap (type only; the encoder is fetched at run time, no libcuda link)
 #include "fb_regfft.cuh"

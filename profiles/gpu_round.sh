@@ -13,6 +13,11 @@ timeout 600 python bench.py --impl reference --steps 20 --warmup 3 > $OUT/bench_
 for wl in xcorr512_nopad xcorr256 xcorr128 xcorr1024 xcorr2048 stitch_fine thumb150 align280; do
   timeout 120 python bench.py --workload $wl --steps 30 --no-cpu-baseline > $OUT/bench_$wl.json 2>> $OUT/bench.err
 done
+# matcher-level workloads (configs 1, 3, 4 through stitching_matcher / section_matcher / bboxes_mesh_renderer_matcher), CPU port beside them
+timeout 300 python bench.py --workload align512_blocks --steps 50 > $OUT/bench_align512_blocks.json 2>> $OUT/bench.err
+for wl in stitch2x3 thumb_sections; do
+  timeout 400 python bench.py --workload $wl --steps 5 > $OUT/bench_$wl.json 2>> $OUT/bench.err
+done
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:fbk -c 400 --csv \
     --log-file $OUT/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/ncu_launches.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:fbk_fast -s 9 -c 3 -f \
