@@ -124,6 +124,9 @@ struct StreamCtx {
     double* dout = nullptr;
     size_t dout_bytes = 0;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    // fast path, pipelined schedule: side stream + ordering events (no timing)
+    cudaStream_t side = nullptr;
+    std::vector<cudaEvent_t> order_ev;
     // per-kernel timing (option "profile"): (slot, start, stop) triples not yet read back
     std::vector<std::tuple<int, cudaEvent_t, cudaEvent_t>> prof_pending;
     std::vector<cudaEvent_t> prof_free;
@@ -138,6 +141,7 @@ static std::map<int, bool> g_attr_done;
 static long long g_opt_ws_bytes = 2LL << 30;
 static long long g_opt_host_chunk = 64LL << 20;
 static long long g_opt_profile = 0;
+static long long g_opt_pipeline = 2;           // fast path: a chunk runs as this many independent parts on separate streams (1: serial)
 static long long g_opt_max_radix = 16;         // largest radix of the shared-memory passes (experiment switch; set before first use)
 static long long g_opt_fast_flags = 0;       // experiment switches, see FastParams::flags (+16: K2 unbatched twiddles, +32: K3 8 lines)
 
@@ -396,60 +400,69 @@ static bool make_gt_map(CUtensorMap* map, void* gt, int nb, int ny, int kp, int 
                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <typename TI>
-static int launch_fast(const Problem& q, StreamCtx& ctx, XcParams& p, int nb, cudaStream_t st)
+// Parameters of the sub-range [lo, lo + cnt) of a chunk of nb pairs (workspace carved by pair index).
+static int fast_prepare(const Problem& q, StreamCtx& ctx, const XcParams& p, int lo, int cnt, int nb, FastParams& fp)
 {
-    FastParams fp{};
     int rc;
     int EX, TX, EY, TY;
     fast_et(q.nx, EX, TX); fast_et(q.ny, EY, TY);
     if ((rc = get_warp_table(ctx.device, q.nx, TX, fp.twx)) != FB_OK) return rc;
     if ((rc = get_warp_table(ctx.device, q.ny, TY, fp.twy)) != FB_OK) return rc;
-    if (!g_num_sms) { cudaDeviceProp pr; CU(cudaGetDeviceProperties(&pr, ctx.device)); g_num_sms = pr.multiProcessorCount; }
     const Geometry& g = q.g;
     unsigned char* w = reinterpret_cast<unsigned char*>(ctx.ws);
     const size_t f0 = (size_t)nb * g.kp * q.hp0 * 8, f1 = (size_t)nb * g.kp * q.hp1 * 8, gg = (size_t)nb * 2 * g.kp * q.ny * 8;
-    fp.FT0 = reinterpret_cast<cx<float>*>(w);
-    fp.FT1 = reinterpret_cast<cx<float>*>(w + f0);
-    fp.GT = reinterpret_cast<cx<float>*>(w + f0 + f1);
-    p.part = reinterpret_cast<Partial*>(w + f0 + f1 + gg);
+    fp.FT0 = reinterpret_cast<cx<float>*>(w) + (size_t)lo * g.kp * q.hp0;
+    fp.FT1 = reinterpret_cast<cx<float>*>(w + f0) + (size_t)lo * g.kp * q.hp1;
+    fp.GT = reinterpret_cast<cx<float>*>(w + f0 + f1) + (size_t)lo * 2 * g.kp * q.ny;
+    XcParams x = p;
+    x.img0 = (const char*)p.img0 + (size_t)lo * q.h0 * q.w0 * q.isz;
+    x.img1 = (const char*)p.img1 + (size_t)lo * q.h1 * q.w1 * q.isz;
+    x.n = cnt;
+    x.dx = p.dx + lo; x.dy = p.dy + lo; x.conf = p.conf + lo;
+    x.peak = p.peak ? p.peak + lo : nullptr; x.mir = p.mir ? p.mir + lo : nullptr;
+    x.part = reinterpret_cast<Partial*>(w + f0 + f1 + gg) + (size_t)lo * q.nrt;
     fp.rblk = fast_rblk(q.nx, TX);                       // rows per K3 tile
     if (q.nx == 1024 && (g_opt_fast_flags & 32)) fp.rblk = 4;
     fp.flags = (int)(g_opt_fast_flags & ~(16 | 32));
-    fp.use_tma = make_gt_map(&fp.gt_map, fp.GT, nb, q.ny, g.kp, fp.rblk) ? 1 : 0;
+    fp.use_tma = make_gt_map(&fp.gt_map, fp.GT, cnt, q.ny, g.kp, fp.rblk) ? 1 : 0;
     fp.gt_tiles = q.ny / fp.rblk;
     fp.gt_pieces = fp.gt_tiles > 256 ? fp.gt_tiles / 256 : 1;
-    p.G = fp.GT; p.gt_layout = fp.rblk; p.nrt = q.nrt; p.out_scale = p.scale;
+    x.G = fp.GT; x.gt_layout = fp.rblk; x.nrt = q.nrt; x.out_scale = x.scale;
     fp.hp0 = q.hp0; fp.hp1 = q.hp1;
-    fp.x = p;
-    // K1
-    {
+    fp.x = x;
+    return FB_OK;
+}
+
+// stage 1: K1 rows forward, 2: K2 columns, 3: K3 rows inverse, 4: K4 finalize -- of the cnt pairs described by fp
+static int fast_stage(int stage, const Problem& q, StreamCtx& ctx, const FastParams& fp, int cnt, int in_dtype, cudaStream_t st)
+{
+    int EX, TX, EY, TY;
+    fast_et(q.nx, EX, TX); fast_et(q.ny, EY, TY);
+    const Geometry& g = q.g;
+    if (stage == 1) {
         const int TR = 2 * fast_lines(TX, kNW1);
-        const int work = nb * ((q.hp0 + TR - 1) / TR + (q.hp1 + TR - 1) / TR);
+        const int work = cnt * ((q.hp0 + TR - 1) / TR + (q.hp1 + TR - 1) / TR);
         const int cap = g_num_sms * (EX > 32 ? 1 : 16 / kNW1);
         const int grid = work < cap ? work : cap;
         const bool pruned = q.w0 <= q.nx / 2 && q.w1 <= q.nx / 2;
         ProfScope ps(ctx, st, SLOT_ROWS_FWD);
-        FastLaunch l{q.nx, std::is_same<TI, float>::value ? FB_F32 : FB_U8, pruned, false, 0, grid, 32 * kNW1, fast_smem(q.nx, kNW1), st};
+        FastLaunch l{q.nx, in_dtype, pruned, false, 0, grid, 32 * kNW1, fast_smem(q.nx, kNW1), st};
         if (!fast_dispatch(1, fp, l)) return fail(FB_ESIZE, "no fast-path row kernel for %d points", q.nx);
-    }
-    // K2
-    {
+    } else if (stage == 2) {
         const int cpg = fast_lines(TY, kNW2) / 2;
-        const int work = nb * ((g.kp + cpg - 1) / cpg);
+        const int work = cnt * ((g.kp + cpg - 1) / cpg);
         const int cap = g_num_sms * (EY > 32 ? 1 : 16 / kNW2);
         const int grid = work < cap ? work : cap;
         const bool pruned = q.h0 <= q.ny / 2 && q.h1 <= q.ny / 2;     // (rows >= h of the row spectra are zero)
         ProfScope ps(ctx, st, SLOT_COLUMNS);
         FastLaunch l{q.ny, 0, pruned, false, 0, grid, 32 * kNW2, fast_smem(q.ny, kNW2), st};
         if (!fast_dispatch(2, fp, l)) return fail(FB_ESIZE, "no fast-path column kernel for %d points", q.ny);
-    }
-    // K3: TX * R threads own R lines (R <= rblk rows of a GT tile)
-    {
+    } else if (stage == 3) {
+        // K3: TX * R threads own R lines (R <= rblk rows of a GT tile)
         int R = fp.rblk;
         if (q.nx == 1024 && (g_opt_fast_flags & 16)) R = 4;          // experiment: half-tile CTAs
         const int nt = k3_threads(TX, R);
-        const int work = nb * (q.nrt / R);
+        const int work = cnt * (q.nrt / R);
         const int cap = g_num_sms * (EX > 32 ? 1 : 512 / nt);
         const int grid = work < cap ? work : cap;
         const int XS = TX * R + (R < 16 ? R : 0);
@@ -461,12 +474,57 @@ static int launch_fast(const Problem& q, StreamCtx& ctx, XcParams& p, int nb, cu
         const int variant = (R == 4 && q.nx == 1024) ? (fp.rblk == 8 ? 3 : 2) : (tma3 ? 0 : 1);
         FastLaunch l{q.nx, 0, false, mir, variant, grid, nt, variant == 0 ? sm3t : sm3, st};
         if (!fast_dispatch(3, fp, l)) return fail(FB_ESIZE, "no fast-path inverse row kernel for %d points", q.nx);
-    }
-    {
+    } else {
         ProfScope ps(ctx, st, SLOT_FINALIZE);
-        fbk_finalize<float><<<nb, 256, (size_t)q.nx * 4 * sizeof(cx<float>) + 2048, st>>>(fp.x);
+        fbk_finalize<float><<<cnt, 256, (size_t)q.nx * 4 * sizeof(cx<float>) + 2048, st>>>(fp.x);
     }
-    g_launches += 4;
+    g_launches += 1;
+    return FB_OK;
+}
+
+template <typename TI>
+static int launch_fast(const Problem& q, StreamCtx& ctx, XcParams& p, int nb, cudaStream_t st)
+{
+    int rc;
+    if (!g_num_sms) { cudaDeviceProp pr; CU(cudaGetDeviceProperties(&pr, ctx.device)); g_num_sms = pr.multiProcessorCount; }
+    const int in_dtype = std::is_same<TI, float>::value ? FB_F32 : FB_U8;
+    // Two-stream schedule: the chunk is cut into S (2) independent parts, each running its four kernels on its own
+    // stream (part 0 on the caller's).  The kernels are persistent and fill the GPU, so the streams mostly
+    // alternate -- but the ramp-up and tail of every kernel (CTAs waiting for the slowest one, launch gaps) are
+    // filled by the other part's kernel: +6 % on the 512^2 / FFT 1024^2 workload (profiles/two_streams.py).
+    // Sharing the SMs between a column kernel and row kernels deliberately (one CTA each, dependency-pipelined
+    // sub-chunks) was measured and lost 4-10 %: both kinds are issue / shared-memory bound.
+    int S = (int)g_opt_pipeline;
+    while (S > 1 && nb / S < 32) --S;
+    if (S <= 1) {
+        FastParams fp{};
+        if ((rc = fast_prepare(q, ctx, p, 0, nb, nb, fp)) != FB_OK) return rc;
+        for (int stage = 1; stage <= 4; ++stage)
+            if ((rc = fast_stage(stage, q, ctx, fp, nb, in_dtype, st)) != FB_OK) return rc;
+        CU(cudaGetLastError());
+        return FB_OK;
+    }
+    if (S > 2) S = 2;
+    if (!ctx.side) CU(cudaStreamCreateWithFlags(&ctx.side, cudaStreamNonBlocking));
+    while ((int)ctx.order_ev.size() < 2) {
+        cudaEvent_t e;
+        CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx.order_ev.push_back(e);
+    }
+    cudaEvent_t fork = ctx.order_ev[0], join = ctx.order_ev[1];
+    FastParams fps[2] = {};
+    const int mid = nb / 2;
+    if ((rc = fast_prepare(q, ctx, p, 0, mid, nb, fps[0])) != FB_OK) return rc;
+    if ((rc = fast_prepare(q, ctx, p, mid, nb - mid, nb, fps[1])) != FB_OK) return rc;
+    cudaStream_t sd = ctx.side;
+    CU(cudaEventRecord(fork, st));                         // inputs (and the workspace's previous use) are ordered on st
+    CU(cudaStreamWaitEvent(sd, fork, 0));
+    for (int stage = 1; stage <= 4; ++stage) {             // interleaved enqueue: both queues fill at the same pace
+        if ((rc = fast_stage(stage, q, ctx, fps[0], mid, in_dtype, st)) != FB_OK) return rc;
+        if ((rc = fast_stage(stage, q, ctx, fps[1], nb - mid, in_dtype, sd)) != FB_OK) return rc;
+    }
+    CU(cudaEventRecord(join, sd));
+    CU(cudaStreamWaitEvent(st, join, 0));                  // results are ordered on the caller's stream again
     CU(cudaGetLastError());
     return FB_OK;
 }
@@ -758,6 +816,7 @@ extern "C" int fb_set_option(const char* name, long long value)
 {
     if (!name) return fail(FB_EINVAL, "null option name");
     std::lock_guard<std::mutex> lk(g_mu);
+    if (!strcmp(name, "pipeline")) { if (value < 1 || value > 16) return fail(FB_EINVAL, "pipeline out of range"); g_opt_pipeline = value; return FB_OK; }
     if (!strcmp(name, "max_radix")) { if (value < 5 || value > 16) return fail(FB_EINVAL, "max_radix out of range"); g_opt_max_radix = value; return FB_OK; }
     if (!strcmp(name, "ws_bytes")) { if (value < (1 << 20)) return fail(FB_EINVAL, "ws_bytes too small"); g_opt_ws_bytes = value; return FB_OK; }
     if (!strcmp(name, "profile")) { g_opt_profile = value ? 1 : 0; return FB_OK; }
@@ -812,6 +871,8 @@ extern "C" int fb_release(int device)
         if (c.dout) cudaFree(c.dout);
         for (auto& t : c.prof_pending) { cudaEventDestroy(std::get<1>(t)); cudaEventDestroy(std::get<2>(t)); }
         for (auto e : c.prof_free) cudaEventDestroy(e);
+        if (c.side) cudaStreamDestroy(c.side);
+        for (auto e : c.order_ev) cudaEventDestroy(e);
         if (c.copy_stream) cudaStreamDestroy(c.copy_stream);
         if (c.own_stream) cudaStreamDestroy(c.own_stream);
         it = g_ctx.erase(it);
