@@ -18,6 +18,9 @@ timeout 300 python bench.py --workload align512_blocks --steps 50 > $OUT/bench_a
 for wl in stitch2x3 thumb_sections; do
   timeout 400 python bench.py --workload $wl --steps 5 > $OUT/bench_$wl.json 2>> $OUT/bench.err
 done
+# ncu serialises kernels: capture the serial schedule (one stream, whole batch per launch), which is also what bench.py's
+# per-kernel roofline numbers are taken from
+export FB_PIPELINE=1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:fbk -c 400 --csv \
     --log-file $OUT/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/ncu_launches.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:fbk_fast -s 9 -c 3 -f \
