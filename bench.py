@@ -365,7 +365,7 @@ def bench_blocks(args, wl, rank, world, local, warmup):
                                 'note': 'crop (u8 gather -> f32) + masked DoG of both stacks + host control flow = step - xcorr kernels'},
                 'kernels': kern}
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:          # N = 1 only (ranks of a multi-GPU run are bound to their GPU's CPUs)
         per_worker = 16
         pool, cores = cpu_blocks_arm(wl, per_worker)
         t0 = time.perf_counter()
@@ -596,7 +596,7 @@ def bench_stitch(args, wl, rank, world, local, warmup):
                         'used as algorithmic bytes; xcorr kernels are %.0f %% of the step, the rest is host control flow + image kernels' % (100 * xcorr_ms / ms),
                 'kernel_share_of_step': kern[dom]['ms_total'] / ms if world == 1 else None, 'kernels': kern}
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:          # N = 1 only (ranks of a multi-GPU run are bound to their GPU's CPUs)
         import psutil
         from concurrent.futures import ProcessPoolExecutor
         import multiprocessing as mp
@@ -917,7 +917,7 @@ def main():
                                          for k, v in prof_timed.items() if v[1]}}
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:          # N = 1 only (ranks of a multi-GPU run are bound to their GPU's CPUs)
         import psutil
         cores = psutil.cpu_count(logical=False) or os.cpu_count() or 1
         per_worker = cpu_pairs_per_worker(wl, 20.0, cores)
