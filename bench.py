@@ -776,6 +776,9 @@ def main():
     import feabas_b200.cuda as fc
     L = fc._lib
     L.set_option('ws_bytes', int(args.ws_gib * (1 << 30)))
+    if os.environ.get('FB_HOST_CHUNK_MIB'):
+        L.set_option('host_chunk_bytes', int(os.environ['FB_HOST_CHUNK_MIB']) << 20)
+        config['host_chunk_mib'] = int(os.environ['FB_HOST_CHUNK_MIB'])
     if os.environ.get('FB_PIPELINE'):
         L.set_option('pipeline', int(os.environ['FB_PIPELINE']))
         config['pipeline'] = int(os.environ['FB_PIPELINE'])
