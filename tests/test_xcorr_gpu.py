@@ -260,3 +260,46 @@ def test_fast_path_many_work_items_per_cta(fc, size, n):
     np.testing.assert_allclose(got[1], gen[1], atol=2e-3)
     np.testing.assert_allclose(got[2], gen[2], rtol=1e-4, atol=1e-6)
     parity.check_against_oracle(tuple(v[:3] for v in got), a[:3], b[:3], subpixel=True)
+
+
+@pytest.mark.parametrize('size,n', [(280, 12), (150, 24), (1024, 6), (100, 40)])
+def test_fast_sizes_size_independent_properties(fc, size, n):
+    """Grids served by the wider fast path (576 = 24 x 24, 300 = 30 x 10, 2048 = 64 x 32, 200 = 20 x 10 points per
+    line), through the two-stream schedule (n >= 64 pairs would be needed to split -- here the serial one) and the
+    pipelined one (option): ground truth recovered, swapping the stacks negates the displacement, results do not
+    depend on batch composition or on the schedule."""
+    import torch
+    a, b, shifts = synth.block_pairs(n, size, seed=size + 1, max_shift=min(32, size // 8))
+    ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    out = fc.xcorr_fft_device(ta, tb, subpixel=True).cpu().numpy()
+    np.testing.assert_array_equal(np.round(out[0]), shifts[:, 0])
+    np.testing.assert_array_equal(np.round(out[1]), shifts[:, 1])
+    swapped = fc.xcorr_fft_device(tb, ta, subpixel=True).cpu().numpy()
+    np.testing.assert_allclose(swapped[0], -out[0], atol=0.02)
+    np.testing.assert_allclose(swapped[1], -out[1], atol=0.02)
+    np.testing.assert_allclose(swapped[2], out[2], rtol=1e-4, atol=1e-6)
+    part = fc.xcorr_fft_device(ta[2:5].contiguous(), tb[2:5].contiguous(), subpixel=True).cpu().numpy()
+    np.testing.assert_array_equal(part, out[:, 2:5])
+
+
+def test_two_stream_schedule_matches_serial(fc):
+    """fb_set_option('pipeline', 2) (default: a chunk runs as two halves on two streams) and 1 (serial) give
+    bit-identical results; so does a workspace so small that the batch is cut into several chunks."""
+    import torch
+    n = 150
+    a, b, shifts = synth.block_pairs(n, 128, seed=77, max_shift=16)
+    ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    L = fc._lib
+    try:
+        L.set_option('pipeline', 1)
+        serial = fc.xcorr_fft_device(ta, tb, subpixel=True).cpu().numpy()
+        L.set_option('pipeline', 2)
+        two = fc.xcorr_fft_device(ta, tb, subpixel=True).cpu().numpy()
+        L.set_option('ws_bytes', 70 * 450000)                     # ~70 pairs per chunk: chunks of 70 / 70 / 10 pairs
+        chunked = fc.xcorr_fft_device(ta, tb, subpixel=True).cpu().numpy()
+    finally:
+        L.set_option('pipeline', 2)
+        L.set_option('ws_bytes', 2 << 30)
+    np.testing.assert_array_equal(serial, two)
+    np.testing.assert_array_equal(serial, chunked)
+    np.testing.assert_array_equal(np.round(two[0]), shifts[:, 0])
