@@ -462,6 +462,70 @@ def _cpu_stitch_task(k):
     return 0 if out[0] is None else len(out[0]), blocks
 
 
+def _gpu_job_worker(workload, seed, steps, local, barrier, queue):
+    """One of P worker processes sharing a GPU (FEABAS's own parallel model: spawned workers, one overlap / section pair
+    per task, feabas/concurrent.py:59-96): every worker has its own CUDA context and runs the job list `steps` times."""
+    try:
+        import torch
+        torch.cuda.set_device(local)
+        import feabas_b200.cuda as fc
+        wl = dict(WORKLOADS[workload])
+        stitch = wl['kind'] == 'stitch'
+        jobs = make_jobs(wl, seed)
+        lib = fc._lib.lib()
+
+        def run():
+            for a, b in jobs:
+                if stitch:
+                    fc.stitching_matcher(a, b, device=local, **STITCH_KW)
+                else:
+                    hh, ww = a.shape
+                    fc.section_matcher(fc.AffineMesh((0, 0, ww, hh), uid=0), fc.AffineMesh((0, 0, ww, hh), uid=1),
+                                       fc.ArrayLoader(a, device=local), fc.ArrayLoader(b, device=local), **SECTION_KW)
+        for _ in range(2):
+            run()
+        torch.cuda.synchronize()
+        p0 = lib.fb_pair_count()
+        barrier.wait()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            run()
+        torch.cuda.synchronize()
+        queue.put((lib.fb_pair_count() - p0, len(jobs) * steps, time.perf_counter() - t0))
+    except Exception as exc:                                   # pragma: no cover
+        queue.put(('error', repr(exc), 0.0))
+        try:
+            barrier.abort()
+        except Exception:
+            pass
+
+
+def multi_process_throughput(workload, workers, steps, local):
+    import multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    barrier, queue = ctx.Barrier(workers + 1), ctx.Queue()
+    procs = [ctx.Process(target=_gpu_job_worker, args=(workload, 11 + k, steps, local, barrier, queue)) for k in range(workers)]
+    for pr in procs:
+        pr.start()
+    try:
+        barrier.wait(timeout=300)
+    except Exception:
+        for pr in procs:
+            pr.terminate()
+        return {'workers': workers, 'error': 'workers did not reach the start barrier'}
+    t0 = time.perf_counter()
+    res = [queue.get(timeout=600) for _ in procs]
+    dt = time.perf_counter() - t0
+    for pr in procs:
+        pr.join(timeout=60)
+    if any(r[0] == 'error' for r in res):
+        return {'workers': workers, 'error': str([r for r in res if r[0] == 'error'][0][1])}
+    return {'workers': workers, 'value': sum(r[0] for r in res) / dt, 'unit': 'matches/s', 'jobs_per_s': sum(r[1] for r in res) / dt,
+            'steps_per_worker': steps, 'seconds': dt,
+            'note': 'wall clock over P spawned worker processes sharing this GPU (one CUDA context each, host strips / thumbnails in), '
+                    'the way FEABAS fans overlaps / section pairs out to workers; supplementary to the single-process numbers'}
+
+
 def bench_stitch(args, wl, rank, world, local, warmup):
     import numpy as np
     stitch = wl['kind'] == 'stitch'
@@ -612,11 +676,15 @@ def bench_stitch(args, wl, rank, world, local, warmup):
         cpu = {'value': blocks / s_, 'unit': 'matches/s', 'cores': cores, 'kind': 'port', 'overlaps_per_s': n_tasks / s_,
                'sample': f'{n_tasks} jobs (the {len(strips)} of one step, cycled), one job per task on {cores} single-thread workers '
                          f"(oracle port of {'stitching_matcher' if stitch else 'the section_matcher loop'}), {s_:.1f} s wall"}
+    multi = None
+    if args.workers > 0 and world == 1:
+        torch.cuda.empty_cache()
+        multi = multi_process_throughput(args.workload, args.workers, max(20, args.steps), local)
     line = {'metric': 'xcorr_block_matches_per_sec', 'value': value, 'unit': 'matches/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic', 'config': dict(config, overlaps_per_s=world * len(strips) * args.steps / (ms * 1e-3),
                                                                    unit_count='xcorr pairs (fb_pair_count)' if pairs else 'returned match points'),
-            'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu}
+            'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu, 'multi_process': multi}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -714,6 +782,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--fast-flags', type=int, default=0, help='kernel experiment switches (fb_set_option fast_flags)')
+    ap.add_argument('--workers', type=int, default=0, help='job workloads: also measure P worker processes sharing the GPU')
     ap.add_argument('--force', default=None, choices=['generic', 'staged', 'fused'], help='force an execution shape (comparison runs)')
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
