@@ -35,6 +35,7 @@ WORKLOADS = {
     'xcorr2048': dict(h=2048, w=2048, pad=True, batch=16),
     'stitch_fine': dict(h=74, w=67, pad=True, batch=16384),       # config 1/2 finest level, FFT 150x135
     'thumb150': dict(h=150, w=150, pad=True, batch=4096),         # config 3, FFT 300x300
+    'xcorr300': dict(h=300, w=300, pad=True, batch=1024),         # FFT 600x600 (60 points per lane)
     'align280': dict(h=280, w=280, pad=True, batch=1024),         # default fine alignment (spacing 400, shrink 0.7), FFT 576x576
     # config 4 through bboxes_mesh_renderer_matcher (matcher.py:781-861): a uint8 section pair, a dense grid of
     # 512x512 blocks gathered + band-passed (sigma 3.5) + matched on the device; e2e uploads the two sections

@@ -18,7 +18,7 @@ FAST_DEPS = ['fb_fast_tu.inc', 'fb_fast_groups.h', 'fb_xcorr_fast.cuh', 'fb_xcor
 UNITS = {
     'fb_xcorr.cu': ['fb_xcorr.cuh', 'fb_xcorr_fast.cuh', 'fb_fast_groups.h', 'fb_regfft.cuh', 'fb_fft.cuh', 'fb_gfft.cuh', 'fb_host_plan.h', 'fb_common.h', HEADER],
     # the register-resident fast path, one translation unit per group of line lengths (parallel build)
-    'fb_fast_pow2.cu': FAST_DEPS, 'fb_fast_big.cu': FAST_DEPS, 'fb_fast_r3.cu': FAST_DEPS, 'fb_fast_r5.cu': FAST_DEPS,
+    'fb_fast_pow2.cu': FAST_DEPS, 'fb_fast_big.cu': FAST_DEPS, 'fb_fast_r3.cu': FAST_DEPS, 'fb_fast_r5.cu': FAST_DEPS, 'fb_fast_r5b.cu': FAST_DEPS,
     'fb_image.cu': ['fb_common.h', HEADER],
 }
 SOURCES = list(UNITS)

@@ -10,7 +10,8 @@
 #define FB_FAST_SIZES_BIG(X) X(2048, 64, 32) X(4096, 64, 64)
 #define FB_FAST_SIZES_R3(X) X(576, 24, 24) X(288, 24, 12) X(384, 48, 8) X(768, 48, 16) X(1152, 48, 24)
 #define FB_FAST_SIZES_R5(X) X(300, 30, 10) X(200, 20, 10) X(400, 40, 10) X(800, 40, 20)
-#define FB_FAST_SIZES(X) FB_FAST_SIZES_POW2(X) FB_FAST_SIZES_BIG(X) FB_FAST_SIZES_R3(X) FB_FAST_SIZES_R5(X)
+#define FB_FAST_SIZES_R5B(X) X(600, 60, 10) X(500, 50, 10) X(1200, 60, 20) X(720, 60, 12)
+#define FB_FAST_SIZES(X) FB_FAST_SIZES_POW2(X) FB_FAST_SIZES_BIG(X) FB_FAST_SIZES_R3(X) FB_FAST_SIZES_R5(X) FB_FAST_SIZES_R5B(X)
 
 namespace fb {
 
@@ -20,6 +21,14 @@ constexpr int kNW1 = 8, kNW2 = 8;                    // warps per CTA of K1 / K2
 template <int E, int T> constexpr int kR3() { return T > 32 || (E * T) % 8 ? 4 : 8; }
 // CTAs per SM the register budget allows: a lane holds E complex points (E > 32: one CTA)
 template <int E> constexpr int kOcc(int full) { return E > 32 ? 1 : full; }
+// K3 CTAs per SM: 512 threads per SM for E <= 32; for E > 32 (up to 255 registers per thread) what the register file holds
+constexpr __host__ __device__ int k3_ctas_per_sm(int E, int threads)
+{
+    const int full = 512 / threads;
+    if (E <= 32) return full;
+    const int byreg = 65536 / (threads * 255);
+    return byreg < 1 ? 1 : (byreg < full ? byreg : full);
+}
 
 // K3 variants: 0 = TMA-fed (default), 1 = LDG, 2 = LDG with 4 lines per CTA on 4-row tiles, 3 = same on 8-row tiles
 // (2, 3: experiment switches, 1024-point lines only)
@@ -44,5 +53,6 @@ FB_FAST_GROUP_DECL(pow2)
 FB_FAST_GROUP_DECL(big)
 FB_FAST_GROUP_DECL(r3)
 FB_FAST_GROUP_DECL(r5)
+FB_FAST_GROUP_DECL(r5b)
 
 }  // namespace fb

@@ -223,7 +223,8 @@ static int set_attrs(int device)
     RS((fbk_fused<float, unsigned char>));
     RS((fbk_fused<double, unsigned char>));
     RS((fbk_fused<double, double>));
-    if (fast_set_attrs_pow2(kMaxSmem) || fast_set_attrs_big(kMaxSmem) || fast_set_attrs_r3(kMaxSmem) || fast_set_attrs_r5(kMaxSmem))
+    if (fast_set_attrs_pow2(kMaxSmem) || fast_set_attrs_big(kMaxSmem) || fast_set_attrs_r3(kMaxSmem) || fast_set_attrs_r5(kMaxSmem) ||
+        fast_set_attrs_r5b(kMaxSmem))
         return fail(FB_ECUDA, "cudaFuncSetAttribute failed for a fast-path kernel");
 #undef RS
     g_attr_done[device] = true;
@@ -345,9 +346,9 @@ struct ProfScope {
 static bool fast_dispatch(int stage, const FastParams& fp, const FastLaunch& l)
 {
     switch (stage) {
-        case 1: return fast_k1_pow2(fp, l) || fast_k1_big(fp, l) || fast_k1_r3(fp, l) || fast_k1_r5(fp, l);
-        case 2: return fast_k2_pow2(fp, l) || fast_k2_big(fp, l) || fast_k2_r3(fp, l) || fast_k2_r5(fp, l);
-        default: return fast_k3_pow2(fp, l) || fast_k3_big(fp, l) || fast_k3_r3(fp, l) || fast_k3_r5(fp, l);
+        case 1: return fast_k1_pow2(fp, l) || fast_k1_big(fp, l) || fast_k1_r3(fp, l) || fast_k1_r5(fp, l) || fast_k1_r5b(fp, l);
+        case 2: return fast_k2_pow2(fp, l) || fast_k2_big(fp, l) || fast_k2_r3(fp, l) || fast_k2_r5(fp, l) || fast_k2_r5b(fp, l);
+        default: return fast_k3_pow2(fp, l) || fast_k3_big(fp, l) || fast_k3_r3(fp, l) || fast_k3_r5(fp, l) || fast_k3_r5b(fp, l);
     }
 }
 static void fast_et(int n, int& E, int& T)
@@ -463,7 +464,7 @@ static int fast_stage(int stage, const Problem& q, StreamCtx& ctx, const FastPar
         if (q.nx == 1024 && (g_opt_fast_flags & 16)) R = 4;          // experiment: half-tile CTAs
         const int nt = k3_threads(TX, R);
         const int work = cnt * (q.nrt / R);
-        const int cap = g_num_sms * (EX > 32 ? 1 : 512 / nt);
+        const int cap = g_num_sms * k3_ctas_per_sm(EX, nt);
         const int grid = work < cap ? work : cap;
         const int XS = TX * R + (R < 16 ? R : 0);
         const size_t sm3 = ((size_t)EX * XS + (kLaneTwiddles ? 0 : q.nx)) * sizeof(cx<float>) + (nt / 32) * R * 2 * (sizeof(float) + sizeof(double));

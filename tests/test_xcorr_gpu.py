@@ -223,6 +223,12 @@ FAST_CASES = [
     (2, (576, 576), (576, 576), dict(subpixel=True)),                          # 1152 x 1152
     (2, (100, 400), (100, 400), dict(subpixel=True)),                          # 200 x 800
     (2, (400, 200), (400, 200), dict(subpixel=True, pad=False)),               # 400 x 200 unpruned
+    # 60 / 50 points per lane: 600 = 60 x 10, 500 = 50 x 10, 1200 = 60 x 20, 720 = 60 x 12
+    (2, (300, 300), (300, 300), dict(subpixel=True)),                          # 600 x 600
+    (2, (250, 250), (250, 250), dict(subpixel=True)),                          # 500 x 500 (K3 tiles of 4 rows)
+    (2, (600, 600), (600, 600), dict(subpixel=True, conf_mode=1)),             # 1200 x 1200, STD
+    (2, (360, 360), (360, 360), dict(subpixel=True, conf_mode=0)),             # 720 x 720, NONE
+    (2, (600, 720), (600, 720), dict(subpixel=True, pad=False)),               # 600 x 720 unpruned
 ]
 
 
