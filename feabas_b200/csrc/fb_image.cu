@@ -146,14 +146,16 @@ constexpr int kFT = 64, kFP = 8, kSlack = 8, kRowPitch = kFT + 1;
 struct GaussTapsF {
     float wc;                          // centre weight
     float wt[kMaxRadius + 8];          // wt[j] = weight at offset +-(radius - j), zero for j >= radius
-    int rpad;                          // radius rounded up to a multiple of 8
+    int rpad;                          // radius rounded up to a multiple of the chunk size
 };
 
 __host__ __device__ inline int gaussf_in_pitch(int r) { return (kFT + 2 * r + kFP) | 1; }
 
-template <typename TS, int MODE>
+// CH: taps per chunk (5..8), chosen on the host so that the tap list needs the least zero padding
+template <typename TS, int MODE, int CH>
 __global__ void __launch_bounds__(kNT) fbk_gauss2d_f32(const __grid_constant__ GaussParams p, const __grid_constant__ GaussTapsF tf)
 {
+    constexpr int WN = CH + kFP - 1;                 // window: CH taps x 8 outputs touch CH + 7 consecutive values
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int r = p.taps.radius, rp = tf.rpad;
     const int in_w = kFT + 2 * r, in_h = kFT + 2 * r, in_pitch = gaussf_in_pitch(r);
@@ -185,17 +187,17 @@ __global__ void __launch_bounds__(kNT) fbk_gauss2d_f32(const __grid_constant__ G
             float acc[kFP];
 #pragma unroll
             for (int o = 0; o < kFP; ++o) acc[o] = row[r + o] * tf.wc;
-            for (int jb = 0; jb < rp; jb += 8) {
-                float a[15], b[15];
+            for (int jb = 0; jb < rp; jb += CH) {
+                float a[WN], b[WN];
                 const float* pa = row + jb;
-                const float* pb = row + 2 * r - jb - 7;
+                const float* pb = row + 2 * r - jb - (CH - 1);
 #pragma unroll
-                for (int k = 0; k < 15; ++k) { a[k] = pa[k]; b[k] = pb[k]; }
+                for (int k = 0; k < WN; ++k) { a[k] = pa[k]; b[k] = pb[k]; }
 #pragma unroll
-                for (int jj = 0; jj < 8; ++jj) {
+                for (int jj = 0; jj < CH; ++jj) {
                     const float wgt = tf.wt[jb + jj];
 #pragma unroll
-                    for (int o = 0; o < kFP; ++o) acc[o] = fmaf(a[jj + o] + b[7 - jj + o], wgt, acc[o]);
+                    for (int o = 0; o < kFP; ++o) acc[o] = fmaf(a[jj + o] + b[CH - 1 - jj + o], wgt, acc[o]);
                 }
             }
             float* dst = s_row + yy * kRowPitch + strip * kFP;
@@ -211,17 +213,17 @@ __global__ void __launch_bounds__(kNT) fbk_gauss2d_f32(const __grid_constant__ G
         float acc[kFP];
 #pragma unroll
         for (int o = 0; o < kFP; ++o) acc[o] = col[(r + o) * kRowPitch] * tf.wc;
-        for (int jb = 0; jb < rp; jb += 8) {
-            float a[15], b[15];
+        for (int jb = 0; jb < rp; jb += CH) {
+            float a[WN], b[WN];
             const float* pa = col + jb * kRowPitch;
-            const float* pb = col + (2 * r - jb - 7) * kRowPitch;
+            const float* pb = col + (2 * r - jb - (CH - 1)) * kRowPitch;
 #pragma unroll
-            for (int k = 0; k < 15; ++k) { a[k] = pa[k * kRowPitch]; b[k] = pb[k * kRowPitch]; }
+            for (int k = 0; k < WN; ++k) { a[k] = pa[k * kRowPitch]; b[k] = pb[k * kRowPitch]; }
 #pragma unroll
-            for (int jj = 0; jj < 8; ++jj) {
+            for (int jj = 0; jj < CH; ++jj) {
                 const float wgt = tf.wt[jb + jj];
 #pragma unroll
-                for (int o = 0; o < kFP; ++o) acc[o] = fmaf(a[jj + o] + b[7 - jj + o], wgt, acc[o]);
+                for (int o = 0; o < kFP; ++o) acc[o] = fmaf(a[jj + o] + b[CH - 1 - jj + o], wgt, acc[o]);
             }
         }
         const int x = x0 + xx;
@@ -494,21 +496,37 @@ size_t gaussf_smem(int r)
     return ((size_t)in_h * gaussf_in_pitch(r) + 2 * kSlack + (size_t)(in_h + 2 * kSlack) * kRowPitch) * sizeof(float);
 }
 
+template <typename TS, int MODE, int CH>
+int launch_gauss_f32_ch(const GaussParams& p, GaussTapsF& tf, cudaStream_t st)
+{
+    const int r = p.taps.radius;
+    tf.rpad = (r + CH - 1) / CH * CH;
+    const size_t smem = gaussf_smem(r);
+    FB_CU(cudaFuncSetAttribute(fbk_gauss2d_f32<TS, MODE, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((p.w + kFT - 1) / kFT, (p.h + kFT - 1) / kFT, p.n);
+    fbk_gauss2d_f32<TS, MODE, CH><<<grid, kNT, smem, st>>>(p, tf);
+    fb_count_launches(1);
+    FB_CU(cudaGetLastError());
+    return FB_OK;
+}
+
 template <typename TS, int MODE>
 int launch_gauss_f32(const GaussParams& p, cudaStream_t st)
 {
     GaussTapsF tf{};
     const int r = p.taps.radius;
     tf.wc = (float)p.taps.w[r];
-    tf.rpad = (r + 7) & ~7;
     for (int j = 0; j < r; ++j) tf.wt[j] = (float)p.taps.w[j];
-    const size_t smem = gaussf_smem(r);
-    FB_CU(cudaFuncSetAttribute(fbk_gauss2d_f32<TS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((p.w + kFT - 1) / kFT, (p.h + kFT - 1) / kFT, p.n);
-    fbk_gauss2d_f32<TS, MODE><<<grid, kNT, smem, st>>>(p, tf);
-    fb_count_launches(1);
-    FB_CU(cudaGetLastError());
-    return FB_OK;
+    // chunk size with the least zero padding of the tap list (the larger one on ties); padded reads stay inside
+    // the slack of at most 7 values either side for every choice
+    int best = 8, pad = (8 - r % 8) % 8;
+    for (int ch = 7; ch >= 5; --ch) { const int q = (ch - r % ch) % ch; if (q < pad) { pad = q; best = ch; } }
+    switch (best) {
+        case 5: return launch_gauss_f32_ch<TS, MODE, 5>(p, tf, st);
+        case 6: return launch_gauss_f32_ch<TS, MODE, 6>(p, tf, st);
+        case 7: return launch_gauss_f32_ch<TS, MODE, 7>(p, tf, st);
+        default: return launch_gauss_f32_ch<TS, MODE, 8>(p, tf, st);
+    }
 }
 
 template <typename TS, int MODE>
