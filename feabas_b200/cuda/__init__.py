@@ -7,7 +7,7 @@ from .image import masked_dog_filter, resize_area, resize_mask, crop_blocks
 from .surrogate import AffineMesh, AffineSLM, ArrayLoader
 from .matcher import (bboxes_mesh_renderer_matcher, global_translation_matcher, iterative_xcorr_matcher_w_mesh,
                       section_matcher, set_mesh_factory, stitching_matcher)
-from . import _lib
+from . import _lib, matchio
 
 __all__ = ['xcorr_fft', 'xcorr_fft_device', 'fft_shape', 'next_fast_len',
            'global_translation_matcher', 'stitching_matcher', 'section_matcher', 'iterative_xcorr_matcher_w_mesh',
