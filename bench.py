@@ -846,6 +846,9 @@ def main():
     import feabas_b200.cuda as fc
     L = fc._lib
     L.set_option('ws_bytes', int(args.ws_gib * (1 << 30)))
+    if os.environ.get('FB_FUSED_THREADS'):
+        L.set_option('fused_threads', int(os.environ['FB_FUSED_THREADS']))
+        config['fused_threads'] = int(os.environ['FB_FUSED_THREADS'])
     if os.environ.get('FB_HOST_CHUNK_MIB'):
         L.set_option('host_chunk_bytes', int(os.environ['FB_HOST_CHUNK_MIB']) << 20)
         config['host_chunk_mib'] = int(os.environ['FB_HOST_CHUNK_MIB'])

@@ -141,6 +141,7 @@ static std::map<int, bool> g_attr_done;
 static long long g_opt_ws_bytes = 2LL << 30;
 static long long g_opt_host_chunk = 64LL << 20;
 static long long g_opt_profile = 0;
+static long long g_opt_fused_threads = 0;      // experiment switch: threads per CTA of the fused kernel (0: 512 above 100 KB, else 256)
 static long long g_opt_pipeline = 2;           // fast path: a chunk runs as this many independent parts on separate streams (1: serial)
 static long long g_opt_max_radix = 16;         // largest radix of the shared-memory passes (experiment switch; set before first use)
 static long long g_opt_fast_flags = 0;       // experiment switches, see FastParams::flags (+16: K2 unbatched twiddles, +32: K3 8 lines)
@@ -483,6 +484,26 @@ static int fast_stage(int stage, const Problem& q, StreamCtx& ctx, const FastPar
     return FB_OK;
 }
 
+// work items and resident-CTA capacity of stage 1..3 for cnt pairs (the same numbers fast_stage launches with)
+static void fast_work(int stage, const Problem& q, int cnt, long long& work, int& cap)
+{
+    int EX, TX, EY, TY;
+    fast_et(q.nx, EX, TX); fast_et(q.ny, EY, TY);
+    if (stage == 1) {
+        const int TR = 2 * fast_lines(TX, kNW1);
+        work = (long long)cnt * ((q.hp0 + TR - 1) / TR + (q.hp1 + TR - 1) / TR);
+        cap = g_num_sms * (EX > 32 ? 1 : 16 / kNW1);
+    } else if (stage == 2) {
+        const int cpg = fast_lines(TY, kNW2) / 2;
+        work = (long long)cnt * ((q.g.kp + cpg - 1) / cpg);
+        cap = g_num_sms * (EY > 32 ? 1 : 16 / kNW2);
+    } else {
+        const int R = fast_rblk(q.nx, TX);
+        work = (long long)cnt * (q.nrt / R);
+        cap = g_num_sms * k3_ctas_per_sm(EX, k3_threads(TX, R));
+    }
+}
+
 template <typename TI>
 static int launch_fast(const Problem& q, StreamCtx& ctx, XcParams& p, int nb, cudaStream_t st)
 {
@@ -496,7 +517,14 @@ static int launch_fast(const Problem& q, StreamCtx& ctx, XcParams& p, int nb, cu
     // Sharing the SMs between a column kernel and row kernels deliberately (one CTA each, dependency-pipelined
     // sub-chunks) was measured and lost 4-10 %: both kinds are issue / shared-memory bound.
     int S = (int)g_opt_pipeline;
-    while (S > 1 && nb / S < 32) --S;
+    if (S > 2) S = 2;
+    if (S == 2) {                                          // each half must still fill every kernel's grid a few times over
+        for (int stage = 1; stage <= 3 && S == 2; ++stage) {
+            long long work; int cap;
+            fast_work(stage, q, nb / 2, work, cap);
+            if (work < 3LL * cap) S = 1;
+        }
+    }
     if (S <= 1) {
         FastParams fp{};
         if ((rc = fast_prepare(q, ctx, p, 0, nb, nb, fp)) != FB_OK) return rc;
@@ -505,7 +533,6 @@ static int launch_fast(const Problem& q, StreamCtx& ctx, XcParams& p, int nb, cu
         CU(cudaGetLastError());
         return FB_OK;
     }
-    if (S > 2) S = 2;
     if (!ctx.side) CU(cudaStreamCreateWithFlags(&ctx.side, cudaStreamNonBlocking));
     while ((int)ctx.order_ev.size() < 2) {
         cudaEvent_t e;
@@ -550,6 +577,7 @@ static int launch_chunk(const Problem& q, StreamCtx& ctx, const void* img0, cons
     if (q.fused) {
         p.tl = g.tl_fused; p.spitch = g.spitch;
         int nthr = g.smem_fused > 100 * 1024 ? 512 : 256;
+        if (g_opt_fused_threads) nthr = (int)g_opt_fused_threads;
         { ProfScope ps(ctx, st, SLOT_FUSED); fbk_fused<T, TI><<<nb, nthr, g.smem_fused, st>>>(p); }
         g_launches += 1;
         CU(cudaGetLastError());
@@ -817,6 +845,7 @@ extern "C" int fb_set_option(const char* name, long long value)
 {
     if (!name) return fail(FB_EINVAL, "null option name");
     std::lock_guard<std::mutex> lk(g_mu);
+    if (!strcmp(name, "fused_threads")) { if (value && (value < 64 || value > 1024 || value % 32)) return fail(FB_EINVAL, "fused_threads out of range"); g_opt_fused_threads = value; return FB_OK; }
     if (!strcmp(name, "pipeline")) { if (value < 1 || value > 16) return fail(FB_EINVAL, "pipeline out of range"); g_opt_pipeline = value; return FB_OK; }
     if (!strcmp(name, "max_radix")) { if (value < 5 || value > 16) return fail(FB_EINVAL, "max_radix out of range"); g_opt_max_radix = value; return FB_OK; }
     if (!strcmp(name, "ws_bytes")) { if (value < (1 << 20)) return fail(FB_EINVAL, "ws_bytes too small"); g_opt_ws_bytes = value; return FB_OK; }
