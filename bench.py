@@ -846,6 +846,9 @@ def main():
     import feabas_b200.cuda as fc
     L = fc._lib
     L.set_option('ws_bytes', int(args.ws_gib * (1 << 30)))
+    if os.environ.get('FB_PIPELINE_WAVES'):
+        L.set_option('pipeline_waves', int(os.environ['FB_PIPELINE_WAVES']))
+        config['pipeline_waves'] = int(os.environ['FB_PIPELINE_WAVES'])
     if os.environ.get('FB_FUSED_THREADS'):
         L.set_option('fused_threads', int(os.environ['FB_FUSED_THREADS']))
         config['fused_threads'] = int(os.environ['FB_FUSED_THREADS'])

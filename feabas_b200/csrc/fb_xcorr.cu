@@ -142,6 +142,7 @@ static long long g_opt_ws_bytes = 2LL << 30;
 static long long g_opt_host_chunk = 64LL << 20;
 static long long g_opt_profile = 0;
 static long long g_opt_fused_threads = 0;      // experiment switch: threads per CTA of the fused kernel (0: 512 above 100 KB, else 256)
+static long long g_opt_pipeline_waves = 1;     // ... when every kernel of a half still has this many work items per resident CTA
 static long long g_opt_pipeline = 2;           // fast path: a chunk runs as this many independent parts on separate streams (1: serial)
 static long long g_opt_max_radix = 16;         // largest radix of the shared-memory passes (experiment switch; set before first use)
 static long long g_opt_fast_flags = 0;       // experiment switches, see FastParams::flags (+16: K2 unbatched twiddles, +32: K3 8 lines)
@@ -518,11 +519,11 @@ static int launch_fast(const Problem& q, StreamCtx& ctx, XcParams& p, int nb, cu
     // sub-chunks) was measured and lost 4-10 %: both kinds are issue / shared-memory bound.
     int S = (int)g_opt_pipeline;
     if (S > 2) S = 2;
-    if (S == 2) {                                          // each half must still fill every kernel's grid a few times over
+    if (S == 2) {                                          // each half must still fill every kernel's grid (measured: +14 % at 16-24 pairs of 512^2)
         for (int stage = 1; stage <= 3 && S == 2; ++stage) {
             long long work; int cap;
             fast_work(stage, q, nb / 2, work, cap);
-            if (work < 3LL * cap) S = 1;
+            if (work < g_opt_pipeline_waves * cap) S = 1;
         }
     }
     if (S <= 1) {
@@ -846,6 +847,7 @@ extern "C" int fb_set_option(const char* name, long long value)
     if (!name) return fail(FB_EINVAL, "null option name");
     std::lock_guard<std::mutex> lk(g_mu);
     if (!strcmp(name, "fused_threads")) { if (value && (value < 64 || value > 1024 || value % 32)) return fail(FB_EINVAL, "fused_threads out of range"); g_opt_fused_threads = value; return FB_OK; }
+    if (!strcmp(name, "pipeline_waves")) { if (value < 1 || value > 64) return fail(FB_EINVAL, "pipeline_waves out of range"); g_opt_pipeline_waves = value; return FB_OK; }
     if (!strcmp(name, "pipeline")) { if (value < 1 || value > 16) return fail(FB_EINVAL, "pipeline out of range"); g_opt_pipeline = value; return FB_OK; }
     if (!strcmp(name, "max_radix")) { if (value < 5 || value > 16) return fail(FB_EINVAL, "max_radix out of range"); g_opt_max_radix = value; return FB_OK; }
     if (!strcmp(name, "ws_bytes")) { if (value < (1 << 20)) return fail(FB_EINVAL, "ws_bytes too small"); g_opt_ws_bytes = value; return FB_OK; }
