@@ -86,6 +86,13 @@ def seeded_xcorr_cases():
         'seed_512_nopad': dict(n=2, size=512, seed=22, max_shift=32, kwargs=dict(subpixel=True, pad=False)),
         'seed_280_pad': dict(n=2, size=280, seed=23, max_shift=20, kwargs=dict(subpixel=True, pad=True)),  # FFT 576
         'seed_600x400': dict(n=2, size=(600, 400), seed=24, max_shift=30, kwargs=dict(subpixel=False, pad=True)),  # 1200 x 800
+        # grids of the wider register-resident path
+        'seed_150_pad': dict(n=3, size=150, seed=25, max_shift=16, kwargs=dict(subpixel=True, pad=True)),      # FFT 300
+        'seed_300_pad': dict(n=2, size=300, seed=26, max_shift=24, kwargs=dict(subpixel=True, pad=True)),      # FFT 600
+        'seed_140_std': dict(n=2, size=140, seed=27, max_shift=16, kwargs=dict(subpixel=True, pad=True, conf_mode=1)),   # FFT 288, STD
+        'seed_1024_pad': dict(n=1, size=1024, seed=28, max_shift=32, kwargs=dict(subpixel=True, pad=True)),    # FFT 2048
+        'seed_2048_pad': dict(n=1, size=2048, seed=29, max_shift=32, kwargs=dict(subpixel=True, pad=True)),    # FFT 4096
+        'seed_192_none': dict(n=2, size=192, seed=30, max_shift=20, kwargs=dict(subpixel=True, pad=True, conf_mode=0)),  # FFT 384, NONE
     }
 
 
