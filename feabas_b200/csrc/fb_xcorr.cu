@@ -6,6 +6,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdint>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -111,9 +112,17 @@ struct DevTables {
     std::vector<int> radix;
 };
 
+struct GtMapKey {
+    void* gt; int nb, ny, kp, rblk;
+    bool operator<(const GtMapKey& o) const { return std::tie(gt, nb, ny, kp, rblk) < std::tie(o.gt, o.nb, o.ny, o.kp, o.rblk); }
+};
+
 struct StreamCtx {
+    std::mutex mu;                 // serialises the users of THIS context (its workspace and staging buffers); contexts of
+                                   // other devices / streams run concurrently
     int device = 0;
     void* ws = nullptr;            // staged-pipeline workspace
+    std::map<GtMapKey, CUtensorMap> gt_maps;     // encoded tensor maps of the workspace's G^T region (dropped with the workspace)
     size_t ws_bytes = 0;
     // host path
     cudaStream_t copy_stream = nullptr, own_stream = nullptr;
@@ -134,27 +143,32 @@ struct StreamCtx {
     long long prof_n[5] = {0, 0, 0, 0, 0};
 };
 
+// Locking: g_mu guards only the process-wide caches below (tables, the context map, attribute flags) and is never held
+// across a copy, a launch sequence or a synchronisation; the work of a call runs under its StreamCtx::mu.  Host threads
+// driving different devices (or different streams of one device) therefore overlap (feabas_b200/cuda/shard.py).
 static std::mutex g_mu;
 static std::map<std::tuple<int, int, int>, DevTables> g_tables;      // (device, n, is_double + 2 * wide radices)
-static std::map<std::pair<int, void*>, StreamCtx> g_ctx;              // (device, stream)
+static std::map<std::pair<int, void*>, StreamCtx> g_ctx;              // (device, stream the work runs on)
 static std::map<int, bool> g_attr_done;
-static long long g_opt_ws_bytes = 2LL << 30;
-static long long g_opt_host_chunk = 64LL << 20;
-static long long g_opt_profile = 0;
-static long long g_opt_fused_threads = 0;      // experiment switch: threads per CTA of the fused kernel (0: 512 above 100 KB, else 256)
-static long long g_opt_pipeline_waves = 1;     // ... when every kernel of a half still has this many work items per resident CTA
-static long long g_opt_pipeline = 2;           // fast path: a chunk runs as this many independent parts on separate streams (1: serial)
-static long long g_opt_max_radix = 16;         // largest radix of the shared-memory passes (experiment switch; set before first use)
-static long long g_opt_fast_flags = 0;       // experiment switches, see FastParams::flags (+16: K2 unbatched twiddles, +32: K3 8 lines)
+static void* const kOwnStreamKey = reinterpret_cast<void*>(~(uintptr_t)0);   // context of the host path's private stream
+static std::atomic<long long> g_opt_ws_bytes{2LL << 30};
+static std::atomic<long long> g_opt_host_chunk{64LL << 20};
+static std::atomic<long long> g_opt_profile{0};
+static std::atomic<long long> g_opt_fused_threads{0};      // experiment switch: threads per CTA of the fused kernel (0: 512 above 100 KB, else 256)
+static std::atomic<long long> g_opt_pipeline_waves{1};     // ... when every kernel of a half still has this many work items per resident CTA
+static std::atomic<long long> g_opt_pipeline{2};           // fast path: a chunk runs as this many independent parts on separate streams (1: serial)
+static std::atomic<long long> g_opt_max_radix{16};         // largest radix of the shared-memory passes (experiment switch; set before first use)
+static std::atomic<long long> g_opt_fast_flags{0};       // experiment switches, see FastParams::flags (+16: K2 unbatched twiddles, +32: K3 8 lines)
 
 template <typename T>
 static int get_tables(int device, int n, Plan1D& out, bool wide = false)
 {
+    std::lock_guard<std::mutex> lk(g_mu);
     auto key = std::make_tuple(device, n, (int)(sizeof(T) == 8) + (wide ? 2 : 0));
     auto it = g_tables.find(key);
     if (it == g_tables.end()) {
         DevTables t;
-        t.radix = wide ? radix_sequence(n, (int)g_opt_max_radix) : radix_sequence_basic(n);
+        t.radix = wide ? radix_sequence(n, (int)g_opt_max_radix.load()) : radix_sequence_basic(n);
         if ((int)t.radix.size() > kMaxPass) return fail(FB_ESIZE, "fft length %d needs too many passes", n);
         auto pos = digit_positions(n, t.radix);
         auto tw = twiddle_table<T>(n);
@@ -177,6 +191,7 @@ static std::map<std::tuple<int, int, int>, void*> g_wtables;           // (devic
 
 static int get_warp_table(int device, int n, int T, const cx<float>*& out)
 {
+    std::lock_guard<std::mutex> lk(g_mu);
     auto key = std::make_tuple(device, n, T);
     auto it = g_wtables.find(key);
     if (it == g_wtables.end()) {
@@ -370,37 +385,44 @@ static size_t fast_smem(int n, int nw)
     return ((size_t)lines * (n + E + 16) + (kLaneTwiddles ? 0 : n)) * sizeof(cx<float>);
 }
 
-static int g_num_sms = 0;
+static std::atomic<int> g_num_sms{0};
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode_tiled = nullptr;
-static bool g_encode_tried = false;
+static std::once_flag g_encode_once;
 
 // G^T of `nb` pairs as a 4-D tensor of 8-byte elements, innermost first: [rblk][kp][2][nb * ny / rblk];
 // box = one column of one plane of one pair: [rblk][1][1][ny / rblk] = ny elements in natural y order
-static bool make_gt_map(CUtensorMap* map, void* gt, int nb, int ny, int kp, int rblk)
+static bool make_gt_map(StreamCtx& ctx, CUtensorMap* map, void* gt, int nb, int ny, int kp, int rblk)
 {
-    if (!g_encode_tried) {
-        g_encode_tried = true;
+    std::call_once(g_encode_once, [] {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
             qres == cudaDriverEntryPointSuccess)
             g_encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
         cudaGetLastError();
-    }
+    });
     if (!g_encode_tiled) return false;
+    // the matcher layers send the same few batch shapes over and over: encode once per (address, shape)
+    const GtMapKey key{gt, nb, ny, kp, rblk};
+    auto hit = ctx.gt_maps.find(key);
+    if (hit != ctx.gt_maps.end()) { *map = hit->second; return true; }
     const int tiles = ny / rblk, boxt = tiles > 256 ? 256 : tiles;      // a box dimension is at most 256: K2 stores long columns in pieces
     if (tiles % boxt) return false;
     const cuuint64_t dims[4] = {(cuuint64_t)rblk, (cuuint64_t)kp, 2, (cuuint64_t)nb * (ny / rblk)};
     const cuuint64_t strides[3] = {(cuuint64_t)rblk * 8, (cuuint64_t)kp * rblk * 8, (cuuint64_t)2 * kp * rblk * 8};
     const cuuint32_t box[4] = {(cuuint32_t)rblk, 1, 1, (cuuint32_t)boxt};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
-    return g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, gt, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    if (g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, gt, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+    if (ctx.gt_maps.size() > 256) ctx.gt_maps.clear();
+    ctx.gt_maps.emplace(key, *map);
+    return true;
 }
 
 // Parameters of the sub-range [lo, lo + cnt) of a chunk of nb pairs (workspace carved by pair index).
@@ -427,7 +449,7 @@ static int fast_prepare(const Problem& q, StreamCtx& ctx, const XcParams& p, int
     fp.rblk = fast_rblk(q.nx, TX);                       // rows per K3 tile
     if (q.nx == 1024 && (g_opt_fast_flags & 32)) fp.rblk = 4;
     fp.flags = (int)(g_opt_fast_flags & ~(16 | 32));
-    fp.use_tma = make_gt_map(&fp.gt_map, fp.GT, cnt, q.ny, g.kp, fp.rblk) ? 1 : 0;
+    fp.use_tma = make_gt_map(ctx, &fp.gt_map, fp.GT, cnt, q.ny, g.kp, fp.rblk) ? 1 : 0;
     fp.gt_tiles = q.ny / fp.rblk;
     fp.gt_pieces = fp.gt_tiles > 256 ? fp.gt_tiles / 256 : 1;
     x.G = fp.GT; x.gt_layout = fp.rblk; x.nrt = q.nrt; x.out_scale = x.scale;
@@ -435,6 +457,10 @@ static int fast_prepare(const Problem& q, StreamCtx& ctx, const XcParams& p, int
     fp.x = x;
     return FB_OK;
 }
+
+// K4's scratch: a 4-line tile (the three rows around the peak at once) when it fits, else one line at a time
+template <typename T> static bool finalize_narrow(int nx) { return (size_t)nx * 4 * sizeof(cx<T>) + 2048 > kMaxSmem; }
+template <typename T> static size_t finalize_smem(int nx) { return (size_t)nx * (finalize_narrow<T>(nx) ? 1 : 4) * sizeof(cx<T>) + 2048; }
 
 // stage 1: K1 rows forward, 2: K2 columns, 3: K3 rows inverse, 4: K4 finalize -- of the cnt pairs described by fp
 static int fast_stage(int stage, const Problem& q, StreamCtx& ctx, const FastParams& fp, int cnt, int in_dtype, cudaStream_t st)
@@ -479,7 +505,7 @@ static int fast_stage(int stage, const Problem& q, StreamCtx& ctx, const FastPar
         if (!fast_dispatch(3, fp, l)) return fail(FB_ESIZE, "no fast-path inverse row kernel for %d points", q.nx);
     } else {
         ProfScope ps(ctx, st, SLOT_FINALIZE);
-        fbk_finalize<float><<<cnt, 256, (size_t)q.nx * 4 * sizeof(cx<float>) + 2048, st>>>(fp.x);
+        fbk_finalize<float><<<cnt, 256, finalize_smem<float>(q.nx), st>>>(fp.x);
     }
     g_launches += 1;
     return FB_OK;
@@ -509,7 +535,7 @@ template <typename TI>
 static int launch_fast(const Problem& q, StreamCtx& ctx, XcParams& p, int nb, cudaStream_t st)
 {
     int rc;
-    if (!g_num_sms) { cudaDeviceProp pr; CU(cudaGetDeviceProperties(&pr, ctx.device)); g_num_sms = pr.multiProcessorCount; }
+    if (!g_num_sms) { int sms = 0; CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx.device)); g_num_sms = sms; }
     const int in_dtype = std::is_same<TI, float>::value ? FB_F32 : FB_U8;
     // Two-stream schedule: the chunk is cut into S (2) independent parts, each running its four kernels on its own
     // stream (part 0 on the caller's).  The kernels are persistent and fill the GPU, so the streams mostly
@@ -575,6 +601,7 @@ static int launch_chunk(const Problem& q, StreamCtx& ctx, const void* img0, cons
     p.fpitch = g.fpitch; p.dx = dx; p.dy = dy; p.conf = conf; p.peak = peak; p.mir = mir;
     p.conf_mode = q.conf_mode; p.subpixel = q.subpixel; p.scale = 1.0 / ((double)q.ny * (double)q.nx);
     p.out_scale = 1.0;
+    p.fin_narrow = (!q.fused && finalize_narrow<T>(q.nx)) ? 1 : 0;
     if (q.fused) {
         p.tl = g.tl_fused; p.spitch = g.spitch;
         int nthr = g.smem_fused > 100 * 1024 ? 512 : 256;
@@ -610,7 +637,7 @@ static int launch_chunk(const Problem& q, StreamCtx& ctx, const void* img0, cons
     }
     p.n = nb;
     { ProfScope ps(ctx, st, SLOT_ROWS_INV); fbk_rows_inverse<T><<<nb * q.nrt, g.nthreads_row, g.smem_row, st>>>(p); }
-    { ProfScope ps(ctx, st, SLOT_FINALIZE); fbk_finalize<T><<<nb, 256, (size_t)q.nx * 4 * sizeof(cx<T>) + 2048, st>>>(p); }
+    { ProfScope ps(ctx, st, SLOT_FINALIZE); fbk_finalize<T><<<nb, 256, finalize_smem<T>(q.nx), st>>>(p); }
     g_launches += 4;
     CU(cudaGetLastError());
     return FB_OK;
@@ -639,7 +666,7 @@ static int run_device(const Problem& q, StreamCtx& ctx, const void* img0, const 
         if (chunk > fit) chunk = (int)fit;
         size_t need = (size_t)chunk * q.ws_per_pair;
         if (need > ctx.ws_bytes) {
-            if (ctx.ws) { CU(cudaStreamSynchronize(st)); CU(cudaFree(ctx.ws)); ctx.ws = nullptr; ctx.ws_bytes = 0; }
+            if (ctx.ws) { CU(cudaStreamSynchronize(st)); CU(cudaFree(ctx.ws)); ctx.ws = nullptr; ctx.ws_bytes = 0; ctx.gt_maps.clear(); }
             if (cudaMalloc(&ctx.ws, need) != cudaSuccess) { cudaGetLastError(); return fail(FB_ENOMEM, "workspace of %zu bytes", need); }
             ctx.ws_bytes = need;
         }
@@ -665,9 +692,10 @@ static int get_ctx(int device, void* stream, StreamCtx*& out)
     }
     if (device < 0 || device >= ndev) return fail(FB_EINVAL, "device %d out of range (%d devices)", device, ndev);
     CU(cudaSetDevice(device));
+    std::lock_guard<std::mutex> lk(g_mu);
     int rc = set_attrs(device);
     if (rc != FB_OK) return rc;
-    StreamCtx& c = g_ctx[std::make_pair(device, stream)];
+    StreamCtx& c = g_ctx[std::make_pair(device, stream)];      // map nodes are stable: the pointer outlives the lock
     c.device = device;
     out = &c;
     return FB_OK;
@@ -686,9 +714,9 @@ extern "C" int fb_xcorr_batch_device(const void* img0, const void* img1, int n, 
     if (rc != FB_OK) return rc;
     if (n == 0) return FB_OK;
     if (!img0 || !img1 || !dx || !dy || !conf) return fail(FB_EINVAL, "null pointer");
-    std::lock_guard<std::mutex> lk(g_mu);
     StreamCtx* ctx;
     if ((rc = get_ctx(device, stream, ctx)) != FB_OK) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
     return run_device(q, *ctx, img0, img1, n, dx, dy, conf, peak, mirror, (cudaStream_t)stream);
 }
 
@@ -702,9 +730,9 @@ extern "C" int fb_xcorr_batch_device_ex(const void* img0, const void* img1, int 
     if (rc != FB_OK) return rc;
     if (n == 0) return FB_OK;
     if (!img0 || !img1 || !dx || !dy || !conf) return fail(FB_EINVAL, "null pointer");
-    std::lock_guard<std::mutex> lk(g_mu);
     StreamCtx* ctx;
     if ((rc = get_ctx(device, stream, ctx)) != FB_OK) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
     return run_device(q, *ctx, img0, img1, n, dx, dy, conf, peak, mirror, (cudaStream_t)stream);
 }
 
@@ -718,10 +746,12 @@ extern "C" int fb_xcorr_batch_host(const void* img0, const void* img1, int n, in
     if (rc != FB_OK) return rc;
     if (n == 0) return FB_OK;
     if (!img0 || !img1 || !dx || !dy || !conf) return fail(FB_EINVAL, "null pointer");
-    std::lock_guard<std::mutex> lk(g_mu);
+    // a NULL stream means "the library's own stream" here, not the legacy default stream the device entry points use
+    // for NULL: the context (workspace) is keyed by the stream the kernels really run on
     StreamCtx* cp;
-    if ((rc = get_ctx(device, stream, cp)) != FB_OK) return rc;
+    if ((rc = get_ctx(device, stream ? stream : kOwnStreamKey, cp)) != FB_OK) return rc;
     StreamCtx& c = *cp;
+    std::lock_guard<std::mutex> lk(c.mu);
     if (!c.copy_stream) {
         CU(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
@@ -859,10 +889,16 @@ extern "C" int fb_set_option(const char* name, long long value)
 
 extern "C" int fb_profile_read(int device, void* stream, double* ms5, long long* launches5, int reset)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
-    auto it = g_ctx.find(std::make_pair(device, stream));
-    if (it == g_ctx.end()) return fail(FB_EINVAL, "no context for device %d / stream %p", device, stream);
-    StreamCtx& c = it->second;
+    StreamCtx* cp = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_ctx.find(std::make_pair(device, stream));
+        if (it == g_ctx.end()) it = g_ctx.find(std::make_pair(device, stream ? stream : kOwnStreamKey));
+        if (it == g_ctx.end()) return fail(FB_EINVAL, "no context for device %d / stream %p", device, stream);
+        cp = &it->second;
+    }
+    StreamCtx& c = *cp;
+    std::lock_guard<std::mutex> lk(c.mu);
     CU(cudaSetDevice(device));
     for (auto& t : c.prof_pending) {
         float ms = 0.f;
@@ -891,6 +927,7 @@ extern "C" int fb_release(int device)
     for (auto it = g_ctx.begin(); it != g_ctx.end();) {
         StreamCtx& c = it->second;
         if (device >= 0 && c.device != device) { ++it; continue; }
+        c.mu.lock();                           // waits for a call in flight on this context (callers must not START one now)
         cudaSetDevice(c.device);
         cudaDeviceSynchronize();
         if (c.ws) cudaFree(c.ws);
@@ -907,6 +944,7 @@ extern "C" int fb_release(int device)
         for (auto e : c.order_ev) cudaEventDestroy(e);
         if (c.copy_stream) cudaStreamDestroy(c.copy_stream);
         if (c.own_stream) cudaStreamDestroy(c.own_stream);
+        c.mu.unlock();
         it = g_ctx.erase(it);
     }
     for (auto it = g_tables.begin(); it != g_tables.end();) {

@@ -72,6 +72,8 @@ struct XcParams {
     int gt_layout;        // K4: != 0: G holds the fast path's conjugated surfaces, tiled
                           //     [ny / gt_layout][P|Q][kx][gt_layout] (gt_layout = rows per K3 tile), and
                           //     the partial's idx only identifies the ROW of the maximum
+    int fin_narrow;       // K4: != 0: the three rows around the peak are recomputed one at a time (scratch of ONE
+                          //     line of nx points instead of a 4-line tile; long lines, e.g. FFT 8192 or float64 4096)
 };
 
 template <typename T> struct Acc {
@@ -331,8 +333,10 @@ FB_DEV void finalize_pair(const XcParams& p, int pair, const Acc<T>& best, const
     const int nx = p.nx, ny = p.ny, kp = p.kp;
     const int py = best.idx / nx;
     int px = best.idx - py * nx;
-    const int pitch = 4;
-    if (p.subpixel || p.gt_layout) {
+    const int pitch = p.fin_narrow ? 1 : 4;
+    T* keep = reinterpret_cast<T*>(s + (size_t)nx * pitch);                 // narrow: c[line][x - 1, x, x + 1]
+    Acc<T>* red = reinterpret_cast<Acc<T>*>(keep + 16);
+    if ((p.subpixel || p.gt_layout) && !p.fin_narrow) {
         for (int idx = tid; idx < kp * 3; idx += nthr) {
             int l = idx / kp, k = idx - l * kp;
             int y = py - 1 + l;
@@ -354,20 +358,48 @@ FB_DEV void finalize_pair(const XcParams& p, int pair, const Acc<T>& best, const
             }
             FB_SYNC();
         }
-    }
-    if (p.gt_layout) {
-        // locate the maximum inside row py (np.argmax: first occurrence)
-        Acc<T> a; acc_init(a);
-        for (int x = tid; x < nx; x += nthr) acc_take(a, s[(size_t)x * pitch + 1].x, x);
-        Acc<T>* red = reinterpret_cast<Acc<T>*>(s + (size_t)nx * pitch);
-        a = block_reduce<T>(a, red, tid, nthr);
-        px = a.idx;
+        if (p.gt_layout) {
+            // locate the maximum inside row py (np.argmax: first occurrence)
+            Acc<T> a; acc_init(a);
+            for (int x = tid; x < nx; x += nthr) acc_take(a, s[(size_t)x * pitch + 1].x, x);
+            a = block_reduce<T>(a, red, tid, nthr);
+            px = a.idx;
+        }
+    } else if (p.subpixel || p.gt_layout) {
+        // one line at a time, the peak's own row first (it yields px on the tiled layout)
+        for (int step = 0; step < 3; ++step) {
+            const int l = step == 0 ? 1 : (step == 1 ? 0 : 2);
+            if (l != 1 && !p.subpixel) break;
+            int y = py - 1 + l;
+            y = y < 0 ? y + ny : (y >= ny ? y - ny : y);
+            const size_t ro = p.gt_layout ? (size_t)(y / p.gt_layout) * 2 * kp * p.gt_layout + (y % p.gt_layout)
+                                          : (size_t)y * rpitch;
+            for (int k = tid; k < kp; k += nthr) rows_inverse_fill<T>(p, Pb + ro, mirror ? Qb + ro : nullptr, s, 1, 0, k, kp, ks);
+            FB_SYNC();
+            fft_lines<T, true, MAXR>(p.px, s, 1, 1, tid, nthr);
+            if (p.norm) {
+                const T* norm = reinterpret_cast<const T*>(p.norm);
+                for (int x = tid; x < nx; x += nthr) s[x].x = s[x].x / norm[(size_t)y * nx + x];
+                FB_SYNC();
+            }
+            if (l == 1 && p.gt_layout) {
+                Acc<T> a; acc_init(a);
+                for (int x = tid; x < nx; x += nthr) acc_take(a, s[x].x, x);
+                a = block_reduce<T>(a, red, tid, nthr);
+                px = a.idx;
+            }
+            if (tid == 0) {
+                const int xm = px == 0 ? nx - 1 : px - 1, xp = px == nx - 1 ? 0 : px + 1;
+                keep[l * 3 + 0] = s[xm].x; keep[l * 3 + 1] = s[px].x; keep[l * 3 + 2] = s[xp].x;
+            }
+            FB_SYNC();
+        }
     }
     if (tid == 0) {
         float ox = 0.f, oy = 0.f;
         if (p.subpixel) {
             const int xm = px == 0 ? nx - 1 : px - 1, xp = px == nx - 1 ? 0 : px + 1;
-#define FB_C(j, xi) (s[(xi) * pitch + ((j) + 1)].x)
+#define FB_C(j, xi) (p.fin_narrow ? keep[((j) + 1) * 3 + ((xi) == px ? 1 : ((xi) == xm ? 0 : 2))] : s[(xi) * pitch + ((j) + 1)].x)
             T c00 = FB_C(0, px);
             T gx = (FB_C(0, xp) - FB_C(0, xm)) / T(2);
             T gy = (FB_C(1, px) - FB_C(-1, px)) / T(2);
@@ -502,7 +534,7 @@ FB_DEV void k4_finalize(const XcParams& p, int bid, int tid, int nthr, unsigned 
 {
     const bool mirror = p.conf_mode == CONF_MIRROR;
     cx<T>* s = reinterpret_cast<cx<T>*>(smem);
-    Acc<T>* red = reinterpret_cast<Acc<T>*>(smem + (size_t)p.nx * 4 * sizeof(cx<T>));
+    Acc<T>* red = reinterpret_cast<Acc<T>*>(smem + (size_t)p.nx * (p.fin_narrow ? 1 : 4) * sizeof(cx<T>) + 16 * sizeof(T));
     Acc<T> acc; acc_init(acc);
     for (int i = tid; i < p.nrt; i += nthr) {
         const Partial& q = p.part[(size_t)bid * p.nrt + i];

@@ -653,8 +653,10 @@ _MESH_FACTORY = None
 
 
 def set_mesh_factory(factory):
-    """``factory(bounds, mesh_size, min_num_blocks, uid, resolution) -> mesh``.  ``None`` restores the default:
-    the reference's ``Mesh.from_bbox`` when FEABAS imports, else the affine stand-in."""
+    """``factory(bounds, mesh_size, min_num_blocks, uid, resolution) -> mesh``.  ``None`` restores the default, the
+    affine stand-in ``AffineMesh.from_bbox``.  A FEABAS installation plugs its elastic meshes in with
+    ``set_mesh_factory(lambda b, s, n, uid, res: Mesh.from_bbox(b, cartesian=True, mesh_size=s, min_num_blocks=n,
+    uid=uid, resolution=res))`` (feabas/matcher.py:354-359)."""
     global _MESH_FACTORY
     _MESH_FACTORY = factory
 

@@ -10,8 +10,9 @@ for its worker processes).
 Two launch models:
 
 * one process per GPU under ``torch.distributed`` (``torchrun``): ``shard_range`` + ``gather_concat``;
-* one process, one host thread per GPU: ``xcorr_fft_multi_gpu`` (the C ABI is re-entrant across
-  devices; each thread drives its own device's streams).
+* one process, one host thread per GPU: ``xcorr_fft_multi_gpu`` (the C ABI only serialises callers of the SAME
+  (device, stream) context -- fb_xcorr.cu ``StreamCtx::mu`` -- so each thread drives its own device concurrently;
+  ctypes releases the GIL for the duration of the call).
 """
 import threading
 
@@ -60,6 +61,22 @@ def gather_concat(parts, group=None):
     return tuple(out)
 
 
+def _stack_ptp(stack):
+    """np.ptp of a whole stack (numpy array or tensor) as a Python float."""
+    if torch is not None and isinstance(stack, torch.Tensor):
+        return float(stack.max() - stack.min()) if stack.dtype.is_floating_point else float(int(stack.max()) - int(stack.min()))
+    stack = np.asarray(stack)
+    return float(np.ptp(stack if stack.dtype.kind == 'f' else stack.astype(np.float64)))
+
+
+def _global_ptp(img0, img1, kwargs):
+    """The mask term of the band-pass uses np.ptp of the WHOLE stack (feabas/common.py:369): take it before the
+    stack is cut into shards, so that the result does not depend on the number of GPUs."""
+    if kwargs.get('sigma', 0) > 0 and 'ptp' not in kwargs and (kwargs.get('mask0') is not None or kwargs.get('mask1') is not None):
+        kwargs = dict(kwargs, ptp=(_stack_ptp(img0), _stack_ptp(img1)))
+    return kwargs
+
+
 def xcorr_fft_sharded(img0, img1, conf_mode=2, group=None, compute=None, **kwargs):
     """``xcorr_fft`` over a batch that every rank holds (or can index) in full: rank r computes pairs
     ``shard_range(N, world, r)`` on its own GPU and all ranks return the full ``(dx, dy, conf)``.
@@ -70,6 +87,7 @@ def xcorr_fft_sharded(img0, img1, conf_mode=2, group=None, compute=None, **kwarg
     world, rank = _world(group)
     n = len(img0)
     lo, hi = shard_range(n, world, rank)
+    kwargs = _global_ptp(img0, img1, kwargs)
     if hi > lo:
         dx, dy, conf = compute(img0[lo:hi], img1[lo:hi], conf_mode=conf_mode, **kwargs)
     else:
@@ -102,6 +120,7 @@ def xcorr_fft_multi_gpu(img0, img1, conf_mode=2, devices=None, compute=None, **k
     n = len(img0)
     ranges = shard_ranges(n, len(devices))
     results, errors = [None] * len(devices), []
+    kwargs = _global_ptp(img0, img1, kwargs)
 
     def work(i):
         lo, hi = ranges[i]

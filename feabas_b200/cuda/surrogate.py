@@ -102,6 +102,23 @@ class AffineMesh:
         eye = (np.eye(2), np.zeros(2))
         self._maps = {MESH_GEAR_INITIAL: eye, MESH_GEAR_FIXED: eye, MESH_GEAR_MOVING: eye, MESH_GEAR_STAGING: eye}
 
+    @classmethod
+    def from_bbox(cls, bbox, cartesian=False, **kwargs):
+        """Same call as ``Mesh.from_bbox`` (feabas/mesh.py:403-437).  The reference puts the outer vertices of the
+        grid at ``bbox - 0.5`` (mesh.py:426-427): the mesh covers the AREA of the pixels ``xmin .. xmax - 1`` whose
+        centres sit at integer coordinates.  ``mesh_size`` / ``min_num_blocks`` (the grid's density) have no
+        meaning for a single affine map and are ignored."""
+        x0, y0, x1, y1 = (float(v) for v in bbox)
+        return cls((x0 - 0.5, y0 - 0.5, x1 - 0.5, y1 - 0.5), uid=kwargs.get('uid', 0),
+                   resolution=kwargs.get('resolution', DEFAULT_RESOLUTION))
+
+    def covered_rect(self):
+        """(xmin, ymin, xmax, ymax), INITIAL gear: the mesh region shrunk by half a pixel, i.e. what
+        ``MeshRenderer.from_mesh`` keeps as ``covered_region`` (feabas/renderer.py:98-101); only source positions
+        STRICTLY inside it count as covered (``shapely.contains_xy``, renderer.py:447)."""
+        x0, y0, x1, y1 = self.bounds
+        return (x0 + 0.5, y0 + 0.5, x1 - 0.5, y1 - 0.5)
+
     # -- state -------------------------------------------------------------------------------
     def copy(self):
         other = AffineMesh(self.bounds, uid=self.uid, resolution=self.resolution)

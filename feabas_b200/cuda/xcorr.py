@@ -176,7 +176,9 @@ def xcorr_fft(img0, img1, conf_mode=FFT_CONF_MIRROR, **kwargs):
     Args and kwargs as the reference: ``sigma`` (0), ``mask0``/``mask1`` (None),
     ``normalize`` (False), ``subpixel`` (False), ``pad`` (True).  Extra,
     non-reference kwargs: ``device`` (GPU index for host input), ``return_debug``
-    (also return a dict with the surface maxima), ``force`` ('fused'|'staged').
+    (also return a dict with the surface maxima), ``force`` ('fused'|'staged'),
+    ``ptp`` (``sigma`` > 0 with masks: the ``np.ptp`` pair ``(ptp0, ptp1)`` of the
+    WHOLE stacks when this call only sees a shard of them, common.py:369).
     Returns ``(dx, dy, conf)``: float64, float64, float32 numpy arrays of length N.
     """
     sigma = kwargs.get('sigma', 0)
@@ -195,8 +197,10 @@ def xcorr_fft(img0, img1, conf_mode=FFT_CONF_MIRROR, **kwargs):
         b = to_device(img1, a.device.index)
         if ndim > 3:
             a, b = a.movedim(-1, 1).contiguous(), b.movedim(-1, 1).contiguous()
-        a = masked_dog_filter(a, sigma, mask=kwargs.get('mask0', None))
-        b = masked_dog_filter(b, sigma, mask=kwargs.get('mask1', None))
+        ptp = kwargs.get('ptp', None)
+        ptp0, ptp1 = (None, None) if ptp is None else (tuple(ptp) if np.ndim(ptp) else (ptp, ptp))
+        a = masked_dog_filter(a, sigma, mask=kwargs.get('mask0', None), ptp=ptp0)
+        b = masked_dog_filter(b, sigma, mask=kwargs.get('mask1', None), ptp=ptp1)
         if ndim > 3:
             a, b = a.movedim(1, -1), b.movedim(1, -1)
         img0, img1 = a, b

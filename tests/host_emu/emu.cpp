@@ -63,6 +63,7 @@ static int run(const void* img0, const void* img1, int n, int h0, int w0, int h1
     g.esize = (int)sizeof(cx<T>); g.mirror = conf_mode == CONF_MIRROR;
     if (!choose_tiles(g)) return -3;
     const bool fused = path == 1 || (path == 0 && g.fused);
+    const bool narrow = path == 3;                 // staged pipeline, K4 recomputing one surface row at a time
     HostPlan<T> px(nx, fused), py(ny, fused);
     XcParams p{};
     p.img0 = img0; p.img1 = img1; p.n = n; p.h0 = h0; p.w0 = w0; p.h1 = h1; p.w1 = w1;
@@ -87,9 +88,10 @@ static int run(const void* img0, const void* img1, int n, int h0, int w0, int h1
     int nct = (g.kp + p.tc - 1) / p.tc;
     run_grid(n * nct, nthr, g.smem_col, [&](int b, int t, int nt, unsigned char* sm) { k2_columns<T>(p, b, t, nt, sm); });
     run_grid(n * p.nrt, nthr, g.smem_row, [&](int b, int t, int nt, unsigned char* sm) { k3_rows_inverse<T>(p, b, t, nt, sm); });
-    size_t sm4 = (size_t)nx * 4 * sizeof(cx<T>) + 2048;
+    p.fin_narrow = narrow ? 1 : 0;
+    size_t sm4 = (size_t)nx * (narrow ? 1 : 4) * sizeof(cx<T>) + 2048;
     run_grid(n, nthr, sm4, [&](int b, int t, int nt, unsigned char* sm) { k4_finalize<T>(p, b, t, nt, sm); });
-    return 2;
+    return narrow ? 3 : 2;
 }
 
 extern "C" int emu_xcorr(const void* img0, const void* img1, int n, int h0, int w0, int h1, int w1, int dtype,

@@ -85,6 +85,19 @@ def test_thread_count_independent(emu):
             np.testing.assert_array_equal(x, y)
 
 
+def test_finalize_one_row_at_a_time(emu, golden_small):
+    """K4's narrow variant (long lines: FFT 8192 float32 / 4096 float64, where a 4-line tile no longer fits in
+    shared memory) recomputes the rows around the peak one by one: same numbers as the 3-rows-at-once variant."""
+    for name in ('roll_f32_sub', 'diffshape_pad', 'stitch_fine_pad', 'uint8_in', 'thumb50_std', 'edge_wrap_nopad', 'odd_sizes'):
+        rec = golden_small[name]
+        kw = case_kwargs(rec)
+        wide = emu(rec['img0'], rec['img1'], path=2, **kw)
+        narrow = emu(rec['img0'], rec['img1'], path=3, **kw)
+        assert narrow[3] == 3
+        for x, y in zip(wide[:3], narrow[:3]):
+            np.testing.assert_array_equal(x, y)
+
+
 def test_register_fft_and_pass_planner(tmp_path):
     """fb_gfft.cuh (compile-time mixed-radix register FFT: the fast path's per-lane transform for lengths with
     factors 3 / 5 and the composite-radix butterfly of the fused kernel's passes) against a direct DFT, forward and
