@@ -340,8 +340,9 @@ struct CropParams {
     double ox, oy;         // integer-valued origin of the reference's source crop (common.py:300-304)
     float fill;
     void* out;
-    int has_cover;         // only pixels whose source position lies inside [cx0, cx1) x [cy0, cy1) are rendered
+    int has_cover;         // only pixels whose source position lies STRICTLY inside (cx0, cx1) x (cy0, cy1) are rendered
     double cx0, cy0, cx1, cy1;
+    const unsigned char* block_full;   // optional [n]: nonzero = the whole block counts as covered (renderer.py:443-444)
     unsigned char* mask_out;
 };
 
@@ -366,7 +367,7 @@ __global__ void __launch_bounds__(256) fbk_crop_blocks(const __grid_constant__ C
     const double xs = __dadd_rn(__dadd_rn(__dmul_rn(xx, q[4]), __dmul_rn(yy, q[5])), q[6]);
     const double ys = __dadd_rn(__dadd_rn(__dmul_rn(xx, q[7]), __dmul_rn(yy, q[8])), q[9]);
     if (p.has_cover) {
-        const bool inside = xs >= p.cx0 && xs < p.cx1 && ys >= p.cy0 && ys < p.cy1;
+        const bool inside = (p.block_full && p.block_full[b]) || (xs > p.cx0 && xs < p.cx1 && ys > p.cy0 && ys < p.cy1);
         if (p.mask_out) p.mask_out[((size_t)b * p.bh + row) * p.bw + col] = inside ? 1 : 0;
         if (!inside) {
             reinterpret_cast<TS*>(p.out)[((size_t)b * p.bh + row) * p.bw + col] = (TS)p.fill;
@@ -420,13 +421,14 @@ __global__ void __launch_bounds__(256) fbk_crop_blocks4(const __grid_constant__ 
     const TS* img = reinterpret_cast<const TS*>(p.img);
     TS px[4];
     unsigned char inside4[4];
+    const bool whole = p.has_cover && p.block_full && p.block_full[b];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const double xx = __dadd_rn(q0, __dmul_rn((double)(col0 + k), q2));
         const double xs = __dadd_rn(__dadd_rn(__dmul_rn(xx, a00), ya), t0);
         const double ys = __dadd_rn(__dadd_rn(__dmul_rn(xx, a01), yb), t1);
         bool inside = true;
-        if (p.has_cover) inside = xs >= p.cx0 && xs < p.cx1 && ys >= p.cy0 && ys < p.cy1;
+        if (p.has_cover) inside = whole || (xs > p.cx0 && xs < p.cx1 && ys > p.cy0 && ys < p.cy1);
         inside4[k] = inside ? 1 : 0;
         if (!inside) { px[k] = (TS)p.fill; continue; }
         const float xf = (float)__dsub_rn(xs, p.ox), yf = (float)__dsub_rn(ys, p.oy);
@@ -642,7 +644,7 @@ extern "C" int fb_resize_nearest(const unsigned char* src, int n, int h, int w, 
 
 extern "C" int fb_crop_blocks(const void* img, int ih, int iw, int in_dtype, const double* blocks, int n, int bh, int bw,
                               double origin_x, double origin_y, double fillval, void* out,
-                              const double* cover, unsigned char* mask_out, int device, void* stream)
+                              const double* cover, const unsigned char* block_full, unsigned char* mask_out, int device, void* stream)
 {
     if (n < 0 || ih < 1 || iw < 1 || bh < 1 || bw < 1) return fb_failf(FB_EINVAL, "bad shape");
     if (in_dtype != FB_F32 && in_dtype != FB_U8) return fb_failf(FB_EINVAL, "crop_blocks: dtype %d not supported", in_dtype);
@@ -655,7 +657,7 @@ extern "C" int fb_crop_blocks(const void* img, int ih, int iw, int in_dtype, con
     p.img = img; p.ih = ih; p.iw = iw; p.blocks = blocks; p.n = n; p.bh = bh; p.bw = bw;
     p.ox = origin_x; p.oy = origin_y; p.out = out;
     p.has_cover = cover ? 1 : 0; p.mask_out = cover ? mask_out : nullptr;
-    if (cover) { p.cx0 = cover[0]; p.cy0 = cover[1]; p.cx1 = cover[2]; p.cy1 = cover[3]; }
+    if (cover) { p.cx0 = cover[0]; p.cy0 = cover[1]; p.cx1 = cover[2]; p.cy1 = cover[3]; p.block_full = block_full; }
     p.fill = in_dtype == FB_U8 ? (float)(fillval < 0 ? 0 : (fillval > 255 ? 255 : rint(fillval))) : (float)fillval;
     const bool vec4 = bw % 4 == 0 && ((size_t)out % 16 == 0) && (!p.mask_out || (size_t)p.mask_out % 4 == 0) && !getenv("FB_CROP_SCALAR");
     if (vec4) {

@@ -183,48 +183,94 @@ def crop_blocks_masked(img, blocks, block_shape, origin=None, fillval=0, cover=N
     (see ``fb_crop_blocks`` in include/feabas_cuda.h).  ``origin``: the integer (x, y) origin OpenCV's
     fixed-point coordinates are taken from; default = what the reference computes for the batch,
     ``floor(min field) - 4`` (common.py:300-304).  ``cover``: (xmin, ymin, xmax, ymax) of the source region
-    the mesh covers, or None.  Returns ``(stack, mask)``; ``mask`` (uint8, 1 = rendered) is None without cover.
-    """
+    the mesh covers (``AffineMesh.covered_rect`` in image pixel coordinates), or None.  The reference's rule
+    (feabas/renderer.py:436-449): a block whose footprint sticks out of the covered region by less than one square
+    pixel is rendered whole, otherwise only the pixels whose source position is strictly inside the region.
+    Returns ``(stack, mask)``; ``mask`` (uint8, 1 = rendered) is None when every block is rendered whole."""
     bh, bw = int(block_shape[0]), int(block_shape[1])
     blk_host = None
     if not is_cuda_tensor(blocks):
         blk_host = np.ascontiguousarray(blocks, dtype=np.float64).reshape(-1, 10)
         blocks = torch.from_numpy(blk_host).to(img.device, non_blocking=True)
     n = blocks.shape[0]
+    if out is None:
+        out = torch.empty((n, bh, bw), dtype=img.dtype, device=img.device)
+    mask, cptr, mptr, fptr = None, None, None, None
+    whole = None
+    if cover is not None and n:
+        if blk_host is None:
+            blk_host = blocks.cpu().numpy()
+        whole = footprint_uncovered_area(blk_host, bh, bw, cover) < 1
     if origin is None:
         if blk_host is None:
             blk_host = blocks.cpu().numpy()
-        origin = batch_origin(blk_host, bh, bw) if n else (0, 0)
-    if out is None:
-        out = torch.empty((n, bh, bw), dtype=img.dtype, device=img.device)
-    mask, cptr, mptr = None, None, None
-    if cover is not None and blk_host is not None and n and _blocks_inside(blk_host, bh, bw, cover):
-        cover = None            # every pixel of every block is covered: same stack, no mask to write / reduce / read back
+        # the reference takes the origin of its source crop from the RENDERED pixels (common.py:300-304): every pixel
+        # of a block rendered whole, only the covered ones otherwise
+        origin = batch_origin(blk_host, bh, bw, None if whole is None else ~whole, cover) if n else (0, 0)
+    if whole is not None and whole.all():
+        cover = None            # every block is rendered whole: same stack, no mask to write / reduce / read back
     if cover is not None:
         import ctypes
         carr = (ctypes.c_double * 4)(*[float(v) for v in cover])
         cptr = ctypes.cast(carr, ctypes.c_void_p)
         mask = torch.empty((n, bh, bw), dtype=torch.uint8, device=img.device)
         mptr = mask.data_ptr()
+        if n and whole.any():
+            full = torch.from_numpy(whole.astype(np.uint8)).to(img.device, non_blocking=True)
+            fptr = full.data_ptr()
     if n:
         ih, iw = img.shape
         _lib.check(_lib.lib().fb_crop_blocks(img.data_ptr(), ih, iw, _code(img), blocks.data_ptr(), n, bh, bw,
                                              float(origin[0]), float(origin[1]), float(fillval), out.data_ptr(),
-                                             cptr, mptr, img.device.index, _stream(img)))
+                                             cptr, fptr, mptr, img.device.index, _stream(img)))
     return out, mask
 
 
-def _blocks_inside(b, bh, bw, cover, margin=0.0):
-    """True when the source positions of all four corners of every block lie inside ``cover``.  The corner
-    values are computed with the kernel's own operation order in float64, and every rounding step of the affine
-    coordinate field is monotone in the column and in the row index, so the corners bound all pixels exactly:
-    the coverage mask would be all ones."""
-    xe = np.stack((b[:, 0], b[:, 0] + (bw - 1) * b[:, 2]), axis=-1)[:, :, None]
-    ye = np.stack((b[:, 1], b[:, 1] + (bh - 1) * b[:, 3]), axis=-1)[:, None, :]
-    xs = xe * b[:, 4, None, None] + ye * b[:, 5, None, None] + b[:, 6, None, None]
-    ys = xe * b[:, 7, None, None] + ye * b[:, 8, None, None] + b[:, 9, None, None]
-    return bool(xs.min() >= cover[0] + margin and xs.max() < cover[2] - margin and
-                ys.min() >= cover[1] + margin and ys.max() < cover[3] - margin)
+def _clip_halfplane(poly, axis, bound, keep_greater):
+    """Sutherland-Hodgman step: the part of the convex polygon ``poly`` (K x 2) with coordinate ``axis`` on the
+    kept side of ``bound``."""
+    if poly.shape[0] == 0:
+        return poly
+    d = (poly[:, axis] - bound) if keep_greater else (bound - poly[:, axis])
+    nxt, dn = np.roll(poly, -1, axis=0), np.roll(d, -1)
+    out = []
+    for p, q, a, b in zip(poly, nxt, d, dn):
+        if a >= 0:
+            out.append(p)
+        if (a >= 0) != (b >= 0):
+            out.append(p + (q - p) * (a / (a - b)))
+    return np.array(out, dtype=np.float64).reshape(-1, 2)
+
+
+def _poly_area(poly):
+    if poly.shape[0] < 3:
+        return 0.0
+    x, y = poly[:, 0], poly[:, 1]
+    return 0.5 * abs(float(np.sum(x * np.roll(y, -1) - np.roll(x, -1) * y)))
+
+
+def footprint_uncovered_area(blocks, bh, bw, cover):
+    """Per block: area of its footprint in the source image that lies outside ``cover``.
+
+    The footprint is the block's bounding box grown to pixel edges, ``bbox - 0.5``, mapped through the block's
+    affine map (feabas/renderer.py:437-442); the reference renders a block whole when less than one square pixel
+    of it is uncovered (:443-444).  Blocks entirely inside report exactly 0 without any clipping."""
+    b = np.asarray(blocks, dtype=np.float64).reshape(-1, 10)
+    x_lo, y_lo = b[:, 0] - 0.5, b[:, 1] - 0.5
+    x_hi, y_hi = x_lo + bw * b[:, 2], y_lo + bh * b[:, 3]
+    cx = np.stack((x_lo, x_hi, x_hi, x_lo), axis=-1)
+    cy = np.stack((y_lo, y_lo, y_hi, y_hi), axis=-1)
+    qx = cx * b[:, 4, None] + cy * b[:, 5, None] + b[:, 6, None]
+    qy = cx * b[:, 7, None] + cy * b[:, 8, None] + b[:, 9, None]
+    inside = (qx.min(axis=1) >= cover[0]) & (qx.max(axis=1) <= cover[2]) & (qy.min(axis=1) >= cover[1]) & (qy.max(axis=1) <= cover[3])
+    out = np.zeros(b.shape[0], dtype=np.float64)
+    for i in np.nonzero(~inside)[0]:
+        quad = np.stack((qx[i], qy[i]), axis=-1)
+        part = quad
+        for axis, bound, greater in ((0, cover[0], True), (0, cover[2], False), (1, cover[1], True), (1, cover[3], False)):
+            part = _clip_halfplane(part, axis, bound, greater)
+        out[i] = _poly_area(quad) - _poly_area(part)
+    return out
 
 
 def crop_blocks(img, blocks, block_shape, origin=None, fillval=0, out=None):
@@ -232,12 +278,17 @@ def crop_blocks(img, blocks, block_shape, origin=None, fillval=0, out=None):
     return crop_blocks_masked(img, blocks, block_shape, origin=origin, fillval=fillval, out=out)[0]
 
 
-def batch_origin(blocks, bh, bw):
+def batch_origin(blocks, bh, bw, partial=None, cover=None):
     """floor(min of the batch's coordinate field) - 4 per axis (common.py:300-304): the field is affine, so
-    its extrema sit at block corners."""
+    its extrema sit at block corners.  ``partial`` (bool per block) marks blocks of which only the pixels inside
+    ``cover`` are rendered: their contribution to the minimum cannot lie below the cover's lower edge."""
     b = np.asarray(blocks, dtype=np.float64).reshape(-1, 10)
     xe = np.stack((b[:, 0], b[:, 0] + (bw - 1) * b[:, 2]), axis=-1)[:, :, None]     # N x 2 x 1
     ye = np.stack((b[:, 1], b[:, 1] + (bh - 1) * b[:, 3]), axis=-1)[:, None, :]     # N x 1 x 2
     xs = xe * b[:, 4, None, None] + ye * b[:, 5, None, None] + b[:, 6, None, None]
     ys = xe * b[:, 7, None, None] + ye * b[:, 8, None, None] + b[:, 9, None, None]
-    return math.floor(xs.min()) - 4, math.floor(ys.min()) - 4
+    x_min, y_min = xs.reshape(b.shape[0], -1).min(axis=1), ys.reshape(b.shape[0], -1).min(axis=1)
+    if partial is not None and cover is not None and np.any(partial):
+        x_min = np.where(partial, np.maximum(x_min, cover[0]), x_min)
+        y_min = np.where(partial, np.maximum(y_min, cover[1]), y_min)
+    return math.floor(x_min.min()) - 4, math.floor(y_min.min()) - 4

@@ -159,6 +159,11 @@ def _block_rows(mesh, loader, bboxes):
     """fb_crop_blocks rows for the blocks ``bboxes`` (output / MOVING frame) of an affine mesh over ``loader``:
     source pixel = (moving @ Ainv + tinv) - loader origin   (feabas/renderer.py:419-450)."""
     ainv, tinv = mesh.render_map()
+    if loader.resolution != mesh.resolution:
+        # crop_multiple rescales the field to the loader's resolution, pixel centres kept (renderer.py:621-624,
+        # spatial.scale_coordinates): one more affine step, folded into the map
+        scale = mesh.resolution / loader.resolution
+        ainv, tinv = ainv * scale, (tinv + 0.5) * scale - 0.5
     b = np.asarray(bboxes, dtype=np.float64).reshape(-1, 4)
     wd = np.round(b[:, 2] - b[:, 0])
     ht = np.round(b[:, 3] - b[:, 1])
@@ -170,14 +175,31 @@ def _block_rows(mesh, loader, bboxes):
     return rows, (int(ht[0]), int(wd[0]))
 
 
-def _render_stack(mesh, loader, bboxes, sigma, ptp_hint=None):
-    """Blocks of one batch as an ``N x H x W`` CUDA tensor (band-passed when ``sigma`` > 0)."""
+def _render_stack(mesh, loader, bboxes, sigma, ptp_hint=None, mask_range=None):
+    """Blocks of one batch as an ``N x H x W`` CUDA tensor (band-passed when ``sigma`` > 0); ``None`` when no pixel
+    of the batch is covered by the mesh (``crop_multiple`` returns None then, feabas/common.py:275-279)."""
     rows, shape = _block_rows(mesh, loader, bboxes)
-    cover = loader.cover_rect() if sigma > 0 else None
+    cover = None
+    if sigma > 0:                                       # precise_mask=log_sigma>0 (feabas/renderer.py:493,506)
+        x_lo, y_lo, x_hi, y_hi = mesh.covered_rect()
+        if loader.resolution != mesh.resolution:
+            scale = mesh.resolution / loader.resolution
+            x_lo, y_lo, x_hi, y_hi = ((v + 0.5) * scale - 0.5 for v in (x_lo, y_lo, x_hi, y_hi))
+        cover = (x_lo - loader.x0, y_lo - loader.y0, x_hi - loader.x0, y_hi - loader.y0)
     stack, mask = _img.crop_blocks_masked(loader.tensor, rows, shape, fillval=loader.default_fillval, cover=cover)
     if sigma > 0:
-        if mask is not None and bool(mask.all()):
-            mask = None
+        if mask is not None:
+            lo, hi = (int(v) for v in torch.stack((mask.min(), mask.max())).cpu())
+            if hi == 0:
+                return None
+            if lo == 1:
+                mask = None
+        if mask_range is not None:                      # renderer.py:633-636: only intensities inside the range are valid
+            rng = np.atleast_1d(mask_range)
+            valid = (stack >= float(rng[0])) & (stack <= float(rng[-1]))
+            mask = valid if mask is None else (mask.to(torch.bool) & valid)
+            if bool(mask.all()):
+                mask = None
         stack = _img.masked_dog_device(stack, sigma, mask, ptp=ptp_hint)
     return stack
 
@@ -187,7 +209,7 @@ def bboxes_mesh_renderer_matcher(mesh0, mesh1, image_loader0, image_loader1, bbo
 
     Returns ``(xy0, xy1, conf)``: matched points (K x 2 float64, in the frame the bboxes live in) and the
     per-block confidence.  kwargs as the reference: ``batch_size``, ``sigma`` (0), ``conf_mode`` (MIRROR),
-    ``pad`` (True), ``subpixel`` (False); ``render_mode`` / ``geodesic_mask`` / ``mask_range`` /
+    ``pad`` (True), ``subpixel`` (False), ``mask_range`` (None); ``render_mode`` / ``geodesic_mask`` /
     ``affine_approx_tol`` / ``render_weight_threshold`` are accepted and only meaningful for reference meshes.
     """
     batch_size = kwargs.get('batch_size', None)
@@ -195,6 +217,7 @@ def bboxes_mesh_renderer_matcher(mesh0, mesh1, image_loader0, image_loader1, bbo
     conf_mode = kwargs.get('conf_mode', FFT_CONF_MIRROR)
     pad = kwargs.get('pad', True)
     subpixel = kwargs.get('subpixel', False)
+    mask_range = kwargs.get('mask_range', None)
     empty = (np.empty((0, 2)), np.empty((0, 2)), np.empty(0))
     if not (hasattr(mesh0, 'render_map') and hasattr(mesh1, 'render_map')):
         return _reference_block_pass(mesh0, mesh1, image_loader0, image_loader1, bboxes0, bboxes1, **kwargs)
@@ -208,8 +231,12 @@ def bboxes_mesh_renderer_matcher(mesh0, mesh1, image_loader0, image_loader1, bbo
     for lo, hi in zip(edges[:-1], edges[1:]):
         if hi <= lo:
             continue
-        stack0 = _render_stack(mesh0, loader0, bboxes0[lo:hi], sigma)
-        stack1 = _render_stack(mesh1, loader1, bboxes1[lo:hi], sigma)
+        stack0 = _render_stack(mesh0, loader0, bboxes0[lo:hi], sigma, mask_range=mask_range)
+        if stack0 is None:
+            continue
+        stack1 = _render_stack(mesh1, loader1, bboxes1[lo:hi], sigma, mask_range=mask_range)
+        if stack1 is None:
+            continue
         pending.append((lo, hi, xcorr_fft_device(stack0, stack1, conf_mode=conf_mode, pad=pad, subpixel=subpixel)))
     if not pending:
         return empty
@@ -671,5 +698,6 @@ def _stitch_meshes(loader0, loader1, mesh_size, min_num_blocks):
 
 def _default_mesh_factory():
     def affine(bounds, mesh_size, min_num_blocks, uid, resolution):
-        return AffineMesh(bounds, uid=uid, resolution=resolution)
+        return AffineMesh.from_bbox(bounds, cartesian=True, mesh_size=mesh_size, min_num_blocks=min_num_blocks, uid=uid,
+                                    resolution=resolution)
     return affine

@@ -68,11 +68,6 @@ class ArrayLoader:
         h, w = self._tensor.shape
         return (self.x0, self.y0, self.x0 + w, self.y0 + h)
 
-    def cover_rect(self):
-        """Source-pixel rectangle a mesh built on ``bounds`` covers."""
-        h, w = self._tensor.shape
-        return (0.0, 0.0, float(w), float(h))
-
     def crop(self, bbox, return_empty=False, **kwargs):
         """Host copy of ``bbox`` = (xmin, ymin, xmax, ymax), ``fillval`` outside the image."""
         fill = kwargs.get('fillval', self.default_fillval)
@@ -187,6 +182,16 @@ class AffineMesh:
 
     def connected_triangles(self):
         return 1, None
+
+    def triangle_mask_for_stiffness(self, **kwargs):
+        """One homogeneous piece of default material: nothing is soft (feabas/matcher.py:386-390)."""
+        return np.ones(1, dtype=bool)
+
+    def triangle_mask_for_render(self, **kwargs):
+        return np.ones(1, dtype=bool)
+
+    def submesh(self, tri_mask, **kwargs):
+        return self if np.all(tri_mask) else None
 
     def stiffness_matrix(self, **kwargs):
         """Identity "stiffness" over the four corner vertices: with it the strain measure of the matcher is the

@@ -150,12 +150,18 @@ int fb_resize_nearest(const unsigned char* src, int n, int h, int w, double inv_
  * (uint8 images) weights; pixels outside the image read `fillval`.
  * origin_x, origin_y: integer-valued; the reference uses floor(min field) - 4 of the batch.
  * cover (HOST pointer, may be NULL): xmin, ymin, xmax, ymax of the region of the source covered by
- * the mesh; pixels whose source position falls outside it are not rendered (they keep `fillval`)
- * and, when mask_out != NULL (n x bh x bw bytes, device), are flagged 0 there: the validity mask
- * of crop_field_affine(precise_mask=True) that masked_dog_filter consumes.                      */
+ * the mesh (MeshRenderer's covered_region, feabas/renderer.py:98-101: the mesh shrunk by half a
+ * pixel); pixels whose source position is not STRICTLY inside it (shapely.contains_xy,
+ * renderer.py:447) are not rendered (they keep `fillval`) and, when mask_out != NULL
+ * (n x bh x bw bytes, device), are flagged 0 there: the validity mask of
+ * crop_field_affine(precise_mask=True) that masked_dog_filter consumes.
+ * block_full (device, n bytes, may be NULL; only read with cover): nonzero = the block counts as
+ * covered as a whole -- the reference skips the per-pixel test when less than one square pixel
+ * of the block's footprint is uncovered (renderer.py:443-444); the caller evaluates that rule.  */
 int fb_crop_blocks(const void* img, int ih, int iw, int in_dtype, const double* blocks, int n, int bh, int bw,
                    double origin_x, double origin_y, double fillval, void* out,
-                   const double* cover, unsigned char* mask_out, int device, void* stream);
+                   const double* cover, const unsigned char* block_full, unsigned char* mask_out,
+                   int device, void* stream);
 
 /* Smallest 2^a 3^b 5^c >= target: scipy.fftpack.next_fast_len as used at
  * feabas/matcher.py:60,62.  Pure host arithmetic.                          */

@@ -96,6 +96,68 @@ def seeded_xcorr_cases():
     }
 
 
+def run_loop_case(h, spec, kind):
+    """One case of tests/loop_cases.py through the UNMODIFIED reference (oracle/ref_harness.py).  Returns the flat
+    dict of arrays stored in the golden file."""
+    import json
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import loop_cases as lc
+    from oracle import matcher_oracle as mo
+    from oracle.ref_harness import flatten_trace
+    img0, img1 = spec['make']()
+    kwargs = dict(spec['kwargs'])
+    rec = {'kwargs_json': np.asarray(json.dumps(kwargs, sort_keys=True)),
+           'input_sum': np.asarray([np.asarray(img0, dtype=np.float64).sum(), np.asarray(img1, dtype=np.float64).sum()])}
+    with h:
+        if kind == 'stitch':
+            if 'masks' in spec:
+                kwargs['mask0'], kwargs['mask1'] = spec['masks'](img0, img1)
+            out = h.matcher.stitching_matcher(img0, img1, **kwargs)
+            xy0, xy1, weight, strain, phtm = out
+            if phtm is not None:
+                rec['phtm'] = np.asarray(phtm, dtype=np.float64)
+        else:
+            if spec['prep'] == 'dog':
+                img0, img1 = mo.masked_dog_oracle(img0, spec['dog_sigma']), mo.masked_dog_oracle(img1, spec['dog_sigma'])
+            h0, w0 = img0.shape
+            h1, w1 = img1.shape
+            mesh0 = h.AffineMesh.from_bbox((0, 0, w0, h0), cartesian=True, uid=0.0, resolution=4.0)
+            mesh1 = h.AffineMesh.from_bbox((0, 0, w1, h1), cartesian=True, uid=1.0, resolution=4.0)
+            ld0, ld1 = h.stream_loader(img0, resolution=4.0), h.stream_loader(img1, resolution=4.0)
+            if spec.get('initial'):
+                p0, p1, w = lc.initial_matches_for(*spec['initial_args']) if 'initial_args' in spec else lc.initial_matches_for(600, 0.02, (30.0, -24.0))
+                kwargs['initial_matches'] = h.common.Match(p0, p1, w)
+            if spec['entry'] == 'section':
+                xy0, xy1, weight, strain = h.matcher.section_matcher(mesh0, mesh1, ld0, ld1, **kwargs)
+            else:
+                spacings = kwargs.pop('spacings')
+                xy0, xy1, weight, strain = h.matcher.iterative_xcorr_matcher_w_mesh(mesh0, mesh1, ld0, ld1, spacings, **kwargs)
+        trace = h.take_trace()
+    rec['failed'] = np.asarray(xy0 is None)
+    if xy0 is not None:
+        rec['xy0'], rec['xy1'], rec['weight'] = np.asarray(xy0), np.asarray(xy1), np.asarray(weight)
+    rec['weight_or_conf'] = np.asarray(weight if xy0 is None else 0.0, dtype=np.float64)
+    rec['strain'] = np.asarray(np.nan if strain is None else strain, dtype=np.float64)
+    flatten_trace('trace', trace, rec)
+    return rec
+
+
+def loop_goldens():
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import loop_cases as lc
+    from oracle.ref_harness import Harness
+    h = Harness()
+    for fname, cases, kind in (('loop_stitch.npz', lc.stitch_cases(), 'stitch'), ('loop_section.npz', lc.section_cases(), 'section')):
+        blob = {}
+        for name, spec in cases.items():
+            rec = run_loop_case(h, spec, kind)
+            levels = [int(rec[f'trace/{i}/conf'].shape[0]) for i in range(int(rec['trace/n'])) if str(rec[f'trace/{i}/kind']) == 'level']
+            print(f'{name}: failed={bool(rec["failed"])} levels={levels} matches={0 if bool(rec["failed"]) else rec["xy0"].shape[0]} strain={float(rec["strain"]):.3e}')
+            for k, v in rec.items():
+                blob[f'{name}/{k}'] = v
+        np.savez_compressed(os.path.join(OUT, fname), **blob)
+
+
 def main():
     if not ref_loader.available():
         raise SystemExit('reference not present; golden vectors can only be generated in the build container')
@@ -206,12 +268,18 @@ def main():
     blob['gt/flat/out'] = np.asarray(matcher.global_translation_matcher(k0, h1, conf_thresh=0.9))
     np.savez_compressed(os.path.join(OUT, 'matcher_host.npz'), **blob)
 
+    # ---- coarse-to-fine loops: stitching_matcher / section_matcher / iterative_xcorr_matcher_w_mesh -------------
+    loop_goldens()
+
     import scipy
     import cv2
     with open(os.path.join(OUT, 'PROVENANCE.txt'), 'w') as fh:
         fh.write('generated by oracle/make_golden.py from the unmodified reference at /root/reference\n')
         fh.write(f'reference version: feabas 3.0.6 (setup.py:4)\n')
         fh.write(f'scipy {scipy.__version__}, numpy {np.__version__}, opencv {cv2.__version__}, python {sys.version.split()[0]}\n')
+        fh.write('loop_*.npz: the unmodified stitching_matcher / section_matcher / iterative_xcorr_matcher_w_mesh / '
+                 'bboxes_mesh_renderer_matcher / MeshRenderer.crop_multiple with the geometry layer (Mesh, SLM, MeshRenderer.from_mesh, '
+                 'five shapely calls) replaced by the affine stand-ins, see oracle/ref_harness.py\n')
     print('golden vectors written to', OUT)
 
 

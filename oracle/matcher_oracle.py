@@ -298,23 +298,34 @@ def render_blocks_oracle(img, bboxes, ainv, tinv, fillval=0, origin_xy=(0, 0), c
     renderer.py:419-450 for every block) over an in-RAM image whose pixel (0, 0) sits at ``origin_xy``
     (``dal.StreamLoader``), rendered by ``common.render_by_subregions`` (common.py:256-350): fields of all
     blocks concatenated, source crop = floor(min) - 4 .. ceil(max) + 4, ``cv2.remap(INTER_LINEAR,
-    BORDER_CONSTANT, fillval)``.  ``cover``: (xmin, ymin, xmax, ymax) in source pixels outside of which the
-    mask is False (only masked pixels are rendered).  Returns (stack N x H x W, mask N x H x W)."""
+    BORDER_CONSTANT, fillval)``.  ``cover``: (xmin, ymin, xmax, ymax), the renderer's covered region (the mesh
+    shrunk by half a pixel, renderer.py:98-101) in source pixels, used as ``crop_field_affine(precise_mask=True)``
+    does (renderer.py:436-449): a block whose footprint (bbox - 0.5, mapped) sticks out by less than one square
+    pixel is rendered whole, otherwise only pixels strictly inside the region.  Returns (stack N x H x W, mask)."""
     import cv2
-    fx, fy = [], []
+    from . import convex
+    fx, fy, masks = [], [], []
     for b in np.asarray(bboxes, dtype=np.float64).reshape(-1, 4):
         wd, ht = round(b[2] - b[0]), round(b[3] - b[1])
         xs = np.linspace(b[0], b[2], num=wd, endpoint=False, dtype=float)
         ys = np.linspace(b[1], b[3], num=ht, endpoint=False, dtype=float)
         xx, yy = np.meshgrid(xs, ys)
-        fx.append(xx * ainv[0, 0] + yy * ainv[1, 0] + tinv[0] - origin_xy[0])
-        fy.append(xx * ainv[0, 1] + yy * ainv[1, 1] + tinv[1] - origin_xy[1])
+        bx = xx * ainv[0, 0] + yy * ainv[1, 0] + tinv[0] - origin_xy[0]
+        by = xx * ainv[0, 1] + yy * ainv[1, 1] + tinv[1] - origin_xy[1]
+        fx.append(bx)
+        fy.append(by)
+        if cover is None:
+            masks.append(np.ones(bx.shape, dtype=bool))
+            continue
+        foot = convex.affine_transform(convex.box(*(b - 0.5)), (ainv[0, 0], ainv[1, 0], ainv[0, 1], ainv[1, 1],
+                                                               tinv[0] - origin_xy[0], tinv[1] - origin_xy[1]))
+        part = convex.box(*cover).intersection(foot)
+        if foot.area - part.area < 1:
+            masks.append(np.ones(bx.shape, dtype=bool))
+        else:
+            masks.append(convex.contains_xy(part, bx, by))
     nblk = len(fx)
-    map_x, map_y = np.concatenate(fx, 0), np.concatenate(fy, 0)
-    if cover is None:
-        mask = np.ones(map_x.shape, dtype=bool)
-    else:
-        mask = (map_x >= cover[0]) & (map_x < cover[2]) & (map_y >= cover[1]) & (map_y < cover[3])
+    map_x, map_y, mask = np.concatenate(fx, 0), np.concatenate(fy, 0), np.concatenate(masks, 0)
     out = np.full(map_x.shape, fillval, dtype=img.dtype)
     if mask.any():
         x_lo, x_hi = np.floor(map_x[mask].min()) - 4, np.ceil(map_x[mask].max()) + 4
@@ -465,8 +476,9 @@ def stitching_oracle(img0, img1, sigma=2.5, coarse_downsample=1, fine_downsample
             f0 = masked_dog_oracle(f0, sigma * fine_downsample)
             f1 = masked_dog_oracle(f1, sigma * fine_downsample)
     tx, ty = tx * fine_downsample / coarse_downsample, ty * fine_downsample / coarse_downsample
-    sec0 = _Section((0, 0, f0.shape[1], f0.shape[0]), locked=True)
-    sec1 = _Section((0, 0, f1.shape[1], f1.shape[0]))
+    # Mesh.from_bbox(cartesian=True) puts the outer vertices at bounds - 0.5 (mesh.py:426-427)
+    sec0 = _Section((-0.5, -0.5, f0.shape[1] - 0.5, f0.shape[0] - 0.5), locked=True)
+    sec1 = _Section((-0.5, -0.5, f1.shape[1] - 0.5, f1.shape[0] - 0.5))
     sec0.t = np.array([tx, ty], dtype=np.float64)
     xy0, xy1, wt = surrogate_loop_oracle(sec0, sec1, f0, f1, spacings * fine_downsample, conf_thresh=conf_thresh,
                                          residue_mode=residue_mode, residue_len=residue_len * fine_downsample,

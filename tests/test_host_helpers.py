@@ -10,17 +10,23 @@ def _rows(x0, y0, a=(1.0, 0.0, 0.0, 1.0), t=(0.0, 0.0), step=1.0):
     return np.array([[x0, y0, step, step, a[0], a[1], t[0], a[2], a[3], t[1]]], dtype=np.float64)
 
 
-def test_blocks_inside_is_exact_at_the_cover_edges():
-    cover = (0.0, 0.0, 1024.0, 768.0)
-    assert _img._blocks_inside(_rows(0, 0), 64, 64, cover)                     # touches the lower edges: x = 0 is inside
-    assert _img._blocks_inside(_rows(960, 704), 64, 64, cover)                 # last pixel 1023 / 767 < upper edges
-    assert not _img._blocks_inside(_rows(961, 704), 64, 64, cover)             # last pixel 1024: outside
-    assert not _img._blocks_inside(_rows(-1, 0), 64, 64, cover)
+def test_footprint_uncovered_area_follows_the_reference_rule():
+    """feabas/renderer.py:436-449: footprint = bbox - 0.5 through the block's affine map; < 1 px^2 outside the covered
+    region -> the block is rendered whole.  Checked against the oracle's convex-polygon restatement."""
+    from oracle import convex
+    cover = (0.0, 0.0, 1023.0, 767.0)                     # mesh on bounds (0, 0, 1024, 768): vertices - 0.5, shrunk by 0.5
+    area = lambda rows: _img.footprint_uncovered_area(rows, 64, 64, cover)
+    assert area(_rows(1, 1))[0] == 0                      # footprint [0.5, 64.5]^2: inside
+    assert area(_rows(0, 0))[0] == 2 * 0.5 * 64 - 0.25    # half a pixel sticks out along two edges
+    np.testing.assert_allclose(area(_rows(-3, 100))[0], 3.5 * 64)
     rot = (np.cos(0.1), -np.sin(0.1), np.sin(0.1), np.cos(0.1))
-    assert _img._blocks_inside(_rows(300, 300, a=rot), 64, 64, cover)
-    assert not _img._blocks_inside(_rows(0, 0, a=rot), 64, 64, cover)          # the rotation pushes a corner below 0
-    both = np.concatenate((_rows(0, 0), _rows(2000, 0)))
-    assert not _img._blocks_inside(both, 64, 64, cover)
+    rows = np.concatenate((_rows(300, 300, a=rot), _rows(0, 0, a=rot), _rows(2000, 0), _rows(1000.3, 740.6, a=rot, t=(3.0, -2.0))))
+    got = area(rows)
+    for r, g in zip(rows, got):
+        foot = convex.affine_transform(convex.box(r[0] - 0.5, r[1] - 0.5, r[0] + 63.5, r[1] + 63.5), (r[4], r[5], r[7], r[8], r[6], r[9]))
+        want = foot.area - convex.box(*cover).intersection(foot).area
+        np.testing.assert_allclose(g, want, atol=1e-9)
+    assert got[0] == 0 and got[2] == 64 * 64
 
 
 def test_batch_origin_matches_the_field_minimum():

@@ -103,9 +103,9 @@ def test_stitching_matcher_vs_oracle(fc, cfg):
     d = got[1] - got[0]
     assert np.all(np.abs(np.median(d, axis=0) - np.array(true)) < 0.5)
     # same blocks, same matches: sub-pixel agreement of every point pair, weights within 1e-3
-    np.testing.assert_allclose(got[0], want[0], atol=0.03)
-    np.testing.assert_allclose(got[1], want[1], atol=0.03)
-    np.testing.assert_allclose(got[2], want[2], rtol=2e-3, atol=1e-4)
+    np.testing.assert_allclose(got[0], want[0], atol=0.02)
+    np.testing.assert_allclose(got[1], want[1], atol=0.02)
+    np.testing.assert_allclose(got[2], want[2], rtol=1e-4, atol=1e-6)
     assert isinstance(got[3], float) or np.isscalar(got[3])
 
 
