@@ -344,12 +344,22 @@ struct CropParams {
     double cx0, cy0, cx1, cy1;
     const unsigned char* block_full;   // optional [n]: nonzero = the whole block counts as covered (renderer.py:443-444)
     unsigned char* mask_out;
+    const fb_crop_src* srcs;           // optional [n]: per-block source image and origin (blocks of many images in one launch)
 };
 
-template <typename TS> __device__ __forceinline__ float fetch(const CropParams& p, const TS* img, int y, int x)
+struct CropSrc {                       // the source of one block, resolved from CropParams / fb_crop_src
+    const void* img; int ih, iw; double ox, oy;
+};
+__device__ __forceinline__ CropSrc crop_source(const CropParams& p, int b)
 {
-    if ((unsigned)y < (unsigned)p.ih && (unsigned)x < (unsigned)p.iw) return (float)__ldg(img + (size_t)y * p.iw + x);
-    return p.fill;
+    if (p.srcs) { const fb_crop_src s = p.srcs[b]; return CropSrc{s.img, s.ih, s.iw, s.origin_x, s.origin_y}; }
+    return CropSrc{p.img, p.ih, p.iw, p.ox, p.oy};
+}
+
+template <typename TS> __device__ __forceinline__ float fetch(const CropSrc& c, float fill, const TS* img, int y, int x)
+{
+    if ((unsigned)y < (unsigned)c.ih && (unsigned)x < (unsigned)c.iw) return (float)__ldg(img + (size_t)y * c.iw + x);
+    return fill;
 }
 
 // renderer.py:419-450 (float64 field), common.py:318-321 (minus origin, float32), cv2.remap INTER_LINEAR:
@@ -374,13 +384,14 @@ __global__ void __launch_bounds__(256) fbk_crop_blocks(const __grid_constant__ C
             return;
         }
     }
-    const float xf = (float)__dsub_rn(xs, p.ox), yf = (float)__dsub_rn(ys, p.oy);
+    const CropSrc c = crop_source(p, b);
+    const float xf = (float)__dsub_rn(xs, c.ox), yf = (float)__dsub_rn(ys, c.oy);
     const int fx = __float2int_rn(__fmul_rn(xf, 32.f)), fy = __float2int_rn(__fmul_rn(yf, 32.f));
-    const int ix = (fx >> 5) + (int)p.ox, iy = (fy >> 5) + (int)p.oy;
+    const int ix = (fx >> 5) + (int)c.ox, iy = (fy >> 5) + (int)c.oy;
     const int ax = fx & 31, ay = fy & 31;
-    const TS* img = reinterpret_cast<const TS*>(p.img);
-    const float v00 = fetch<TS>(p, img, iy, ix), v01 = fetch<TS>(p, img, iy, ix + 1);
-    const float v10 = fetch<TS>(p, img, iy + 1, ix), v11 = fetch<TS>(p, img, iy + 1, ix + 1);
+    const TS* img = reinterpret_cast<const TS*>(c.img);
+    const float v00 = fetch<TS>(c, p.fill, img, iy, ix), v01 = fetch<TS>(c, p.fill, img, iy, ix + 1);
+    const float v10 = fetch<TS>(c, p.fill, img, iy + 1, ix), v11 = fetch<TS>(c, p.fill, img, iy + 1, ix + 1);
     TS* out = reinterpret_cast<TS*>(p.out) + ((size_t)b * p.bh + row) * p.bw + col;
     if (sizeof(TS) == 1) {
         // weights (32 - a) * (32 - b) * 32 sum to 2^15 exactly
@@ -418,7 +429,8 @@ __global__ void __launch_bounds__(256) fbk_crop_blocks4(const __grid_constant__ 
     const double q0 = q[0], q2 = q[2], a00 = q[4], a01 = q[7], t0 = q[6], t1 = q[9];
     const double yy = __dadd_rn(q[1], __dmul_rn((double)row, q[3]));
     const double ya = __dmul_rn(yy, q[5]), yb = __dmul_rn(yy, q[8]);
-    const TS* img = reinterpret_cast<const TS*>(p.img);
+    const CropSrc c = crop_source(p, b);
+    const TS* img = reinterpret_cast<const TS*>(c.img);
     TS px[4];
     unsigned char inside4[4];
     const bool whole = p.has_cover && p.block_full && p.block_full[b];
@@ -431,12 +443,12 @@ __global__ void __launch_bounds__(256) fbk_crop_blocks4(const __grid_constant__ 
         if (p.has_cover) inside = whole || (xs > p.cx0 && xs < p.cx1 && ys > p.cy0 && ys < p.cy1);
         inside4[k] = inside ? 1 : 0;
         if (!inside) { px[k] = (TS)p.fill; continue; }
-        const float xf = (float)__dsub_rn(xs, p.ox), yf = (float)__dsub_rn(ys, p.oy);
+        const float xf = (float)__dsub_rn(xs, c.ox), yf = (float)__dsub_rn(ys, c.oy);
         const int fx = __float2int_rn(__fmul_rn(xf, 32.f)), fy = __float2int_rn(__fmul_rn(yf, 32.f));
-        const int ix = (fx >> 5) + (int)p.ox, iy = (fy >> 5) + (int)p.oy;
+        const int ix = (fx >> 5) + (int)c.ox, iy = (fy >> 5) + (int)c.oy;
         const int ax = fx & 31, ay = fy & 31;
-        const float v00 = fetch<TS>(p, img, iy, ix), v01 = fetch<TS>(p, img, iy, ix + 1);
-        const float v10 = fetch<TS>(p, img, iy + 1, ix), v11 = fetch<TS>(p, img, iy + 1, ix + 1);
+        const float v00 = fetch<TS>(c, p.fill, img, iy, ix), v01 = fetch<TS>(c, p.fill, img, iy, ix + 1);
+        const float v10 = fetch<TS>(c, p.fill, img, iy + 1, ix), v11 = fetch<TS>(c, p.fill, img, iy + 1, ix + 1);
         if (sizeof(TS) == 1) {
             const int w00 = (32 - ax) * (32 - ay) * 32, w01 = ax * (32 - ay) * 32, w10 = (32 - ax) * ay * 32, w11 = ax * ay * 32;
             const int acc = (int)v00 * w00 + (int)v01 * w01 + (int)v10 * w10 + (int)v11 * w11;
@@ -642,34 +654,63 @@ extern "C" int fb_resize_nearest(const unsigned char* src, int n, int h, int w, 
     return FB_OK;
 }
 
+static int crop_launch(CropParams& p, int in_dtype, double fillval, int device, void* stream)
+{
+    const int n = p.n, bh = p.bh, bw = p.bw;
+    if (n > 65535 * 64) return fb_failf(FB_EINVAL, "too many blocks in one call");
+    int rc = check_device(device);
+    if (rc != FB_OK) return rc;
+    p.fill = in_dtype == FB_U8 ? (float)(fillval < 0 ? 0 : (fillval > 255 ? 255 : rint(fillval))) : (float)fillval;
+    const bool vec4 = bw % 4 == 0 && ((size_t)p.out % 16 == 0) && (!p.mask_out || (size_t)p.mask_out % 4 == 0) && !getenv("FB_CROP_SCALAR");
+    const size_t esz = in_dtype == FB_U8 ? 1 : 4;
+    // grid.y carries the block index (at most 65535 per launch): long lists go out in slices
+    for (int lo = 0; lo < n; lo += 65535) {
+        CropParams q = p;
+        q.n = n - lo < 65535 ? n - lo : 65535;
+        q.blocks = p.blocks + (size_t)lo * 10;
+        q.out = (char*)p.out + (size_t)lo * bh * bw * esz;
+        if (p.mask_out) q.mask_out = p.mask_out + (size_t)lo * bh * bw;
+        if (p.block_full) q.block_full = p.block_full + lo;
+        if (p.srcs) q.srcs = p.srcs + lo;
+        if (vec4) {
+            dim3 grid((bh * (bw / 4) + 255) / 256, q.n);
+            if (in_dtype == FB_F32) fbk_crop_blocks4<float><<<grid, 256, 0, (cudaStream_t)stream>>>(q);
+            else fbk_crop_blocks4<unsigned char><<<grid, 256, 0, (cudaStream_t)stream>>>(q);
+        } else {
+            dim3 grid((bh * bw + 255) / 256, q.n);
+            if (in_dtype == FB_F32) fbk_crop_blocks<float><<<grid, 256, 0, (cudaStream_t)stream>>>(q);
+            else fbk_crop_blocks<unsigned char><<<grid, 256, 0, (cudaStream_t)stream>>>(q);
+        }
+        fb_count_launches(1);
+    }
+    FB_CU(cudaGetLastError());
+    return FB_OK;
+}
+
 extern "C" int fb_crop_blocks(const void* img, int ih, int iw, int in_dtype, const double* blocks, int n, int bh, int bw,
                               double origin_x, double origin_y, double fillval, void* out,
                               const double* cover, const unsigned char* block_full, unsigned char* mask_out, int device, void* stream)
 {
     if (n < 0 || ih < 1 || iw < 1 || bh < 1 || bw < 1) return fb_failf(FB_EINVAL, "bad shape");
     if (in_dtype != FB_F32 && in_dtype != FB_U8) return fb_failf(FB_EINVAL, "crop_blocks: dtype %d not supported", in_dtype);
-    if (n > 65535) return fb_failf(FB_EINVAL, "at most 65535 blocks per call");
     if (n == 0) return FB_OK;
     if (!img || !blocks || !out) return fb_failf(FB_EINVAL, "null pointer");
-    int rc = check_device(device);
-    if (rc != FB_OK) return rc;
     CropParams p{};
     p.img = img; p.ih = ih; p.iw = iw; p.blocks = blocks; p.n = n; p.bh = bh; p.bw = bw;
     p.ox = origin_x; p.oy = origin_y; p.out = out;
     p.has_cover = cover ? 1 : 0; p.mask_out = cover ? mask_out : nullptr;
     if (cover) { p.cx0 = cover[0]; p.cy0 = cover[1]; p.cx1 = cover[2]; p.cy1 = cover[3]; p.block_full = block_full; }
-    p.fill = in_dtype == FB_U8 ? (float)(fillval < 0 ? 0 : (fillval > 255 ? 255 : rint(fillval))) : (float)fillval;
-    const bool vec4 = bw % 4 == 0 && ((size_t)out % 16 == 0) && (!p.mask_out || (size_t)p.mask_out % 4 == 0) && !getenv("FB_CROP_SCALAR");
-    if (vec4) {
-        dim3 grid((bh * (bw / 4) + 255) / 256, n);
-        if (in_dtype == FB_F32) fbk_crop_blocks4<float><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
-        else fbk_crop_blocks4<unsigned char><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
-    } else {
-        dim3 grid((bh * bw + 255) / 256, n);
-        if (in_dtype == FB_F32) fbk_crop_blocks<float><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
-        else fbk_crop_blocks<unsigned char><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
-    }
-    fb_count_launches(1);
-    FB_CU(cudaGetLastError());
-    return FB_OK;
+    return crop_launch(p, in_dtype, fillval, device, stream);
+}
+
+extern "C" int fb_crop_blocks_multi(const fb_crop_src* sources, int in_dtype, const double* blocks, int n, int bh, int bw,
+                                    double fillval, void* out, int device, void* stream)
+{
+    if (n < 0 || bh < 1 || bw < 1) return fb_failf(FB_EINVAL, "bad shape");
+    if (in_dtype != FB_F32 && in_dtype != FB_U8) return fb_failf(FB_EINVAL, "crop_blocks_multi: dtype %d not supported", in_dtype);
+    if (n == 0) return FB_OK;
+    if (!sources || !blocks || !out) return fb_failf(FB_EINVAL, "null pointer");
+    CropParams p{};
+    p.srcs = sources; p.blocks = blocks; p.n = n; p.bh = bh; p.bw = bw; p.out = out;
+    return crop_launch(p, in_dtype, fillval, device, stream);
 }

@@ -42,6 +42,7 @@ SYMBOLS = {
     'fb_resize_area': (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp]),
     'fb_resize_nearest': (_i, [_vp, _i, _i, _i, ctypes.c_double, ctypes.c_double, _vp, _i, _i, _i, _vp]),
     'fb_crop_blocks': (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, ctypes.c_double, ctypes.c_double, ctypes.c_double, _vp, _vp, _vp, _vp, _i, _vp]),
+    'fb_crop_blocks_multi': (_i, [_vp, _i, _vp, _i, _i, _i, ctypes.c_double, _vp, _i, _vp]),
     'fb_next_fast_len': (_i, [_i]),
     'fb_xcorr_plan_info': (_i, [_i, _i, _i, _i, _i, _i, _i, _i, ctypes.POINTER(_ll)]),
     'fb_set_option': (_i, [ctypes.c_char_p, _ll]),

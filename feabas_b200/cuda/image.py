@@ -273,6 +273,38 @@ def footprint_uncovered_area(blocks, bh, bw, cover):
     return out
 
 
+_SRC_DTYPE = np.dtype([('img', np.uint64), ('ih', np.int32), ('iw', np.int32), ('ox', np.float64), ('oy', np.float64)])   # fb_crop_src
+
+
+def crop_blocks_multi(parts, block_shape, fillval=0):
+    """Blocks of MANY source images in one launch (``fb_crop_blocks_multi``).  ``parts``: list of ``(img, blocks)``
+    -- a 2-D CUDA tensor and the ``K x 10`` float64 rows (numpy) of the blocks to cut from it; every part is one batch
+    of the reference (its source-crop origin, ``floor(min field) - 4``, is taken over the part).  All images share a
+    dtype and a device.  Returns the stack ``sum(K) x bh x bw``, parts in order."""
+    bh, bw = int(block_shape[0]), int(block_shape[1])
+    img0 = parts[0][0]
+    rows = np.concatenate([np.ascontiguousarray(b, dtype=np.float64).reshape(-1, 10) for _, b in parts], axis=0)
+    n = rows.shape[0]
+    src = np.empty(n, dtype=_SRC_DTYPE)
+    at = 0
+    for img, b in parts:
+        k = np.asarray(b).reshape(-1, 10).shape[0]
+        if img.dtype != img0.dtype or img.device != img0.device or img.dim() != 2 or not img.is_contiguous():
+            raise ValueError('crop_blocks_multi: the source images must be contiguous 2-D tensors of one dtype on one device')
+        ox, oy = batch_origin(b, bh, bw)
+        src['img'][at:at + k], src['ih'][at:at + k], src['iw'][at:at + k] = img.data_ptr(), img.shape[0], img.shape[1]
+        src['ox'][at:at + k], src['oy'][at:at + k] = ox, oy
+        at += k
+    out = torch.empty((n, bh, bw), dtype=img0.dtype, device=img0.device)
+    if n:
+        packed = np.concatenate((rows.view(np.uint8).reshape(-1), src.view(np.uint8).reshape(-1)))    # one upload
+        dev_buf = torch.from_numpy(packed).to(img0.device, non_blocking=True)
+        rows_ptr = dev_buf.data_ptr()
+        _lib.check(_lib.lib().fb_crop_blocks_multi(rows_ptr + rows.nbytes, _code(img0), rows_ptr, n, bh, bw, float(fillval),
+                                                  out.data_ptr(), img0.device.index, _stream(img0)))
+    return out
+
+
 def crop_blocks(img, blocks, block_shape, origin=None, fillval=0, out=None):
     """``crop_blocks_masked`` without a coverage region; returns the stack only."""
     return crop_blocks_masked(img, blocks, block_shape, origin=origin, fillval=fillval, out=out)[0]

@@ -70,14 +70,27 @@ def global_translation_matcher(img0, img1, **kwargs):
     if sigma > 0:
         a = _masked_dog_any(a, sigma, kwargs.get('mask0', None))
         b = _masked_dog_any(b, sigma, kwargs.get('mask1', None))
-    h0, w0 = a.shape[-2:]
-    h1, w1 = b.shape[-2:]
-    res = xcorr_fft_device(a.reshape(1, h0, w0), b.reshape(1, h1, w1), conf_mode=conf_mode, pad=True).cpu().numpy()
-    tx, ty, conf = float(res[0, 0]), float(res[1, 0]), _conf_scalar(res[2, 0], conf_mode)
-    tx += (w1 - w0) / 2
-    ty += (h1 - h0) / 2
+    tx, ty, conf = _whole_image_translations(a[None], b[None], conf_mode)[0]
     if conf > conf_thresh:
         return tx, ty, conf
+    return _translation_retry(a, b, tx, ty, conf, conf_mode, divide_factor)
+
+
+def _whole_image_translations(stack0, stack1, conf_mode):
+    """First shot of ``global_translation_matcher`` (feabas/matcher.py:148-156) for a STACK of image pairs of one
+    shape: one batched padded cross-correlation, one read-back.  -> list of (tx, ty, conf)."""
+    h0, w0 = stack0.shape[-2:]
+    h1, w1 = stack1.shape[-2:]
+    res = xcorr_fft_device(stack0, stack1, conf_mode=conf_mode, pad=True).cpu().numpy()
+    return [(float(res[0, k]) + (w1 - w0) / 2, float(res[1, k]) + (h1 - h0) / 2, _conf_scalar(res[2, k], conf_mode))
+            for k in range(res.shape[1])]
+
+
+def _translation_retry(a, b, tx, ty, conf, conf_mode, divide_factor):
+    """Second shot (feabas/matcher.py:159-221): the images cut into ``divide_factor`` blocks, the most confident
+    block wins if it beats the whole-image confidence."""
+    h0, w0 = a.shape[-2:]
+    h1, w1 = b.shape[-2:]
     rows_cols = _blk.balanced_division(np.minimum((h0, w0), (h1, w1)), divide_factor)
     xa0, ya0, xb0, yb0 = _blk.divide_bbox((0, 0, w0, h0), min_num_blocks=rows_cols)
     xa1, ya1, xb1, yb1 = _blk.divide_bbox((0, 0, w1, h1), min_num_blocks=rows_cols)
@@ -250,6 +263,87 @@ def bboxes_mesh_renderer_matcher(mesh0, mesh1, image_loader0, image_loader1, bbo
     return np.concatenate(xy0, axis=0), np.concatenate(xy1, axis=0), np.concatenate(conf, axis=0)
 
 
+_MERGE_BYTES = 1 << 30          # blocks of one merged launch: at most this many bytes per stack
+
+
+def _mergeable(req):
+    """Block passes that may share launches with other overlaps / section pairs: affine meshes, no per-batch
+    band-pass (``sigma`` == 0: the stitching and thumbnail paths filter whole images up front)."""
+    mesh0, mesh1, loader0, loader1 = req.args[:4]
+    kw = req.kwargs
+    return (hasattr(mesh0, 'render_map') and hasattr(mesh1, 'render_map') and kw.get('sigma', 0.0) == 0 and
+            isinstance(loader0, ArrayLoader) and isinstance(loader1, ArrayLoader))
+
+
+def _block_pass_many(requests):
+    """``bboxes_mesh_renderer_matcher`` for a list of ``_BlockPass`` requests -> list of ``(xy0, xy1, conf)``.
+
+    Every request is cut into batches exactly as the reference cuts it (feabas/matcher.py:804-822: new batch where the
+    block size changes, at most ``batch_size`` blocks); batches of EQUAL block shapes, padding and sub-pixel flags are
+    then concatenated across requests: one ``fb_crop_blocks_multi`` per side, one ``xcorr_fft`` launch sequence and, for
+    the whole round, one device -> host copy.  A block keeps the source-crop origin of its own batch, and block pairs
+    are independent in the xcorr kernels, so the numbers equal those of the one-request-at-a-time path bit for bit."""
+    answers = [None] * len(requests)
+    groups = {}
+    for i, req in enumerate(requests):
+        if not _mergeable(req):
+            answers[i] = bboxes_mesh_renderer_matcher(*req.args, **req.kwargs)
+            continue
+        mesh0, mesh1, loader0, loader1, boxes0, boxes1 = req.args
+        kw = req.kwargs
+        if boxes0 is None or len(boxes0) == 0:
+            answers[i] = (np.empty((0, 2)), np.empty((0, 2)), np.empty(0))
+            continue
+        boxes0, boxes1 = np.asarray(boxes0), np.asarray(boxes1)
+        conf_mode = kw.get('conf_mode', FFT_CONF_MIRROR)
+        edges = _blk.split_batches(boxes0, boxes1, kw.get('batch_size', None))
+        for lo, hi in zip(edges[:-1], edges[1:]):
+            if hi <= lo:
+                continue
+            rows0, shape0 = _block_rows(mesh0, loader0, boxes0[lo:hi])
+            rows1, shape1 = _block_rows(mesh1, loader1, boxes1[lo:hi])
+            t0, t1 = loader0.tensor, loader1.tensor
+            key = (shape0, shape1, bool(kw.get('pad', True)), bool(kw.get('subpixel', False)), conf_mode, t0.dtype, t1.dtype,
+                   t0.device.index, float(loader0.default_fillval), float(loader1.default_fillval))
+            groups.setdefault(key, []).append((i, lo, hi, rows0, rows1, t0, t1))
+    pending = []
+    for key, items in groups.items():
+        shape0, shape1, pad, subpixel, conf_mode, dt0, dt1, dev, fill0, fill1 = key
+        per_block = max(shape0[0] * shape0[1] * _itemsize(dt0), shape1[0] * shape1[1] * _itemsize(dt1))
+        limit = max(1, _MERGE_BYTES // per_block)
+        start = 0
+        while start < len(items):                              # whole batches per launch, bounded memory
+            stop, count = start, 0
+            while stop < len(items) and (count == 0 or count + items[stop][2] - items[stop][1] <= limit):
+                count += items[stop][2] - items[stop][1]
+                stop += 1
+            part = items[start:stop]
+            stack0 = _img.crop_blocks_multi([(it[5], it[3]) for it in part], shape0, fillval=fill0)
+            stack1 = _img.crop_blocks_multi([(it[6], it[4]) for it in part], shape1, fillval=fill1)
+            pending.append((part, conf_mode, xcorr_fft_device(stack0, stack1, conf_mode=conf_mode, pad=pad, subpixel=subpixel)))
+            start = stop
+    if pending:
+        flat = torch.cat([res for _, _, res in pending], dim=1).cpu().numpy()      # the round's only synchronising read
+        pieces = {}
+        col = 0
+        for part, conf_mode, _ in pending:
+            for i, lo, hi, *_ in part:
+                res = flat[:, col:col + hi - lo]
+                col += hi - lo
+                boxes0, boxes1 = np.asarray(requests[i].args[4]), np.asarray(requests[i].args[5])
+                p0, p1 = _blk.block_points(boxes0[lo:hi], boxes1[lo:hi], res[0], res[1])
+                pieces.setdefault(i, []).append((lo, p0, p1, res[2].astype(np.float64 if conf_mode == 1 else np.float32)))
+        for i, parts in pieces.items():
+            parts.sort(key=lambda x: x[0])
+            answers[i] = (np.concatenate([x[1] for x in parts], axis=0), np.concatenate([x[2] for x in parts], axis=0),
+                          np.concatenate([x[3] for x in parts], axis=0))
+    return answers
+
+
+def _itemsize(dtype):
+    return torch.empty((), dtype=dtype).element_size()
+
+
 def _reference_block_pass(mesh0, mesh1, image_loader0, image_loader1, bboxes0, bboxes1, **kwargs):
     """Reference ``Mesh`` objects: blocks are rendered by the reference's own ``MeshRenderer`` on the host
     (piecewise-linear fields, shapely masks: SURVEY section 2 row 9, not part of this package) and matched by the
@@ -307,6 +401,54 @@ def iterative_xcorr_matcher_w_mesh(mesh0, mesh1, image_loader0, image_loader1, s
     Returns ``(xy0, xy1, weight, strain)``; ``(None, None, 0, strain)`` when nothing could be matched.
     kwargs and their defaults are the reference's (feabas/matcher.py:485-507).
     """
+    return _drive(_coarse_to_fine(mesh0, mesh1, image_loader0, image_loader1, spacings, **kwargs))
+
+
+class _BlockPass:
+    """What the coarse-to-fine loop asks for at every level: one ``bboxes_mesh_renderer_matcher`` call."""
+    __slots__ = ('args', 'kwargs')
+
+    def __init__(self, *args, **kwargs):
+        self.args, self.kwargs = args, kwargs
+
+
+def _drive(loop):
+    """Run one coarse-to-fine loop (a generator that yields ``_BlockPass`` requests) to completion."""
+    try:
+        request = next(loop)
+        while True:
+            request = loop.send(bboxes_mesh_renderer_matcher(*request.args, **request.kwargs))
+    except StopIteration as stop:
+        return stop.value
+
+
+def _drive_many(loops):
+    """Run many independent coarse-to-fine loops in lockstep: at every round the block passes all the loops are
+    waiting for are executed TOGETHER (``_block_pass_many``: one gather + one xcorr launch sequence + one read-back
+    per block shape, whatever the number of overlaps / section pairs), then every loop relaxes its own meshes on the
+    host and asks for its next level.  Same results as driving the loops one after the other."""
+    results = [None] * len(loops)
+    waiting = {}
+
+    def advance(i, answer):
+        try:
+            waiting[i] = loops[i].send(answer) if answer is not None else next(loops[i])
+        except StopIteration as stop:
+            results[i] = stop.value
+
+    for i in range(len(loops)):
+        advance(i, None)
+    while waiting:
+        order = sorted(waiting)
+        requests = [waiting.pop(i) for i in order]
+        for i, answer in zip(order, _block_pass_many(requests)):
+            advance(i, answer)
+    return results
+
+
+def _coarse_to_fine(mesh0, mesh1, image_loader0, image_loader1, spacings, **kwargs):
+    """The loop of ``iterative_xcorr_matcher_w_mesh`` as a generator: it yields a ``_BlockPass`` wherever the
+    reference calls ``bboxes_mesh_renderer_matcher`` (feabas/matcher.py:626,668) and is sent ``(xy0, xy1, conf)``."""
     num_workers = kwargs.get('num_workers', 1)            # accepted; the GPU path batches instead of forking
     conf_thresh = kwargs.get('conf_thresh', 0.3)
     residue_mode = kwargs.get('residue_mode', 'huber')
@@ -381,9 +523,9 @@ def iterative_xcorr_matcher_w_mesh(mesh0, mesh1, image_loader0, image_loader1, s
             boxes0, boxes1 = _region_blocks(mesh0, mesh1, spacing, distributor, at_finest, refine_mode, **kwargs)
         if boxes0 is None:
             return nothing
-        xy0, xy1, conf = bboxes_mesh_renderer_matcher(mesh0, mesh1, image_loader0, image_loader1, boxes0, boxes1,
-                                                      batch_size=batch_size, pad=pad, subpixel=subpixel,
-                                                      affine_approx_tol=affine_tol, **kwargs)
+        xy0, xy1, conf = yield _BlockPass(mesh0, mesh1, image_loader0, image_loader1, boxes0, boxes1,
+                                          batch_size=batch_size, pad=pad, subpixel=subpixel,
+                                          affine_approx_tol=affine_tol, **kwargs)
         good = conf > conf_thresh
         if not np.any(good):
             if not started:
@@ -653,6 +795,138 @@ def stitching_matcher(img0, img1, **kwargs):
         xy0 = _scale_coordinates(xy0, 1 / fine)
         xy1 = _scale_coordinates(xy1, 1 / fine)
     return xy0, xy1, weight, strain, phtm
+
+
+def stitching_matcher_many(pairs, masks=None, chunk=256, **kwargs):
+    """``stitching_matcher`` for MANY overlaps at once (the overlaps of a section: feabas/stitcher.py:385-394 hands
+    them to worker processes one by one; here they advance together).
+
+    ``pairs``: sequence of ``(img0, img1)`` strips; ``masks``: optional sequence of ``(mask0, mask1)`` (entries may be
+    None); the keyword arguments are ``stitching_matcher``'s and apply to every overlap.  Returns the list of
+    ``stitching_matcher`` results, in order, with the same numbers as one call per overlap would give:
+
+    * strips of equal shape are uploaded, resized and band-passed as stacks and get their coarse translation from one
+      batched cross-correlation;
+    * the coarse-to-fine loops of all overlaps run in lockstep (``_drive_many``): per round, the blocks of every
+      overlap that share a shape are gathered, correlated and read back together.
+    """
+    sigma = kwargs.pop('sigma', 2.5)
+    compute_photometric = kwargs.pop('compute_photometric', False)
+    coarse = kwargs.pop('coarse_downsample', 1)
+    fine = kwargs.pop('fine_downsample', 1)
+    spacings_arg = kwargs.pop('spacings', None)
+    residue_len = kwargs.pop('residue_len', 5)
+    dev = kwargs.pop('device', None)
+    kwargs.pop('mask0', None), kwargs.pop('mask1', None)
+    conf_mode = kwargs.get('conf_mode', FFT_CONF_MIRROR)
+    conf_thresh = kwargs.get('conf_thresh', 0.3)
+    min_num_blocks = kwargs.get('min_num_blocks', 2)
+    kwargs.setdefault('residue_mode', 'huber')
+    kwargs.setdefault('opt_tol', None)
+    pairs = list(pairs)
+    results = [None] * len(pairs)
+    single_kw = dict(kwargs, sigma=sigma, compute_photometric=compute_photometric, coarse_downsample=coarse, fine_downsample=fine,
+                     spacings=spacings_arg, residue_len=residue_len, device=dev)
+    groups = {}
+    for k, (img0, img1) in enumerate(pairs):
+        m0, m1 = (None, None) if masks is None or masks[k] is None else masks[k]
+        if m0 is not None or m1 is not None or img0.dtype != img1.dtype:
+            # masked band-pass takes np.ptp per image (feabas/common.py:369): not stackable, one call
+            results[k] = stitching_matcher(img0, img1, mask0=m0, mask1=m1, **dict(single_kw))
+            continue
+        groups.setdefault((tuple(img0.shape), tuple(img1.shape), str(img0.dtype)), []).append(k)
+    loops, owners, finish = [], [], {}
+    for (shape0, shape1, _), members in groups.items():
+        for at in range(0, len(members), chunk):
+            part = members[at:at + chunk]
+            raw0 = _stack_to_device([pairs[k][0] for k in part], dev)
+            dev = raw0.device.index
+            raw1 = _stack_to_device([pairs[k][1] for k in part], dev)
+            c0 = raw0 if coarse == 1 else _img.resize_area(raw0, coarse)
+            c1 = raw1 if coarse == 1 else _img.resize_area(raw1, coarse)
+            g0 = _img.masked_dog_device(c0, sigma * coarse) if sigma > 0 else c0
+            g1 = _img.masked_dog_device(c1, sigma * coarse) if sigma > 0 else c1
+            coarse_txy = _whole_image_translations(g0, g1, conf_mode)
+            if fine == coarse:
+                f0, f1 = g0, g1
+            else:
+                f0 = raw0 if fine == 1 else _img.resize_area(raw0, fine)
+                f1 = raw1 if fine == 1 else _img.resize_area(raw1, fine)
+                if sigma > 0:
+                    f0, f1 = _img.masked_dog_device(f0, sigma * fine), _img.masked_dog_device(f1, sigma * fine)
+            for j, k in enumerate(part):
+                tx, ty, conf = coarse_txy[j]
+                if not conf > conf_thresh:
+                    tx, ty, conf = _translation_retry(g0[j], g1[j], tx, ty, conf, conf_mode, 6)
+                if conf < conf_thresh:
+                    results[k] = (None, None, conf_thresh, None, None)
+                    continue
+                phtm = _photometric(c0[j], c1[j], g0[j], g1[j], None, None, tx, ty, sigma > 0) if compute_photometric else None
+                tx, ty = tx * fine / coarse, ty * fine / coarse
+                resolution = _data_resolution() / fine
+                loader0 = ArrayLoader(f0[j], fillval=0, resolution=resolution)
+                loader1 = ArrayLoader(f1[j], fillval=0, resolution=resolution)
+                if spacings_arg is None:
+                    spacings = _blk.auto_spacings(shape0, shape1)
+                else:
+                    spacings = np.array(spacings_arg, dtype=np.float64, copy=True).ravel()
+                if np.any(spacings < 1):
+                    box, _ = _blk.intersect_bbox(np.array(loader0.bounds) + np.tile((tx, ty), 2), loader1.bounds)
+                    spacings[spacings < 1] *= max(box[2] - box[0], box[3] - box[1])
+                spacings = spacings * fine
+                mesh0, mesh1 = _stitch_meshes(loader0, loader1, np.min(spacings), min_num_blocks)
+                mesh0.apply_translation((tx, ty), MESH_GEAR_FIXED)
+                mesh0.lock()
+                loops.append(_coarse_to_fine(mesh0, mesh1, loader0, loader1, spacings=spacings, distributor='cartesian_bbox',
+                                             residue_len=residue_len * fine, **kwargs))
+                owners.append(k)
+                finish[k] = phtm
+    for k, (xy0, xy1, weight, strain) in zip(owners, _drive_many(loops)):
+        if fine != 1 and xy0 is not None:
+            xy0, xy1 = _scale_coordinates(xy0, 1 / fine), _scale_coordinates(xy1, 1 / fine)
+        results[k] = (xy0, xy1, weight, strain, finish[k])
+    return results
+
+
+def section_matcher_many(jobs, **kwargs):
+    """``section_matcher`` for many section pairs at once: ``jobs`` is a sequence of
+    ``(mesh0, mesh1, image_loader0, image_loader1)`` (optionally a 5th entry: the pair's ``initial_matches``); the keyword
+    arguments are ``section_matcher``'s.  The pairs' coarse-to-fine loops run in lockstep (``_drive_many``).  Returns the
+    list of ``(xy0, xy1, weight, strain)``."""
+    spacings = kwargs.pop('spacings', [100])
+    kwargs.pop('initial_matches', None)
+    kwargs.setdefault('sigma', 2.5)
+    kwargs.setdefault('batch_size', 100)
+    kwargs.setdefault('distributor', 'cartesian_region')
+    kwargs.setdefault('link_weight_decay', 0.0)
+    compute_strain = kwargs.pop('compute_strain', False)
+    stiff_thresh = kwargs.get('stiffness_multiplier_threshold', 0.1)
+    kwargs.setdefault('render_weight_threshold', 0.1)
+    kwargs.setdefault('stiffness_lambda', 0.5)
+    results, loops, owners = [None] * len(jobs), [], []
+    for k, job in enumerate(jobs):
+        mesh0, mesh1, loader0, loader1 = job[:4]
+        initial = job[4] if len(job) > 4 else None
+        if stiff_thresh > 0 and hasattr(mesh0, 'triangle_mask_for_stiffness'):
+            mesh0 = mesh0.submesh(mesh0.triangle_mask_for_stiffness(stiffness_multiplier_threshold=stiff_thresh))
+            mesh1 = mesh1.submesh(mesh1.triangle_mask_for_stiffness(stiffness_multiplier_threshold=stiff_thresh))
+        if initial is not None and not (mesh0.connected_triangles()[0] == 1 and mesh1.connected_triangles()[0] == 1):
+            results[k] = section_matcher(mesh0, mesh1, loader0, loader1, spacings=spacings, initial_matches=initial,
+                                         compute_strain=compute_strain, **dict(kwargs, stiffness_multiplier_threshold=0))
+            continue
+        loops.append(_coarse_to_fine(mesh0, mesh1, loader0, loader1, spacings=spacings, initial_matches=initial,
+                                     compute_strain=compute_strain, **kwargs))
+        owners.append(k)
+    for k, out in zip(owners, _drive_many(loops)):
+        results[k] = out
+    return results
+
+
+def _stack_to_device(images, device):
+    """Equal-shaped 2-D images (numpy arrays or tensors) -> one contiguous ``N x H x W`` CUDA tensor."""
+    if all(isinstance(x, np.ndarray) for x in images):
+        return _img.to_device(np.stack(images, axis=0), device)
+    return torch.stack([_img.to_device(x, device) for x in images], dim=0).contiguous()
 
 
 def _scale_coordinates(xy, scale):

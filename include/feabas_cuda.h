@@ -163,6 +163,20 @@ int fb_crop_blocks(const void* img, int ih, int iw, int in_dtype, const double* 
                    const double* cover, const unsigned char* block_full, unsigned char* mask_out,
                    int device, void* stream);
 
+/* The same gather for blocks that come from MANY source images in one launch: the block lists of all the
+ * overlaps / section pairs that are at the same pyramid level (feabas/stitcher.py:385-394 fans them out to
+ * worker processes; here they share one batch).  sources: device array of n records, one per block: the
+ * block's source image (device pointer, dtype in_dtype), its size and the origin of the reference's source
+ * crop for the batch the block belongs to.  No covered-region test (the sigma == 0 paths).              */
+typedef struct fb_crop_src {
+    const void* img;
+    int ih, iw;
+    double origin_x, origin_y;
+} fb_crop_src;
+
+int fb_crop_blocks_multi(const fb_crop_src* sources, int in_dtype, const double* blocks, int n, int bh, int bw,
+                         double fillval, void* out, int device, void* stream);
+
 /* Smallest 2^a 3^b 5^c >= target: scipy.fftpack.next_fast_len as used at
  * feabas/matcher.py:60,62.  Pure host arithmetic.                          */
 int fb_next_fast_len(int target);

@@ -1,0 +1,127 @@
+"""GPU tier: the lockstep ("many") entry points give the numbers of one call per overlap / section pair, bit for bit;
+the multi-image block gather equals the per-image one; host threads on different GPUs overlap."""
+import time
+
+import numpy as np
+import pytest
+
+import loop_cases as lc
+from oracle import matcher_oracle as mo
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def fc():
+    import torch
+    assert torch.cuda.is_available(), 'GPU tests need a CUDA device'
+    import feabas_b200.cuda as fc
+    return fc
+
+
+def _same(a, b):
+    assert len(a) == len(b)
+    for x, y in zip(a, b):
+        if isinstance(x, np.ndarray):
+            np.testing.assert_array_equal(x, y)
+        else:
+            assert x == y, (x, y)
+
+
+def test_crop_blocks_multi_equals_per_image(fc):
+    import torch
+    from feabas_b200.cuda import image as im
+    rng = np.random.default_rng(3)
+    imgs = [torch.from_numpy(rng.standard_normal((h, w)).astype(np.float32)).cuda() for h, w in ((200, 320), (150, 400), (260, 260))]
+    parts = []
+    for t in imgs:
+        k = int(rng.integers(3, 9))
+        rows = np.zeros((k, 10))
+        rows[:, 0], rows[:, 1] = rng.uniform(-20, t.shape[1] - 30, k), rng.uniform(-20, t.shape[0] - 30, k)
+        rows[:, 2] = rows[:, 3] = 1.0
+        th = rng.uniform(-0.05, 0.05)
+        rows[:, 4], rows[:, 5], rows[:, 7], rows[:, 8] = np.cos(th), -np.sin(th), np.sin(th), np.cos(th)
+        rows[:, 6], rows[:, 9] = rng.uniform(-3, 3, 2)
+        parts.append((t, rows))
+    got = im.crop_blocks_multi(parts, (48, 64), fillval=0).cpu().numpy()
+    want = np.concatenate([im.crop_blocks(t, rows, (48, 64), fillval=0).cpu().numpy() for t, rows in parts])
+    np.testing.assert_array_equal(got, want)
+    u8 = [(t.mul(20).add(128).clamp(0, 255).to(torch.uint8).contiguous(), rows) for t, rows in parts]
+    got = im.crop_blocks_multi(u8, (48, 64), fillval=7).cpu().numpy()
+    want = np.concatenate([im.crop_blocks(t, rows, (48, 64), fillval=7).cpu().numpy() for t, rows in u8])
+    np.testing.assert_array_equal(got, want)
+
+
+def test_stitching_matcher_many_equals_one_call_per_overlap(fc):
+    pairs, masks = [], []
+    for seed, shape in ((41, (700, 260)), (42, (700, 260)), (43, (240, 900)), (44, (700, 260)), (45, (2400, 200))):
+        a, b, _ = lc.strips(seed, shape if shape[0] >= shape[1] else shape[::-1])
+        if shape[0] < shape[1]:
+            a, b = np.ascontiguousarray(a.T), np.ascontiguousarray(b.T)
+        pairs.append((a, b))
+        masks.append(None)
+    rng = np.random.default_rng(0)
+    pairs.append((rng.integers(0, 256, (700, 260), dtype=np.uint8), rng.integers(0, 256, (700, 260), dtype=np.uint8)))   # fails
+    masks.append(None)
+    a, b, _ = lc.strips(46)
+    pairs.append((a, b))
+    m = np.ones(a.shape, bool)
+    m[:, :25] = False
+    masks.append((m, None))                                                                                                  # masked: single path
+    kw = dict(lc.YAML_STITCH, compute_photometric=True)
+    many = fc.stitching_matcher_many(pairs, masks=masks, **kw)
+    assert len(many) == len(pairs) and many[5][0] is None and many[5][2] == kw['conf_thresh']
+    for (a, b), mk, got in zip(pairs, masks, many):
+        mkw = {} if mk is None else dict(mask0=mk[0], mask1=mk[1])
+        want = fc.stitching_matcher(a, b, **kw, **mkw)
+        _same(got, want)
+    # other keyword sets: relative spacings, two levels at half resolution, automatic padding rule
+    for kw in (dict(sigma=2.5, coarse_downsample=0.5, fine_downsample=1, spacings=[0.1, 0.4], pad=True, residue_mode='threshold', residue_len=1.5),
+               dict(sigma=2.0, coarse_downsample=0.5, fine_downsample=0.5, spacings=[60, 200], pad=True),
+               dict(sigma=2.5, coarse_downsample=1, fine_downsample=1, spacings=[50, 200], conf_thresh=0.3)):
+        many = fc.stitching_matcher_many(pairs[:5], **kw)
+        for (a, b), got in zip(pairs[:5], many):
+            _same(got, fc.stitching_matcher(a, b, **kw))
+
+
+def test_section_matcher_many_equals_one_call_per_pair(fc):
+    jobs = []
+    for seed, size in ((51, 600), (52, 600), (53, 520)):
+        img0, img1 = lc.section_pair(seed, size=size)
+        img0, img1 = mo.masked_dog_oracle(img0, 3.5), mo.masked_dog_oracle(img1, 3.5)
+        jobs.append((img0, img1))
+
+    def make(k):
+        a, b = jobs[k]
+        h, w = a.shape
+        return (fc.AffineMesh.from_bbox((0, 0, w, h), cartesian=True, uid=0.0), fc.AffineMesh.from_bbox((0, 0, w, h), cartesian=True, uid=1.0),
+                fc.ArrayLoader(a), fc.ArrayLoader(b))
+    kw = dict(lc.YAML_THUMB, sigma=0.0, compute_strain=True)
+    many = fc.section_matcher_many([make(k) for k in range(3)], **kw)
+    for k in range(3):
+        want = fc.section_matcher(*make(k), **kw)
+        _same(many[k], want)
+    assert many[0][0].shape[0] > 100
+
+
+def test_host_threads_on_two_gpus_overlap(fc):
+    """fb_xcorr_batch_host holds only its own (device, stream) context: two host threads feeding two GPUs run
+    concurrently (round 1 serialised them on a global mutex)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs')
+    from feabas_b200 import synth
+    from feabas_b200.cuda import shard
+    a, b, _ = synth.block_pairs(64, 256, seed=5, max_shift=16)
+    a, b = np.tile(a, (8, 1, 1)), np.tile(b, (8, 1, 1))                 # 512 pairs, 268 MB of input: PCIe bound
+    for d in (0, 1):
+        fc.xcorr_fft(a[:64], b[:64], subpixel=True, device=d)           # contexts, tables, staging buffers
+    t0 = time.perf_counter()
+    one = fc.xcorr_fft(a, b, subpixel=True, device=0)
+    t_one = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    two = shard.xcorr_fft_multi_gpu(a, b, subpixel=True, devices=[0, 1])
+    t_two = time.perf_counter() - t0
+    for x, y in zip(one, two):
+        np.testing.assert_array_equal(x, y)
+    assert t_two < 0.7 * t_one, f'two GPUs took {t_two:.3f} s, one GPU {t_one:.3f} s'
