@@ -226,27 +226,42 @@ def crop_blocks_masked(img, blocks, block_shape, origin=None, fillval=0, cover=N
     return out, mask
 
 
-def _clip_halfplane(poly, axis, bound, keep_greater):
-    """Sutherland-Hodgman step: the part of the convex polygon ``poly`` (K x 2) with coordinate ``axis`` on the
-    kept side of ``bound``."""
-    if poly.shape[0] == 0:
-        return poly
-    d = (poly[:, axis] - bound) if keep_greater else (bound - poly[:, axis])
-    nxt, dn = np.roll(poly, -1, axis=0), np.roll(d, -1)
-    out = []
-    for p, q, a, b in zip(poly, nxt, d, dn):
-        if a >= 0:
-            out.append(p)
-        if (a >= 0) != (b >= 0):
-            out.append(p + (q - p) * (a / (a - b)))
-    return np.array(out, dtype=np.float64).reshape(-1, 2)
+def _clip_many(pts, cnt, axis, bound, keep_greater):
+    """One Sutherland-Hodgman step for MANY convex polygons at once: ``pts`` is ``B x V x 2`` with the first ``cnt[b]``
+    vertices of polygon b valid; keeps the part with coordinate ``axis`` on the kept side of ``bound``.  Returns the
+    clipped polygons in the same representation (``V`` grows by one per step at most)."""
+    nb, nv, _ = pts.shape
+    idx = np.arange(nv)[None, :]
+    valid = idx < cnt[:, None]
+    nxt_i = np.where(idx + 1 < cnt[:, None], idx + 1, 0)
+    nxt = np.take_along_axis(pts, nxt_i[:, :, None].repeat(2, axis=2), axis=1)
+    d = (pts[:, :, axis] - bound) if keep_greater else (bound - pts[:, :, axis])
+    dn = np.take_along_axis(d, nxt_i, axis=1)
+    keep = valid & (d >= 0)
+    cross = valid & ((d >= 0) != (dn >= 0))
+    with np.errstate(divide='ignore', invalid='ignore'):
+        frac = np.where(cross, d / (d - dn), 0.0)
+    inter = pts + (nxt - pts) * frac[:, :, None]
+    # candidates in polygon order: vertex i (if kept), then the crossing on edge i -> i + 1
+    cand = np.stack((pts, inter), axis=2).reshape(nb, 2 * nv, 2)
+    flag = np.stack((keep, cross), axis=2).reshape(nb, 2 * nv)
+    order = np.argsort(~flag, axis=1, kind='stable')
+    out_n = flag.sum(axis=1)
+    width = min(2 * nv, nv + 1)
+    sel = order[:, :width]
+    out = np.take_along_axis(cand, sel[:, :, None].repeat(2, axis=2), axis=1)
+    return out, out_n
 
 
-def _poly_area(poly):
-    if poly.shape[0] < 3:
-        return 0.0
-    x, y = poly[:, 0], poly[:, 1]
-    return 0.5 * abs(float(np.sum(x * np.roll(y, -1) - np.roll(x, -1) * y)))
+def _poly_areas(pts, cnt):
+    """Shoelace areas of many polygons in the ``_clip_many`` representation."""
+    nb, nv, _ = pts.shape
+    idx = np.arange(nv)[None, :]
+    valid = idx < cnt[:, None]
+    nxt_i = np.where(idx + 1 < cnt[:, None], idx + 1, 0)
+    nxt = np.take_along_axis(pts, nxt_i[:, :, None].repeat(2, axis=2), axis=1)
+    cross = np.where(valid, pts[:, :, 0] * nxt[:, :, 1] - nxt[:, :, 0] * pts[:, :, 1], 0.0)
+    return np.where(cnt >= 3, 0.5 * np.abs(cross.sum(axis=1)), 0.0)
 
 
 def footprint_uncovered_area(blocks, bh, bw, cover):
@@ -254,7 +269,8 @@ def footprint_uncovered_area(blocks, bh, bw, cover):
 
     The footprint is the block's bounding box grown to pixel edges, ``bbox - 0.5``, mapped through the block's
     affine map (feabas/renderer.py:437-442); the reference renders a block whole when less than one square pixel
-    of it is uncovered (:443-444).  Blocks entirely inside report exactly 0 without any clipping."""
+    of it is uncovered (:443-444).  Blocks entirely inside report exactly 0 without any clipping; the others are
+    clipped against the four sides of ``cover`` together (vectorised Sutherland-Hodgman)."""
     b = np.asarray(blocks, dtype=np.float64).reshape(-1, 10)
     x_lo, y_lo = b[:, 0] - 0.5, b[:, 1] - 0.5
     x_hi, y_hi = x_lo + bw * b[:, 2], y_lo + bh * b[:, 3]
@@ -264,12 +280,14 @@ def footprint_uncovered_area(blocks, bh, bw, cover):
     qy = cx * b[:, 7, None] + cy * b[:, 8, None] + b[:, 9, None]
     inside = (qx.min(axis=1) >= cover[0]) & (qx.max(axis=1) <= cover[2]) & (qy.min(axis=1) >= cover[1]) & (qy.max(axis=1) <= cover[3])
     out = np.zeros(b.shape[0], dtype=np.float64)
-    for i in np.nonzero(~inside)[0]:
-        quad = np.stack((qx[i], qy[i]), axis=-1)
-        part = quad
+    todo = np.nonzero(~inside)[0]
+    if todo.size:
+        pts = np.stack((qx[todo], qy[todo]), axis=-1)                      # K x 4 x 2
+        cnt = np.full(todo.size, 4, dtype=np.int64)
+        whole = _poly_areas(pts, cnt)
         for axis, bound, greater in ((0, cover[0], True), (0, cover[2], False), (1, cover[1], True), (1, cover[3], False)):
-            part = _clip_halfplane(part, axis, bound, greater)
-        out[i] = _poly_area(quad) - _poly_area(part)
+            pts, cnt = _clip_many(pts, cnt, axis, bound, greater)
+        out[todo] = whole - _poly_areas(pts, cnt)
     return out
 
 

@@ -83,6 +83,15 @@ class ArrayLoader:
         return out
 
 
+_IDENTITY8 = None
+
+
+def _rank_deficient(centered):
+    """``np.linalg.matrix_rank(centered) < 2`` for an N x 2 array (same singular values, same tolerance rule)."""
+    sv = np.linalg.svd(centered, compute_uv=False)
+    return int(np.count_nonzero(sv > sv.max() * max(centered.shape) * np.finfo(np.float64).eps)) < 2
+
+
 class AffineMesh:
     """A section whose deformation is one affine map per gear: ``p_gear = p_initial @ A + t``."""
 
@@ -196,8 +205,11 @@ class AffineMesh:
     def stiffness_matrix(self, **kwargs):
         """Identity "stiffness" over the four corner vertices: with it the strain measure of the matcher is the
         RMS corner displacement relative to the RMS corner radius."""
-        from scipy import sparse
-        return sparse.identity(8, format='csr'), None
+        global _IDENTITY8
+        if _IDENTITY8 is None:
+            from scipy import sparse
+            _IDENTITY8 = sparse.identity(8, format='csr')
+        return _IDENTITY8, None
 
 
 class _AffineLink:
@@ -275,7 +287,7 @@ class AffineSLM:
     @staticmethod
     def _fit_affine(src, dst, w):
         w = np.asarray(w, dtype=np.float64)
-        if src.shape[0] < 3 or np.linalg.matrix_rank(src - src.mean(0)) < 2:
+        if src.shape[0] < 3 or _rank_deficient(src - src.mean(0)):
             t = np.average(dst - src, axis=0, weights=w) if w.sum() > 0 else np.zeros(2)
             return np.eye(2), t
         sw = np.sqrt(w)[:, None]

@@ -41,4 +41,6 @@ def test_gpu_arm_line():
     assert r['kernel'] in r['kernels'] and 0.3 < r['kernel_share_of_step'] < 0.8
     e = d['e2e']
     assert e['h2d_bytes_per_step'] == 2 * 256 * 512 * 512 * 4 and e['d2h_bytes_per_step'] > 0 and 0 < e['value'] < d['value']
-    assert d['config']['ground_truth_recovered'] == 1.0
+    assert d['run_info']['ground_truth_recovered'] == 1.0 and set(d['config']) == {'workload', 'pairs_per_step_per_gpu', 'fft', 'l2'}
+    assert d['clocks']['samples'] >= 3 and d['e2e']['h2d_ceiling_gbs'] > 0 and d['e2e']['pageable']['value'] > 0
+    assert {'burst', 'sustained'} == set(d['regimes'])
