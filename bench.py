@@ -1113,7 +1113,7 @@ def main():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--fast-flags', type=int, default=0, help='kernel experiment switches (fb_set_option fast_flags)')
     ap.add_argument('--workers', type=int, default=0, help='job workloads: also measure P worker processes sharing the GPU')
-    ap.add_argument('--force', default=None, choices=['generic', 'staged', 'fused'], help='force an execution shape (comparison runs)')
+    ap.add_argument('--force', default=None, choices=['generic', 'staged', 'fused', 'fused_smem'], help='force an execution shape (comparison runs)')
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.batch:
@@ -1186,7 +1186,7 @@ def main():
         run_info['fast_flags'] = args.fast_flags
     flags = 0x2 | (2 << 2) | (1 if pad else 0)
     info = L.plan_info(h, w, h, w, L.FB_F32, ny, nx, flags)
-    fused = info['path'] == 'fused'
+    fused = info['path'].startswith('fused')
     run_info['path'] = info['path'] if not args.force else 'forced ' + args.force
 
     a, b, shifts = make_pairs(batch, h, w, seed=100 + rank, device=dev, max_shift=min(32, min(h, w) // 8))

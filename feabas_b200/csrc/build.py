@@ -14,12 +14,15 @@ LIB = os.path.join(HERE, 'libfeabas_cuda.so')
 OBJ_DIR = os.path.join(HERE, 'build')
 HEADER = os.path.join('..', '..', 'include', 'feabas_cuda.h')
 FAST_DEPS = ['fb_fast_tu.inc', 'fb_fast_groups.h', 'fb_xcorr_fast.cuh', 'fb_xcorr.cuh', 'fb_regfft.cuh', 'fb_fft.cuh', 'fb_gfft.cuh', HEADER]
+WF_DEPS = ['fb_wf_tu.inc', 'fb_wf_groups.h', 'fb_xcorr_wf.cuh', 'fb_xcorr.cuh', 'fb_regfft.cuh', 'fb_fft.cuh', 'fb_gfft.cuh', HEADER]
 # translation unit -> headers it includes
 UNITS = {
-    'fb_xcorr.cu': ['fb_xcorr.cuh', 'fb_xcorr_fast.cuh', 'fb_fast_groups.h', 'fb_regfft.cuh', 'fb_fft.cuh', 'fb_gfft.cuh', 'fb_host_plan.h', 'fb_common.h', HEADER],
+    'fb_xcorr.cu': ['fb_xcorr.cuh', 'fb_xcorr_fast.cuh', 'fb_fast_groups.h', 'fb_wf_groups.h', 'fb_xcorr_wf.cuh', 'fb_regfft.cuh', 'fb_fft.cuh', 'fb_gfft.cuh', 'fb_host_plan.h', 'fb_common.h', HEADER],
     # the register-resident fast path, one translation unit per group of line lengths (parallel build)
     'fb_fast_pow2.cu': FAST_DEPS, 'fb_fast_big.cu': FAST_DEPS, 'fb_fast_r3.cu': FAST_DEPS, 'fb_fast_r5.cu': FAST_DEPS, 'fb_fast_r5b.cu': FAST_DEPS,
     'fb_image.cu': ['fb_common.h', HEADER],
+    # the warp-fused kernel (whole pair on one SM, register transforms), one translation unit per group of grids
+    'fb_wf_a.cu': WF_DEPS, 'fb_wf_b.cu': WF_DEPS, 'fb_wf_c.cu': WF_DEPS,
 }
 SOURCES = list(UNITS)
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',

@@ -19,6 +19,7 @@
 #include "fb_host_plan.h"
 #include "fb_xcorr.cuh"
 #include "fb_fast_groups.h"
+#include "fb_wf_groups.h"
 
 using namespace fb;
 
@@ -158,6 +159,7 @@ static std::atomic<long long> g_opt_fused_threads{0};      // experiment switch:
 static std::atomic<long long> g_opt_pipeline_waves{1};     // ... when every kernel of a half still has this many work items per resident CTA
 static std::atomic<long long> g_opt_pipeline{2};           // fast path: a chunk runs as this many independent parts on separate streams (1: serial)
 static std::atomic<long long> g_opt_max_radix{16};         // largest radix of the shared-memory passes (experiment switch; set before first use)
+static std::atomic<long long> g_opt_warp_fused{1};         // 0: small grids run on the first fused kernel (shared-memory radix passes)
 static std::atomic<long long> g_opt_fast_flags{0};       // experiment switches, see FastParams::flags (+16: K2 unbatched twiddles, +32: K3 8 lines)
 
 template <typename T>
@@ -213,6 +215,39 @@ static int get_warp_table(int device, int n, int T, const cx<float>*& out)
     return FB_OK;
 }
 
+// warp-fused kernel: plain [E][T] table of w_n^(k1 t)
+static int get_wf_table(int device, int n, int T, const cx<float>*& out)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto key = std::make_tuple(device, n, -T);
+    auto it = g_wtables.find(key);
+    if (it == g_wtables.end()) {
+        const int E = n / T;
+        std::vector<cx<float>> tw((size_t)n);
+        for (int k1 = 0; k1 < E; ++k1)
+            for (int t = 0; t < T; ++t) {
+                long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)((k1 * t) % n) / (long double)n;
+                tw[(size_t)k1 * T + t].x = (float)std::cos(a);
+                tw[(size_t)k1 * T + t].y = (float)std::sin(a);
+            }
+        void* d = nullptr;
+        CU(cudaMalloc(&d, tw.size() * sizeof(cx<float>)));
+        CU(cudaMemcpy(d, tw.data(), tw.size() * sizeof(cx<float>), cudaMemcpyHostToDevice));
+        it = g_wtables.emplace(key, d).first;
+    }
+    out = reinterpret_cast<const cx<float>*>(it->second);
+    return FB_OK;
+}
+
+static int wf_lanes(int ny, int nx, int& ty, int& tx)
+{
+    ty = tx = 0;
+#define X(NY_, NX_, EY_, TY_, EX_, TX_, NW_, XP_) if (ny == NY_ && nx == NX_) { ty = TY_; tx = TX_; }
+    FB_WF_SIZES(X)
+#undef X
+    return ty && tx;
+}
+
 template <typename F>
 static int raise_smem(F* fn)
 {
@@ -243,6 +278,8 @@ static int set_attrs(int device)
     if (fast_set_attrs_pow2(kMaxSmem) || fast_set_attrs_big(kMaxSmem) || fast_set_attrs_r3(kMaxSmem) || fast_set_attrs_r5(kMaxSmem) ||
         fast_set_attrs_r5b(kMaxSmem))
         return fail(FB_ECUDA, "cudaFuncSetAttribute failed for a fast-path kernel");
+    if (wf_set_attrs_a(kMaxSmem) || wf_set_attrs_b(kMaxSmem) || wf_set_attrs_c(kMaxSmem))
+        return fail(FB_ECUDA, "cudaFuncSetAttribute failed for a warp-fused kernel");
 #undef RS
     g_attr_done[device] = true;
     return FB_OK;
@@ -258,6 +295,7 @@ struct Problem {
     int isz;        // bytes per input element
     Geometry g;
     bool fused;
+    bool wf;        // fused, warp-per-line register transforms (fb_xcorr_wf.cuh)
     bool fast;      // register-resident power-of-two pipeline
     int hp0, hp1;   // fast: padded heights of the transposed row spectra
     size_t ws_per_pair;
@@ -265,6 +303,15 @@ struct Problem {
     int nchan;      // channels per image (cross-power averaged); > 1 or any fb_xcorr_ext pointer -> generic staged path
     fb_xcorr_ext ext;
 };
+
+static bool wf_shape(int ny, int nx, int& threads, size_t& smem)
+{
+    WfLaunch l{ny, nx, FB_F32, 0, nullptr, 0, 0};
+    WfParams none{};
+    if (!(wf_launch_a(none, l) || wf_launch_b(none, l) || wf_launch_c(none, l))) return false;
+    threads = l.threads; smem = l.smem;
+    return true;
+}
 
 static int fast_rblk_of(int nx);
 static bool fast_size(int n)
@@ -309,6 +356,11 @@ static int make_problem(Problem& q, int n, int h0, int w0, int h1, int w1, int i
     if (flags & FB_FLAG_FORCE_FUSED) {
         if (!g.fused) return fail(FB_ESIZE, "fused path unavailable for %dx%d", fft_h, fft_w);
         q.fused = true;
+    }
+    {
+        int wt; size_t ws;
+        q.wf = !q.f64 && !ext_active && !(flags & (FB_FLAG_FORCE_STAGED | FB_FLAG_FORCE_FUSED_SMEM)) && g_opt_warp_fused && wf_shape(fft_h, fft_w, wt, ws);
+        if (q.wf) q.fused = true;
     }
     const int rpt = g.mirror ? g.tl_row : 2 * g.tl_row;
     q.nrt = q.fused ? 0 : (fft_h + rpt - 1) / rpt;
@@ -602,6 +654,25 @@ static int launch_chunk(const Problem& q, StreamCtx& ctx, const void* img0, cons
     p.conf_mode = q.conf_mode; p.subpixel = q.subpixel; p.scale = 1.0 / ((double)q.ny * (double)q.nx);
     p.out_scale = 1.0;
     p.fin_narrow = (!q.fused && finalize_narrow<T>(q.nx)) ? 1 : 0;
+    if (q.wf) {
+        if constexpr (std::is_same<T, float>::value) {
+            WfParams wp{};
+            wp.x = p;
+            int ty, tx;
+            wf_lanes(q.ny, q.nx, ty, tx);
+            if ((rc = get_wf_table(ctx.device, q.nx, tx, wp.twx)) != FB_OK) return rc;
+            if ((rc = get_wf_table(ctx.device, q.ny, ty, wp.twy)) != FB_OK) return rc;
+            if (!g_num_sms) { int sms = 0; CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx.device)); g_num_sms = sms; }
+            WfLaunch l{q.ny, q.nx, std::is_same<TI, float>::value ? FB_F32 : FB_U8, 0, st, 0, 0};
+            wf_shape(q.ny, q.nx, l.threads, l.smem);
+            const int cap = g_num_sms * (l.smem <= 112 * 1024 ? 2 : 1);
+            l.grid = nb < cap ? nb : cap;
+            { ProfScope ps(ctx, st, SLOT_FUSED); wf_launch_a(wp, l) || wf_launch_b(wp, l) || wf_launch_c(wp, l); }
+            g_launches += 1;
+            CU(cudaGetLastError());
+            return FB_OK;
+        }
+    }
     if (q.fused) {
         p.tl = g.tl_fused; p.spitch = g.spitch;
         int nthr = g.smem_fused > 100 * 1024 ? 512 : 256;
@@ -861,7 +932,7 @@ extern "C" int fb_xcorr_plan_info(int h0, int w0, int h1, int w1, int in_dtype, 
     int rc = make_problem(q, 1, h0, w0, h1, w1, in_dtype, fft_h, fft_w, flags);
     if (rc != FB_OK) return rc;
     if (!info) return fail(FB_EINVAL, "null info");
-    info[0] = q.fused ? 1 : (q.fast ? 3 : 2);
+    info[0] = q.wf ? 4 : (q.fused ? 1 : (q.fast ? 3 : 2));
     info[1] = (long long)q.ws_per_pair;
     info[2] = q.g.fused ? (long long)q.g.smem_fused : 0;
     info[3] = (long long)q.g.smem_row;
@@ -883,6 +954,7 @@ extern "C" int fb_set_option(const char* name, long long value)
     if (!strcmp(name, "ws_bytes")) { if (value < (1 << 20)) return fail(FB_EINVAL, "ws_bytes too small"); g_opt_ws_bytes = value; return FB_OK; }
     if (!strcmp(name, "profile")) { g_opt_profile = value ? 1 : 0; return FB_OK; }
     if (!strcmp(name, "fast_flags")) { g_opt_fast_flags = value; return FB_OK; }
+    if (!strcmp(name, "warp_fused")) { g_opt_warp_fused = value ? 1 : 0; return FB_OK; }
     if (!strcmp(name, "host_chunk_bytes")) { if (value < 4096) return fail(FB_EINVAL, "host_chunk_bytes too small"); g_opt_host_chunk = value; return FB_OK; }
     return fail(FB_EINVAL, "unknown option %s", name);
 }

@@ -19,6 +19,7 @@ FB_FLAG_FORCE_STAGED = 0x10
 FB_FLAG_FORCE_FUSED = 0x20
 FB_FLAG_U8_AS_F32 = 0x40
 FB_FLAG_FORCE_GENERIC = 0x80
+FB_FLAG_FORCE_FUSED_SMEM = 0x100
 FB_DOG_UNSIGNED = 0x1
 FB_DOG_EXACT = 0x2
 
@@ -89,7 +90,7 @@ def plan_info(h0, w0, h1, w1, in_dtype, fft_h, fft_w, flags):
     check(lib().fb_xcorr_plan_info(h0, w0, h1, w1, in_dtype, fft_h, fft_w, flags, buf))
     keys = ('path', 'ws_bytes_per_pair', 'smem_fused', 'smem_row', 'smem_col', 'row_tile', 'col_tile', 'launches_per_chunk')
     out = dict(zip(keys, list(buf)))
-    out['path'] = {1: 'fused', 2: 'staged', 3: 'staged-fast'}[out['path']]
+    out['path'] = {1: 'fused', 2: 'staged', 3: 'staged-fast', 4: 'fused-warp'}[out['path']]
     return out
 
 

@@ -61,6 +61,8 @@ def _flags(conf_mode, subpixel, pad, force=None, u8_as_f32=False):
         f |= _lib.FB_FLAG_FORCE_STAGED
     elif force == 'fused':
         f |= _lib.FB_FLAG_FORCE_FUSED
+    elif force == 'fused_smem':
+        f |= _lib.FB_FLAG_FORCE_FUSED | _lib.FB_FLAG_FORCE_FUSED_SMEM
     elif force == 'generic':
         f |= _lib.FB_FLAG_FORCE_STAGED | _lib.FB_FLAG_FORCE_GENERIC
     if u8_as_f32:

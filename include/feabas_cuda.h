@@ -44,6 +44,8 @@ extern "C" {
 #define FB_FLAG_FORCE_FUSED 0x20  /* testing: always use the single-CTA fused kernel         */
 #define FB_FLAG_U8_AS_F32 0x40    /* opt-in: compute uint8 input in float32 (not reference-exact) */
 #define FB_FLAG_FORCE_GENERIC 0x80 /* testing: staged pipeline with the generic mixed-radix kernels */
+#define FB_FLAG_FORCE_FUSED_SMEM 0x100 /* testing: the single-CTA kernel with shared-memory radix passes, never the
+                                          warp-per-line one */
 
 /* xcorr_fft (feabas/matcher.py:22-135) on a stack of n image pairs, sigma == 0,
  * single channel, no mask normalisation (those: fb_xcorr_batch_device_ex below).
@@ -181,8 +183,8 @@ int fb_crop_blocks_multi(const fb_crop_src* sources, int in_dtype, const double*
  * feabas/matcher.py:60,62.  Pure host arithmetic.                          */
 int fb_next_fast_len(int target);
 
-/* How a problem class will be executed.  info[0] = 1 fused / 2 staged (generic
- * mixed-radix kernels) / 3 staged (register-resident power-of-two kernels),
+/* How a problem class will be executed.  info[0] = 1 fused (shared-memory passes) / 2 staged (generic
+ * mixed-radix kernels) / 3 staged (register-resident kernels) / 4 fused (warp-per-line register transforms),
  * info[1] = bytes of HBM workspace per pair, info[2..4] = shared memory per
  * CTA of the fused / row / column kernels, info[5] = row tile lines,
  * info[6] = column tile width, info[7] = kernel launches per chunk.

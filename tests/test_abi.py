@@ -52,7 +52,9 @@ def test_plan_info(lib):
     # F0 + F1 + G(P,Q) ~ 12.6 MB per 512^2 pair
     assert 12.5e6 < big['ws_bytes_per_pair'] < 13.0e6
     small = lib.plan_info(74, 67, 74, 67, lib.FB_F32, 150, 135, 0x2 | (2 << 2))
-    assert small['path'] == 'fused' and small['smem_fused'] <= 227 * 1024
+    assert small['path'] == 'fused-warp' and small['smem_fused'] <= 227 * 1024
+    odd = lib.plan_info(70, 70, 70, 70, lib.FB_F32, 140, 140, 0x2 | (2 << 2))     # 140 = 2^2 5 7: not in the warp-fused table
+    assert odd['path'] == 'fused'
 
 
 def test_bad_arguments(lib):

@@ -27,7 +27,7 @@ def _tol(kw):
     return dict(conf_rtol=5e-2) if kw.get('conf_mode', 2) == 1 else {}
 
 
-@pytest.mark.parametrize('force', [None, 'staged', 'fused'])
+@pytest.mark.parametrize('force', [None, 'staged', 'fused', 'fused_smem'])
 def test_golden_small(fc, golden_small, force):
     n = 0
     for name, rec in golden_small.items():
@@ -37,11 +37,11 @@ def test_golden_small(fc, golden_small, force):
         try:
             dx, dy, cf = fc.xcorr_fft(rec['img0'], rec['img1'], force=force, **kw)
         except fc._lib.FeabasCudaError as e:
-            assert force == 'fused' and 'unavailable' in str(e), (name, e)
+            assert force in ('fused', 'fused_smem') and 'unavailable' in str(e), (name, e)
             continue
         parity.compare(dx, dy, cf, rec['dx'], rec['dy'], rec['conf'], rec['img0'], rec['img1'], **_tol(kw), **kw)
         n += 1
-    assert n >= (14 if force == 'fused' else 20)
+    assert n >= (14 if force in ('fused', 'fused_smem') else 20)
     assert fc._lib.launch_count() > 0
 
 
@@ -309,3 +309,58 @@ def test_two_stream_schedule_matches_serial(fc):
     np.testing.assert_array_equal(serial, two)
     np.testing.assert_array_equal(serial, chunked)
     np.testing.assert_array_equal(np.round(two[0]), shifts[:, 0])
+
+
+# warp-fused kernel (fb_xcorr_wf.cuh): every grid of its size table, the three confidence modes, equal and different
+# image shapes, padded and not, float32 and uint8 (computed in float32 on request)
+WF_CASES = [
+    (40, (74, 67), (74, 67), dict(subpixel=True)),                               # FFT 150 x 135
+    (40, (74, 67), (74, 67), dict(subpixel=True, pad=False)),                    # 75 x 72
+    (24, (60, 75), (60, 75), dict(subpixel=True)),                               # 120 x 150
+    (24, (60, 75), (60, 75), dict(subpixel=False, pad=False)),                   # 60 x 75
+    (24, (60, 67), (60, 67), dict(subpixel=True)),                               # 120 x 135
+    (50, (50, 50), (50, 50), dict(subpixel=True)),                               # 100 x 100
+    (50, (50, 50), (50, 50), dict(subpixel=True, pad=False)),                    # 50 x 50
+    (30, (64, 64), (64, 64), dict(subpixel=True)),                               # 128 x 128
+    (30, (64, 64), (64, 64), dict(subpixel=True, pad=False)),                    # 64 x 64
+    (13, (74, 67), (74, 67), dict(subpixel=True, conf_mode=0)),
+    (13, (74, 67), (74, 67), dict(subpixel=True, conf_mode=1)),
+    (13, (73, 66), (75, 68), dict(subpixel=True)),                               # different shapes, odd heights, same grid
+    (7, (50, 50), (48, 50), dict(subpixel=True, conf_mode=1)),                   # 100 x 100 from unequal blocks, STD
+    (5, (75, 72), (75, 72), dict(subpixel=True, pad=False, conf_mode=0)),        # no free rows to stage the images in
+]
+
+
+@pytest.mark.parametrize('n,shape0,shape1,kw', WF_CASES)
+def test_warp_fused_against_oracle(fc, n, shape0, shape1, kw):
+    from feabas_b200.cuda import _lib, fft_shape
+    ny, nx = fft_shape(shape0, shape1, kw.get('pad', True))
+    info = _lib.plan_info(shape0[0], shape0[1], shape1[0], shape1[1], _lib.FB_F32, ny, nx, 0)
+    assert info['path'] == 'fused-warp', (ny, nx, info)
+    if shape0 == shape1:
+        a, b, shifts = synth.block_pairs(n, shape0, seed=sum(shape0) + n, max_shift=min(shape0) // 8)
+    else:
+        big = (max(shape0[0], shape1[0]) + 8, max(shape0[1], shape1[1]) + 8)
+        c0, c1, _ = synth.block_pairs(n, big, seed=77, max_shift=3)
+        a = np.ascontiguousarray(c0[:, 2:2 + shape0[0], 3:3 + shape0[1]])
+        b = np.ascontiguousarray(c1[:, 4:4 + shape1[0], 1:1 + shape1[1]])
+        shifts = None
+    got = fc.xcorr_fft(a, b, **kw)
+    parity.check_against_oracle(got, a, b, **_tol(kw), **kw)
+    if shifts is not None and kw.get('pad', True):
+        assert np.mean((np.round(got[0]) == shifts[:, 0]) & (np.round(got[1]) == shifts[:, 1])) > 0.95
+    # the first fused kernel (shared-memory passes) agrees within the same gates
+    old = fc.xcorr_fft(a, b, force='fused_smem', **kw)
+    parity.compare(got[0], got[1], got[2], old[0], old[1], old[2], a, b, **_tol(kw), **kw)
+
+
+def test_warp_fused_uint8_as_float32_and_large_batch(fc):
+    import torch
+    a, b, shifts = synth.block_pairs(700, (74, 67), seed=5, max_shift=9, dtype=np.float32, band_pass=False)   # > 2 waves of CTAs
+    ua, ub = a.clip(0, 255).astype(np.uint8), b.clip(0, 255).astype(np.uint8)
+    out = fc.xcorr_fft_device(torch.from_numpy(ua).cuda(), torch.from_numpy(ub).cuda(), subpixel=True, u8_as_f32=True).cpu().numpy()
+    ref = fc.xcorr_fft(ua.astype(np.float32), ub.astype(np.float32), subpixel=True)
+    np.testing.assert_array_equal(out[0], ref[0])
+    np.testing.assert_array_equal(out[1], ref[1])
+    np.testing.assert_array_equal(out[2].astype(np.float32), ref[2])
+    parity.check_against_oracle(ref, ua.astype(np.float32), ub.astype(np.float32), subpixel=True)   # (raw, un-band-passed pixels)
