@@ -50,6 +50,7 @@ struct GaussParams {
     float* dst;            // BLUR: blur; DOG: blur - blur(blur); MASK: in-place mask suppression of dst
     int n, h, w;
     long long src_stride;  // elements between consecutive images of src (0: one mask for all)
+    const int* dst_index;  // MASK: image z of src belongs to image dst_index[z] of dst (null: z); n counts the images of src
     const float* span;     // MASK: device pointer to {min, max} of the image stack, or null
     float span_value;      //       used when span == null
     float sc2, s02;        // MASK: sigma_c^2, sigma^2 as float32 (common.py:371)
@@ -91,8 +92,9 @@ __global__ void __launch_bounds__(kNT) fbk_gauss2d(const __grid_constant__ Gauss
     const int in_pitch = in_w | 1;
     float* s_in = reinterpret_cast<float*>(smem_raw);             // [in_h][in_pitch]
     float* s_row = s_in + (size_t)in_h * in_pitch;                // [in_h][kTW]
-    const int img = blockIdx.z, x0 = blockIdx.x * kTW, y0 = blockIdx.y * kTH, tid = threadIdx.x;
-    const TS* base = reinterpret_cast<const TS*>(p.src) + (size_t)img * p.src_stride;
+    const int x0 = blockIdx.x * kTW, y0 = blockIdx.y * kTH, tid = threadIdx.x;
+    const int img = (MODE == MODE_MASK && p.dst_index) ? p.dst_index[blockIdx.z] : (int)blockIdx.z;     // image of dst
+    const TS* base = reinterpret_cast<const TS*>(p.src) + (size_t)blockIdx.z * p.src_stride;
     float span = 0.f;
     if (MODE == MODE_MASK) span = p.span ? (p.span[1] - p.span[0]) : p.span_value;
     for (int i = tid; i < in_h * in_w; i += kNT) {
@@ -163,8 +165,9 @@ __global__ void __launch_bounds__(kNT) fbk_gauss2d_f32(const __grid_constant__ G
     float* s_in = s_in_base + kSlack;
     float* s_row_base = s_in + (size_t)in_h * in_pitch + kSlack;              // slack rows | [in_h][kRowPitch] | slack rows
     float* s_row = s_row_base + kSlack * kRowPitch;
-    const int img = blockIdx.z, x0 = blockIdx.x * kFT, y0 = blockIdx.y * kFT, tid = threadIdx.x;
-    const TS* base = reinterpret_cast<const TS*>(p.src) + (size_t)img * p.src_stride;
+    const int x0 = blockIdx.x * kFT, y0 = blockIdx.y * kFT, tid = threadIdx.x;
+    const int img = (MODE == MODE_MASK && p.dst_index) ? p.dst_index[blockIdx.z] : (int)blockIdx.z;     // image of dst
+    const TS* base = reinterpret_cast<const TS*>(p.src) + (size_t)blockIdx.z * p.src_stride;
     float span = 0.f;
     if (MODE == MODE_MASK) span = p.span ? (p.span[1] - p.span[0]) : p.span_value;
     // input tile (+ zeroed pitch padding and slack)
@@ -238,6 +241,121 @@ __global__ void __launch_bounds__(kNT) fbk_gauss2d_f32(const __grid_constant__ G
                 *out = g;
             } else if (MODE == MODE_DOG) {
                 float f = __fsub_rn(s_in[(yy + r) * in_pitch + xx + r], g);     // img0f - img1f
+                *out = p.take_abs ? fabsf(f) : f;
+            } else {
+                const float mf = __fdiv_rn(__fmul_rn(g, p.sc2), p.s02);
+                const float f = *out;
+                float v = fmaxf(__fsub_rn(fabsf(f), mf), 0.f);
+                if (!p.take_abs) v = f > 0.f ? v : (f < 0.f ? -v : __fmul_rn(v, 0.f));
+                *out = v;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Register-window variant (the default for radius <= 24): same arithmetic, in the same order, as
+// fbk_gauss2d_f32 -- acc = centre * wc, then fmaf(x[-j] + x[+j], w, acc) from the outermost tap inwards -- but
+// a thread pulls the 8 + 2 R values its 8 outputs need into registers with 128-bit shared-memory loads and runs
+// every tap from registers (compile-time radius bucket R, tap list padded with zero weights on the outside:
+// fmaf(x, 0, acc) == acc).  The row pass leaves its result TRANSPOSED, so the column pass is the same code reading
+// contiguous memory.  Instructions per output and pass: 2 R + 1 floating point, (8 + 2 R) / 32 loads, against ~95 in
+// the kernel above (ncu: that one is issue bound with LSU and ALU as busy as the FMA pipe).
+// ---------------------------------------------------------------------------------------------
+template <int R> struct RegGauss {
+    static constexpr int IN = kFT + 2 * R;                         // input tile side
+    static constexpr int PITCH = ((IN + 31 - 4) / 32) * 32 + 4 >= IN ? ((IN + 31 - 4) / 32) * 32 + 4 : ((IN + 31 - 4) / 32) * 32 + 36;   // >= IN, = 4 (mod 32)
+    static constexpr int WIN = kFP + 2 * R;                        // values a thread needs (a multiple of 4)
+    static constexpr size_t SMEM = ((size_t)IN * PITCH + (size_t)kFT * PITCH) * sizeof(float);
+};
+
+struct RegTaps {
+    float wc;
+    float w[24];                        // w[j]: weight at offset +-(R - j), zero for the padded outer taps
+};
+
+// 8 outputs along a contiguous line: out[o] = centre + sum_j w[j] (x[o + j] + x[o + 2 R - j]), x = window of 8 + 2 R values
+template <int R>
+__device__ __forceinline__ void reg_line(const float* __restrict__ src, const RegTaps& t, float (&acc)[kFP])
+{
+    constexpr int WIN = RegGauss<R>::WIN;
+    float x[WIN];
+#pragma unroll
+    for (int k = 0; k < WIN; k += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(src + k);
+        x[k] = v.x; x[k + 1] = v.y; x[k + 2] = v.z; x[k + 3] = v.w;
+    }
+#pragma unroll
+    for (int o = 0; o < kFP; ++o) acc[o] = x[R + o] * t.wc;
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+        const float wgt = t.w[j];
+#pragma unroll
+        for (int o = 0; o < kFP; ++o) acc[o] = fmaf(x[o + j] + x[o + 2 * R - j], wgt, acc[o]);
+    }
+}
+
+template <typename TS, int MODE, int R>
+__global__ void __launch_bounds__(kNT) fbk_gauss2d_reg(const __grid_constant__ GaussParams p, const __grid_constant__ RegTaps tf)
+{
+    using G = RegGauss<R>;
+    constexpr int IN = G::IN, PITCH = G::PITCH;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* s_in = reinterpret_cast<float*>(smem_raw);              // [IN][PITCH]: input tile, halo R
+    float* s_t = s_in + (size_t)IN * PITCH;                        // [kFT][PITCH]: row pass, transposed: s_t[x][y]
+    const int x0 = blockIdx.x * kFT, y0 = blockIdx.y * kFT, tid = threadIdx.x;
+    const int img = (MODE == MODE_MASK && p.dst_index) ? p.dst_index[blockIdx.z] : (int)blockIdx.z;     // image of dst
+    const TS* base = reinterpret_cast<const TS*>(p.src) + (size_t)blockIdx.z * p.src_stride;
+    float span = 0.f;
+    if (MODE == MODE_MASK) span = p.span ? (p.span[1] - p.span[0]) : p.span_value;
+    {
+        // batches of independent loads (the tile load is pure latency otherwise): UN values per thread in flight
+        constexpr int TOT = IN * IN, UN = 6;
+        for (int i0 = tid; i0 < TOT; i0 += kNT * UN) {
+            TS v[UN];
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                const int i = i0 + u * kNT;
+                const int yy = i / IN, xx = i - yy * IN;           // IN is a compile-time constant
+                const int ysrc = min(max(y0 + yy - R, 0), p.h - 1), xsrc = min(max(x0 + xx - R, 0), p.w - 1);
+                v[u] = i < TOT ? __ldg(base + (size_t)ysrc * p.w + xsrc) : TS(0);
+            }
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                const int i = i0 + u * kNT;
+                const int yy = i / IN, xx = i - yy * IN;
+                if (i < TOT) s_in[yy * PITCH + xx] = MODE == MODE_MASK ? (v[u] ? 0.f : span) : (float)v[u];
+            }
+        }
+    }
+    __syncthreads();
+    // row pass: item = (row yy, strip of 8 outputs); consecutive threads take consecutive rows (pitch = 4 mod 32: the
+    // 128-bit loads of 8 consecutive rows fall into different banks)
+    for (int i = tid; i < IN * (kFT / kFP); i += kNT) {
+        const int strip = i / IN, yy = i - strip * IN;
+        float acc[kFP];
+        reg_line<R>(s_in + yy * PITCH + strip * kFP, tf, acc);
+#pragma unroll
+        for (int o = 0; o < kFP; ++o) s_t[(strip * kFP + o) * PITCH + yy] = acc[o];
+    }
+    __syncthreads();
+    // column pass: item = (column xx, strip of 8 output rows); consecutive threads take consecutive columns
+    for (int i = tid; i < kFT * (kFT / kFP); i += kNT) {
+        const int ys = i / kFT, xx = i - ys * kFT;
+        float acc[kFP];
+        reg_line<R>(s_t + xx * PITCH + ys * kFP, tf, acc);
+        const int x = x0 + xx;
+        if (x >= p.w) continue;
+#pragma unroll
+        for (int o = 0; o < kFP; ++o) {
+            const int yy = ys * kFP + o, y = y0 + yy;
+            if (y >= p.h) break;
+            const float g = acc[o];
+            float* out = p.dst + ((size_t)img * p.h + y) * p.w + x;
+            if (MODE == MODE_BLUR) {
+                *out = g;
+            } else if (MODE == MODE_DOG) {
+                float f = __fsub_rn(s_in[(yy + R) * PITCH + xx + R], g);     // img0f - img1f
                 *out = p.take_abs ? fabsf(f) : f;
             } else {
                 const float mf = __fdiv_rn(__fmul_rn(g, p.sc2), p.s02);
@@ -342,7 +460,8 @@ struct CropParams {
     void* out;
     int has_cover;         // only pixels whose source position lies STRICTLY inside (cx0, cx1) x (cy0, cy1) are rendered
     double cx0, cy0, cx1, cy1;
-    const unsigned char* block_full;   // optional [n]: nonzero = the whole block counts as covered (renderer.py:443-444)
+    const int* block_slot;             // optional [n]: < 0 = the whole block counts as covered (renderer.py:443-444), else the
+                                       // image of mask_out that receives the block's mask (compact: only partial blocks have one)
     unsigned char* mask_out;
     const fb_crop_src* srcs;           // optional [n]: per-block source image and origin (blocks of many images in one launch)
 };
@@ -377,8 +496,9 @@ __global__ void __launch_bounds__(256) fbk_crop_blocks(const __grid_constant__ C
     const double xs = __dadd_rn(__dadd_rn(__dmul_rn(xx, q[4]), __dmul_rn(yy, q[5])), q[6]);
     const double ys = __dadd_rn(__dadd_rn(__dmul_rn(xx, q[7]), __dmul_rn(yy, q[8])), q[9]);
     if (p.has_cover) {
-        const bool inside = (p.block_full && p.block_full[b]) || (xs > p.cx0 && xs < p.cx1 && ys > p.cy0 && ys < p.cy1);
-        if (p.mask_out) p.mask_out[((size_t)b * p.bh + row) * p.bw + col] = inside ? 1 : 0;
+        const int slot = p.block_slot ? p.block_slot[b] : b;
+        const bool inside = slot < 0 || (xs > p.cx0 && xs < p.cx1 && ys > p.cy0 && ys < p.cy1);
+        if (p.mask_out && slot >= 0) p.mask_out[((size_t)slot * p.bh + row) * p.bw + col] = inside ? 1 : 0;
         if (!inside) {
             reinterpret_cast<TS*>(p.out)[((size_t)b * p.bh + row) * p.bw + col] = (TS)p.fill;
             return;
@@ -433,7 +553,8 @@ __global__ void __launch_bounds__(256) fbk_crop_blocks4(const __grid_constant__ 
     const TS* img = reinterpret_cast<const TS*>(c.img);
     TS px[4];
     unsigned char inside4[4];
-    const bool whole = p.has_cover && p.block_full && p.block_full[b];
+    const int slot = (p.has_cover && p.block_slot) ? p.block_slot[b] : b;
+    const bool whole = p.has_cover && slot < 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const double xx = __dadd_rn(q0, __dmul_rn((double)(col0 + k), q2));
@@ -469,7 +590,8 @@ __global__ void __launch_bounds__(256) fbk_crop_blocks4(const __grid_constant__ 
     typename Vec4<TS>::type v;
     v.x = px[0]; v.y = px[1]; v.z = px[2]; v.w = px[3];
     *reinterpret_cast<typename Vec4<TS>::type*>(reinterpret_cast<TS*>(p.out) + o) = v;
-    if (p.has_cover && p.mask_out) *reinterpret_cast<uchar4*>(p.mask_out + o) = make_uchar4(inside4[0], inside4[1], inside4[2], inside4[3]);
+    if (p.has_cover && p.mask_out && slot >= 0)
+        *reinterpret_cast<uchar4*>(p.mask_out + ((size_t)slot * p.bh + row) * p.bw + col0) = make_uchar4(inside4[0], inside4[1], inside4[2], inside4[3]);
 }
 
 int check_device(int device)
@@ -543,11 +665,41 @@ int launch_gauss_f32(const GaussParams& p, cudaStream_t st)
     }
 }
 
+template <typename TS, int MODE, int R>
+int launch_gauss_reg_r(const GaussParams& p, cudaStream_t st)
+{
+    RegTaps tf{};
+    const int r = p.taps.radius;
+    tf.wc = (float)p.taps.w[r];
+    for (int j = 0; j < R; ++j) tf.w[j] = j < R - r ? 0.f : (float)p.taps.w[j - (R - r)];     // zero taps on the outside
+    const size_t smem = RegGauss<R>::SMEM;
+    FB_CU(cudaFuncSetAttribute(fbk_gauss2d_reg<TS, MODE, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((p.w + kFT - 1) / kFT, (p.h + kFT - 1) / kFT, p.n);
+    fbk_gauss2d_reg<TS, MODE, R><<<grid, kNT, smem, st>>>(p, tf);
+    fb_count_launches(1);
+    FB_CU(cudaGetLastError());
+    return FB_OK;
+}
+
+template <typename TS, int MODE>
+int launch_gauss_reg(const GaussParams& p, cudaStream_t st)
+{
+    const int r = p.taps.radius;
+    if (r <= 8) return launch_gauss_reg_r<TS, MODE, 8>(p, st);
+    if (r <= 12) return launch_gauss_reg_r<TS, MODE, 12>(p, st);
+    if (r <= 16) return launch_gauss_reg_r<TS, MODE, 16>(p, st);
+    if (r <= 20) return launch_gauss_reg_r<TS, MODE, 20>(p, st);
+    return launch_gauss_reg_r<TS, MODE, 24>(p, st);
+}
+
+bool g_gauss_blocked = false;     // FB_GAUSS_BLOCKED=1: the shared-memory window kernel of round 1 (comparison runs)
+
 template <typename TS, int MODE>
 int launch_gauss_acc(const GaussParams& p, bool exact, cudaStream_t st)
 {
     if (exact) return launch_gauss<TS, MODE, double>(p, st);
     if (g_gauss_legacy) return launch_gauss<TS, MODE, float>(p, st);
+    if (p.taps.radius <= 24 && !g_gauss_blocked) return launch_gauss_reg<TS, MODE>(p, st);
     return launch_gauss_f32<TS, MODE>(p, st);
 }
 
@@ -563,10 +715,19 @@ extern "C" int fb_masked_dog(const void* img, const unsigned char* mask, int n, 
                              double sigma, double ptp, int flags, float* out, void* work, long long work_bytes,
                              int device, void* stream)
 {
+    return fb_masked_dog_sparse(img, mask, nullptr, n, h, w, in_dtype, mask_n, sigma, ptp, flags, out, work, work_bytes, device, stream);
+}
+
+extern "C" int fb_masked_dog_sparse(const void* img, const unsigned char* mask, const int* mask_images, int n, int h, int w, int in_dtype,
+                                    int mask_n, double sigma, double ptp, int flags, float* out, void* work, long long work_bytes,
+                                    int device, void* stream)
+{
     if (n < 0 || h < 1 || w < 1) return fb_failf(FB_EINVAL, "bad shape n=%d %dx%d", n, h, w);
     g_gauss_legacy = getenv("FB_GAUSS_LEGACY") != nullptr;
+    g_gauss_blocked = getenv("FB_GAUSS_BLOCKED") != nullptr;
     if (in_dtype != FB_F32 && in_dtype != FB_U8) return fb_failf(FB_EINVAL, "masked_dog: dtype %d not supported (float32 / uint8)", in_dtype);
-    if (mask && mask_n != 1 && mask_n != n) return fb_failf(FB_EINVAL, "mask_n must be 1 or n");
+    if (mask && !mask_images && mask_n != 1 && mask_n != n) return fb_failf(FB_EINVAL, "mask_n must be 1 or n");
+    if (mask && mask_images && (mask_n < 1 || mask_n > n)) return fb_failf(FB_EINVAL, "mask_n must be 1 .. n with an image list");
     if (n == 0) return FB_OK;
     if (!img || !out || !work) return fb_failf(FB_EINVAL, "null pointer");
     if (work_bytes < fb_masked_dog_workspace(n, h, w)) return fb_failf(FB_EINVAL, "workspace too small (%lld < %lld)", work_bytes, fb_masked_dog_workspace(n, h, w));
@@ -600,7 +761,14 @@ extern "C" int fb_masked_dog(const void* img, const unsigned char* mask, int n, 
     const double sigma_c = sqrt(sigma * sigma + sigma * sigma);
     if (!make_taps(sigma_c, p.taps)) return fb_failf(FB_ESIZE, "sigma %g too large for the mask term", sigma);
     p.sc2 = (float)(sigma_c * sigma_c); p.s02 = (float)(sigma * sigma);
-    p.src = mask; p.dst = out; p.src_stride = mask_n == 1 ? 0 : (long long)h * w; p.take_abs = (flags & FB_DOG_UNSIGNED) ? 1 : 0;
+    p.src = mask; p.dst = out; p.take_abs = (flags & FB_DOG_UNSIGNED) ? 1 : 0;
+    if (mask_images) {
+        // only the listed images carry masked pixels: for the others the term is zero and |x| - 0 keeps x as it is
+        p.n = mask_n; p.dst_index = mask_images; p.src_stride = (long long)h * w;
+        if ((flags & FB_DOG_UNSIGNED) && mask_n < n) return fb_failf(FB_EINVAL, "unsigned output needs the mask pass on every image");
+    } else {
+        p.src_stride = mask_n == 1 ? 0 : (long long)h * w;
+    }
     return launch_gauss_acc<unsigned char, MODE_MASK>(p, exact, st);
 }
 
@@ -669,8 +837,8 @@ static int crop_launch(CropParams& p, int in_dtype, double fillval, int device, 
         q.n = n - lo < 65535 ? n - lo : 65535;
         q.blocks = p.blocks + (size_t)lo * 10;
         q.out = (char*)p.out + (size_t)lo * bh * bw * esz;
-        if (p.mask_out) q.mask_out = p.mask_out + (size_t)lo * bh * bw;
-        if (p.block_full) q.block_full = p.block_full + lo;
+        if (p.mask_out && !p.block_slot) q.mask_out = p.mask_out + (size_t)lo * bh * bw;
+        if (p.block_slot) q.block_slot = p.block_slot + lo;
         if (p.srcs) q.srcs = p.srcs + lo;
         if (vec4) {
             dim3 grid((bh * (bw / 4) + 255) / 256, q.n);
@@ -689,7 +857,7 @@ static int crop_launch(CropParams& p, int in_dtype, double fillval, int device, 
 
 extern "C" int fb_crop_blocks(const void* img, int ih, int iw, int in_dtype, const double* blocks, int n, int bh, int bw,
                               double origin_x, double origin_y, double fillval, void* out,
-                              const double* cover, const unsigned char* block_full, unsigned char* mask_out, int device, void* stream)
+                              const double* cover, const int* block_slot, unsigned char* mask_out, int device, void* stream)
 {
     if (n < 0 || ih < 1 || iw < 1 || bh < 1 || bw < 1) return fb_failf(FB_EINVAL, "bad shape");
     if (in_dtype != FB_F32 && in_dtype != FB_U8) return fb_failf(FB_EINVAL, "crop_blocks: dtype %d not supported", in_dtype);
@@ -699,7 +867,7 @@ extern "C" int fb_crop_blocks(const void* img, int ih, int iw, int in_dtype, con
     p.img = img; p.ih = ih; p.iw = iw; p.blocks = blocks; p.n = n; p.bh = bh; p.bw = bw;
     p.ox = origin_x; p.oy = origin_y; p.out = out;
     p.has_cover = cover ? 1 : 0; p.mask_out = cover ? mask_out : nullptr;
-    if (cover) { p.cx0 = cover[0]; p.cy0 = cover[1]; p.cx1 = cover[2]; p.cy1 = cover[3]; p.block_full = block_full; }
+    if (cover) { p.cx0 = cover[0]; p.cy0 = cover[1]; p.cx1 = cover[2]; p.cy1 = cover[3]; p.block_slot = block_slot; }
     return crop_launch(p, in_dtype, fillval, device, stream);
 }
 

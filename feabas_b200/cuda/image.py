@@ -81,9 +81,11 @@ def stack_minmax(stack):
     return out
 
 
-def masked_dog_device(img, sigma, mask=None, signed=True, ptp=None, exact=False, out=None):
+def masked_dog_device(img, sigma, mask=None, signed=True, ptp=None, exact=False, out=None, mask_images=None):
     """``img``: CUDA tensor ``(..., H, W)`` float32 or uint8; ``mask``: None or CUDA tensor broadcastable to
-    ``img`` (nonzero = keep) that is known NOT to be all true.  Returns float32, same shape."""
+    ``img`` (nonzero = keep) that is known NOT to be all true.  ``mask_images``: int32 CUDA tensor, one entry per image of
+    ``mask``: the image of the stack that mask belongs to (``mask`` then only covers the images that have masked pixels;
+    ``fb_masked_dog_sparse``).  Returns float32, same shape."""
     shape = img.shape
     h, w = shape[-2:]
     n = int(np.prod(shape[:-2])) if len(shape) > 2 else 1
@@ -95,8 +97,12 @@ def masked_dog_device(img, sigma, mask=None, signed=True, ptp=None, exact=False,
         img = img.to(torch.float32)
     if out is None:
         out = torch.empty(shape, dtype=torch.float32, device=img.device)
-    mask_n, mptr = 1, None
-    if mask is not None:
+    mask_n, mptr, iptr = 1, None, None
+    if mask is not None and mask_images is not None:
+        m = mask if mask.dtype == torch.uint8 else (mask != 0).to(torch.uint8)
+        m = m.reshape(-1, h, w).contiguous()
+        mask_n, mptr, iptr = m.shape[0], m.data_ptr(), mask_images.data_ptr()
+    elif mask is not None:
         m = mask
         if m.dtype != torch.uint8:
             m = (m != 0).to(torch.uint8)
@@ -110,9 +116,9 @@ def masked_dog_device(img, sigma, mask=None, signed=True, ptp=None, exact=False,
     wb = L.fb_masked_dog_workspace(n, h, w)
     work = torch.empty(wb, dtype=torch.uint8, device=img.device)
     flags = (0 if signed else _lib.FB_DOG_UNSIGNED) | (_lib.FB_DOG_EXACT if exact else 0)
-    _lib.check(L.fb_masked_dog(img.data_ptr(), mptr, n, h, w, _code(img), mask_n, float(sigma),
-                               float('nan') if ptp is None else float(ptp), flags, out.data_ptr(), work.data_ptr(), wb,
-                               img.device.index, _stream(img)))
+    _lib.check(L.fb_masked_dog_sparse(img.data_ptr(), mptr, iptr, n, h, w, _code(img), mask_n, float(sigma),
+                                      float('nan') if ptp is None else float(ptp), flags, out.data_ptr(), work.data_ptr(), wb,
+                                      img.device.index, _stream(img)))
     return out
 
 
@@ -176,7 +182,7 @@ def resize_mask(mask, factor, **kwargs):
     return out if on_gpu else out.cpu().numpy()
 
 
-def crop_blocks_masked(img, blocks, block_shape, origin=None, fillval=0, cover=None, out=None):
+def crop_blocks_masked(img, blocks, block_shape, origin=None, fillval=0, cover=None, out=None, compact=False):
     """Gather ``len(blocks)`` blocks of ``block_shape = (bh, bw)`` from the 2-D CUDA tensor ``img``.
 
     ``blocks``: ``N x 10`` float64 (numpy or CUDA): x0, y0, step_x, step_y, A00, A10, t0, A01, A11, t1
@@ -186,7 +192,10 @@ def crop_blocks_masked(img, blocks, block_shape, origin=None, fillval=0, cover=N
     the mesh covers (``AffineMesh.covered_rect`` in image pixel coordinates), or None.  The reference's rule
     (feabas/renderer.py:436-449): a block whose footprint sticks out of the covered region by less than one square
     pixel is rendered whole, otherwise only the pixels whose source position is strictly inside the region.
-    Returns ``(stack, mask)``; ``mask`` (uint8, 1 = rendered) is None when every block is rendered whole."""
+    Returns ``(stack, mask)``; ``mask`` (uint8, 1 = rendered) is None when every block is rendered whole.  With
+    ``compact=True`` the third value ``mask_images`` (int32 CUDA tensor) lists the blocks that are only partly covered and
+    ``mask`` holds one image per entry of it (the layout ``masked_dog_device(..., mask_images=...)`` takes); the fourth,
+    ``any_covered``, is False when no pixel of the whole batch can be covered."""
     bh, bw = int(block_shape[0]), int(block_shape[1])
     blk_host = None
     if not is_cuda_tensor(blocks):
@@ -196,11 +205,14 @@ def crop_blocks_masked(img, blocks, block_shape, origin=None, fillval=0, cover=N
     if out is None:
         out = torch.empty((n, bh, bw), dtype=img.dtype, device=img.device)
     mask, cptr, mptr, fptr = None, None, None, None
-    whole = None
+    whole, mask_images, any_covered = None, None, True
     if cover is not None and n:
         if blk_host is None:
             blk_host = blocks.cpu().numpy()
-        whole = footprint_uncovered_area(blk_host, bh, bw, cover) < 1
+        uncovered = footprint_uncovered_area(blk_host, bh, bw, cover)
+        whole = uncovered < 1
+        full_area = np.abs(blk_host[:, 4] * blk_host[:, 8] - blk_host[:, 5] * blk_host[:, 7]) * (bw * blk_host[:, 2]) * (bh * blk_host[:, 3])
+        any_covered = bool(np.any(uncovered < full_area * (1 - 1e-9)))
     if origin is None:
         if blk_host is None:
             blk_host = blocks.cpu().numpy()
@@ -213,16 +225,29 @@ def crop_blocks_masked(img, blocks, block_shape, origin=None, fillval=0, cover=N
         import ctypes
         carr = (ctypes.c_double * 4)(*[float(v) for v in cover])
         cptr = ctypes.cast(carr, ctypes.c_void_p)
-        mask = torch.empty((n, bh, bw), dtype=torch.uint8, device=img.device)
+        if compact:
+            part = np.nonzero(~whole)[0].astype(np.int32)
+            slot = np.full(n, -1, dtype=np.int32)
+            slot[part] = np.arange(part.size, dtype=np.int32)
+            both = torch.from_numpy(np.concatenate((slot, part))).to(img.device, non_blocking=True)
+            slots, mask_images = both[:n], both[n:]
+            mask = torch.empty((part.size, bh, bw), dtype=torch.uint8, device=img.device)
+            fptr = slots.data_ptr()
+        else:
+            mask = torch.empty((n, bh, bw), dtype=torch.uint8, device=img.device)
+            if n and whole.any():
+                slots = torch.from_numpy(np.where(whole, -1, np.arange(n)).astype(np.int32)).to(img.device, non_blocking=True)
+                fptr = slots.data_ptr()
         mptr = mask.data_ptr()
-        if n and whole.any():
-            full = torch.from_numpy(whole.astype(np.uint8)).to(img.device, non_blocking=True)
-            fptr = full.data_ptr()
     if n:
         ih, iw = img.shape
         _lib.check(_lib.lib().fb_crop_blocks(img.data_ptr(), ih, iw, _code(img), blocks.data_ptr(), n, bh, bw,
                                              float(origin[0]), float(origin[1]), float(fillval), out.data_ptr(),
                                              cptr, fptr, mptr, img.device.index, _stream(img)))
+    if not compact and mask is not None and whole is not None and whole.any():
+        mask[torch.from_numpy(np.nonzero(whole)[0]).to(img.device)] = 1          # (whole blocks: the kernel wrote no mask)
+    if compact:
+        return out, mask, mask_images, any_covered
     return out, mask
 
 

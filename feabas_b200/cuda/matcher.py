@@ -199,22 +199,25 @@ def _render_stack(mesh, loader, bboxes, sigma, ptp_hint=None, mask_range=None):
             scale = mesh.resolution / loader.resolution
             x_lo, y_lo, x_hi, y_hi = ((v + 0.5) * scale - 0.5 for v in (x_lo, y_lo, x_hi, y_hi))
         cover = (x_lo - loader.x0, y_lo - loader.y0, x_hi - loader.x0, y_hi - loader.y0)
-    stack, mask = _img.crop_blocks_masked(loader.tensor, rows, shape, fillval=loader.default_fillval, cover=cover)
-    if sigma > 0:
-        if mask is not None:
-            lo, hi = (int(v) for v in torch.stack((mask.min(), mask.max())).cpu())
-            if hi == 0:
-                return None
-            if lo == 1:
-                mask = None
-        if mask_range is not None:                      # renderer.py:633-636: only intensities inside the range are valid
-            rng = np.atleast_1d(mask_range)
-            valid = (stack >= float(rng[0])) & (stack <= float(rng[-1]))
-            mask = valid if mask is None else (mask.to(torch.bool) & valid)
-            if bool(mask.all()):
-                mask = None
-        stack = _img.masked_dog_device(stack, sigma, mask, ptp=ptp_hint)
-    return stack
+    if sigma <= 0:
+        return _img.crop_blocks_masked(loader.tensor, rows, shape, fillval=loader.default_fillval, cover=None)[0]
+    if mask_range is not None:
+        # renderer.py:633-636: only intensities inside the range are valid -- a mask for every block
+        stack, mask = _img.crop_blocks_masked(loader.tensor, rows, shape, fillval=loader.default_fillval, cover=cover)
+        rng = np.atleast_1d(mask_range)
+        valid = (stack >= float(rng[0])) & (stack <= float(rng[-1]))
+        mask = valid if mask is None else (mask.to(torch.bool) & valid)
+        lo, hi = (int(v) for v in torch.stack((mask.min(), mask.max())).cpu())
+        if hi == 0:
+            return None
+        return _img.masked_dog_device(stack, sigma, None if lo == 1 else mask, ptp=ptp_hint)
+    # masks only for the blocks that hang over the border of the mesh (a block without masked pixels gets no mask term:
+    # the term is zero there); nothing is read back from the device
+    stack, mask, mask_images, any_covered = _img.crop_blocks_masked(loader.tensor, rows, shape, fillval=loader.default_fillval,
+                                                                    cover=cover, compact=True)
+    if not any_covered:
+        return None
+    return _img.masked_dog_device(stack, sigma, mask, ptp=ptp_hint, mask_images=mask_images)
 
 
 def bboxes_mesh_renderer_matcher(mesh0, mesh1, image_loader0, image_loader1, bboxes0, bboxes1, **kwargs):

@@ -123,6 +123,14 @@ long long fb_masked_dog_workspace(int n, int h, int w);
 int fb_masked_dog(const void* img, const unsigned char* mask, int n, int h, int w, int in_dtype, int mask_n,
                   double sigma, double ptp, int flags, float* out, void* work, long long work_bytes,
                   int device, void* stream);
+/* The same with masks for SOME images only: mask holds mask_n images, mask_images[i] (device, mask_n ints) says
+ * which image of the stack mask i belongs to; images not listed have no masked pixel (their mask term is zero, the
+ * result is what the reference computes for them).  The block passes of the matcher use it: only blocks that hang
+ * over the border of the mesh carry a mask (feabas/renderer.py:436-449), the band-pass still sees the whole batch
+ * (ptp of the whole stack, feabas/common.py:369).                                                              */
+int fb_masked_dog_sparse(const void* img, const unsigned char* mask, const int* mask_images, int n, int h, int w, int in_dtype,
+                         int mask_n, double sigma, double ptp, int flags, float* out, void* work, long long work_bytes,
+                         int device, void* stream);
 
 /* {min, max} (float32) of each of n images of `elems` elements: np.ptp of blocks
  * (feabas/matcher.py:196,205) and of stacks (feabas/common.py:369).  minmax: n x 2 floats.      */
@@ -157,12 +165,14 @@ int fb_resize_nearest(const unsigned char* src, int n, int h, int w, double inv_
  * renderer.py:447) are not rendered (they keep `fillval`) and, when mask_out != NULL
  * (n x bh x bw bytes, device), are flagged 0 there: the validity mask of
  * crop_field_affine(precise_mask=True) that masked_dog_filter consumes.
- * block_full (device, n bytes, may be NULL; only read with cover): nonzero = the block counts as
- * covered as a whole -- the reference skips the per-pixel test when less than one square pixel
- * of the block's footprint is uncovered (renderer.py:443-444); the caller evaluates that rule.  */
+ * block_slot (device, n ints, may be NULL = block b writes mask image b; only read with cover):
+ * < 0: the block counts as covered as a whole -- the reference skips the per-pixel test when less
+ * than one square pixel of the block's footprint is uncovered (renderer.py:443-444), the caller
+ * evaluates that rule -- and writes no mask; >= 0: the image of mask_out that receives the block's
+ * mask (mask_out then only holds the partially covered blocks, see fb_masked_dog_sparse).        */
 int fb_crop_blocks(const void* img, int ih, int iw, int in_dtype, const double* blocks, int n, int bh, int bw,
                    double origin_x, double origin_y, double fillval, void* out,
-                   const double* cover, const unsigned char* block_full, unsigned char* mask_out,
+                   const double* cover, const int* block_slot, unsigned char* mask_out,
                    int device, void* stream);
 
 /* The same gather for blocks that come from MANY source images in one launch: the block lists of all the

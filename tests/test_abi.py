@@ -53,7 +53,7 @@ def test_plan_info(lib):
     assert 12.5e6 < big['ws_bytes_per_pair'] < 13.0e6
     small = lib.plan_info(74, 67, 74, 67, lib.FB_F32, 150, 135, 0x2 | (2 << 2))
     assert small['path'] == 'fused-warp' and small['smem_fused'] <= 227 * 1024
-    odd = lib.plan_info(70, 70, 70, 70, lib.FB_F32, 140, 140, 0x2 | (2 << 2))     # 140 = 2^2 5 7: not in the warp-fused table
+    odd = lib.plan_info(72, 72, 72, 72, lib.FB_F32, 144, 144, 0x2 | (2 << 2))     # 144 x 144: fits one SM, not in the warp-fused table
     assert odd['path'] == 'fused'
 
 
