@@ -697,26 +697,28 @@ def cpu_jobs_arm(wl, seed, n_sample):
     return pool, cores, ids, sdir
 
 
-def _gpu_job_worker(workload, seed, steps, local, barrier, queue):
-    """One of P worker processes sharing a GPU (FEABAS's own parallel model: spawned workers, one overlap / section pair
-    per task, feabas/concurrent.py:59-96): every worker has its own CUDA context and runs the job list `steps` times."""
+def _gpu_job_worker(workload, seed, steps, local, barrier, queue, part, parts):
+    """One of P worker processes sharing a GPU (FEABAS's own parallel model: spawned workers, feabas/concurrent.py:59-96):
+    every worker has its own CUDA context, takes the contiguous range `part` of `parts` of the fixed job list and
+    advances it in lockstep (``stitching_matcher_many`` / ``section_matcher_many``), `steps` times."""
     try:
         import torch
         torch.cuda.set_device(local)
         import feabas_b200.cuda as fc
+        from feabas_b200.cuda import shard
         wl = dict(WORKLOADS[workload])
         stitch = wl['kind'] == 'stitch'
-        jobs = [(_np(a), _np(b)) for a, b in make_jobs(wl, seed)]
+        lo, hi = shard.shard_range(job_count(wl), parts, part)
+        jobs = [(_np(a), _np(b)) for a, b in make_jobs(wl, seed, lo, hi)]
         lib = fc._lib.lib()
 
         def run():
-            for a, b in jobs:
-                if stitch:
-                    fc.stitching_matcher(a, b, device=local, **STITCH_KW)
-                else:
-                    hh, ww = a.shape
-                    fc.section_matcher(fc.AffineMesh.from_bbox((0, 0, ww, hh), uid=0), fc.AffineMesh.from_bbox((0, 0, ww, hh), uid=1),
-                                       fc.ArrayLoader(a, device=local), fc.ArrayLoader(b, device=local), **SECTION_KW)
+            if stitch:
+                fc.stitching_matcher_many(jobs, device=local, **STITCH_KW)
+            else:
+                fc.section_matcher_many([(fc.AffineMesh.from_bbox((0, 0, a.shape[1], a.shape[0]), uid=0),
+                                          fc.AffineMesh.from_bbox((0, 0, a.shape[1], a.shape[0]), uid=1),
+                                          fc.ArrayLoader(a, device=local), fc.ArrayLoader(b, device=local)) for a, b in jobs], **SECTION_KW)
         for _ in range(2):
             run()
         torch.cuda.synchronize()
@@ -739,17 +741,17 @@ def multi_process_throughput(workload, workers, steps, local):
     import multiprocessing as mp
     ctx = mp.get_context('spawn')
     barrier, queue = ctx.Barrier(workers + 1), ctx.Queue()
-    procs = [ctx.Process(target=_gpu_job_worker, args=(workload, 11 + k, steps, local, barrier, queue)) for k in range(workers)]
+    procs = [ctx.Process(target=_gpu_job_worker, args=(workload, 1, steps, local, barrier, queue, k, workers)) for k in range(workers)]
     for pr in procs:
         pr.start()
     try:
-        barrier.wait(timeout=300)
+        barrier.wait(timeout=600)
     except Exception:
         for pr in procs:
             pr.terminate()
         return {'workers': workers, 'error': 'workers did not reach the start barrier'}
     t0 = time.perf_counter()
-    res = [queue.get(timeout=600) for _ in procs]
+    res = [queue.get(timeout=900) for _ in procs]
     dt = time.perf_counter() - t0
     for pr in procs:
         pr.join(timeout=60)
@@ -757,8 +759,9 @@ def multi_process_throughput(workload, workers, steps, local):
         return {'workers': workers, 'error': str([r for r in res if r[0] == 'error'][0][1])}
     return {'workers': workers, 'value': sum(r[0] for r in res) / dt, 'unit': 'matches/s', 'jobs_per_s': sum(r[1] for r in res) / dt,
             'steps_per_worker': steps, 'seconds': dt,
-            'note': 'wall clock over P spawned worker processes sharing this GPU (one CUDA context each, host strips / thumbnails in), '
-                    'one matcher call per job, the way FEABAS fans overlaps / section pairs out to workers; supplementary'}
+            'note': 'wall clock over P spawned worker processes sharing this GPU (one CUDA context each, host arrays in), every worker '
+                    'advancing its contiguous share of the job list in lockstep: the coarse-to-fine loops are host (Python) bound in one '
+                    'process, so FEABAS\'s own worker fan-out (feabas/concurrent.py) still pays on one GPU; supplementary'}
 
 
 def _pack_results(results):
@@ -963,9 +966,10 @@ def bench_jobs(args, wl, rank, world, local, warmup):
                'sample': f'{n_tasks} jobs ({len(ids)} spread evenly over the list of {total}, cycled; the arrays of this run), one job per task on {cores} '
                          f"single-thread workers (oracle port of {'stitching_matcher' if stitch else 'the section_matcher loop'}), {s_:.1f} s wall"}
     multi = None
-    if args.workers > 0 and world == 1 and not wl.get('synth'):
+    if args.workers > 0 and world == 1:
+        del djobs
         torch.cuda.empty_cache()
-        multi = multi_process_throughput(args.workload, args.workers, max(20, args.steps), local)
+        multi = multi_process_throughput(args.workload, args.workers, max(3, args.steps), local)
     line = {'metric': 'xcorr_block_matches_per_sec', 'value': value, 'unit': 'matches/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic', 'config': config, 'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline,

@@ -434,7 +434,7 @@ static size_t fast_smem(int n, int nw)
 {
     int E, T; fast_et(n, E, T);
     const int lines = fast_lines(T, nw);
-    return ((size_t)lines * (n + E + 16) + (kLaneTwiddles ? 0 : n)) * sizeof(cx<float>);
+    return ((size_t)lines * ((wfft_region(E, T) + 15 + 16) & ~15) + (kLaneTwiddles ? 0 : n)) * sizeof(cx<float>);
 }
 
 static std::atomic<int> g_num_sms{0};

@@ -122,6 +122,63 @@ __device__ __forceinline__ void named_barrier(int id, int nthreads)
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// ---- exchange-tile layout for lane groups that are not powers of two ---------------------------------------------
+// 8-byte shared-memory accesses are served one half-warp at a time, 16 slots of 8 bytes per wavefront: a half-warp needs
+// as many wavefronts as its busiest slot holds DISTINCT addresses.  With T = 10, 12, 20 or 24 lanes per line the lines
+// of a warp straddle the half-warps, and the plain layout (tile pitch T + 1, every line's region starting on a 128-byte
+// boundary) puts the lanes of two lines into the same slots: ncu shows 30 - 50 % of the shared-memory wavefronts of the
+// 300 / 600 / 288 families as bank conflicts.  wfft_layout() picks, at compile time (and again on the host for the
+// shared-memory size), the tile pitch and a per-line shift of the tile inside its region with the fewest wavefronts over
+// the two access patterns of WarpFFT::run (stage-A store: lanes consecutive; stage-B load: lanes pitch apart).
+constexpr __host__ __device__ int wfft_wavefronts(int T, int al, int sh0, int a, int b)
+{
+    int total = 0;
+    for (int half = 0; half < 2; ++half) {
+        int addr[16] = {0};
+        for (int i = 0; i < 16; ++i) {
+            int l = half * 16 + i;
+            l = l >= al ? sh0 + (l - al) % (al - sh0) : l;
+            addr[i] = (l / T) * b + (l % T) * a;
+        }
+        int worst = 0;
+        for (int slot = 0; slot < 16; ++slot) {
+            int distinct = 0;
+            for (int i = 0; i < 16; ++i) {
+                if ((addr[i] & 15) != slot) continue;
+                bool seen = false;
+                for (int k = 0; k < i; ++k) seen = seen || addr[k] == addr[i];
+                distinct += seen ? 0 : 1;
+            }
+            worst = distinct > worst ? distinct : worst;
+        }
+        total += worst;
+    }
+    return total;
+}
+struct WfftLayout { int pitch, shift; };
+constexpr __host__ __device__ WfftLayout wfft_layout(int E, int T)
+{
+    if (T >= 32 || (T & (T - 1)) == 0) return WfftLayout{T + 1, 0};        // powers of two: lines and half-warps line up
+    const int lpw = 32 / T, al = lpw * T, sh0 = al > 16 ? 16 : 0;
+    WfftLayout best{T + 1, 0};
+    int cost = 1 << 30;
+    for (int p = T; p < T + 8; ++p)
+        for (int s = 0; s < 16; ++s) {
+            // a line's region starts on a multiple of 16 slots, its tile s * (line in warp) slots further
+            const int c = (2 * wfft_wavefronts(T, al, sh0, 1, 16 * 64 + s) + wfft_wavefronts(T, al, sh0, p, 16 * 64 + s)) * 1024 + (p - T) * 16 + s;
+            if (c < cost) { cost = c; best = WfftLayout{p, s}; }
+        }
+    return best;
+}
+// complex elements a line's region needs: the tile [E][pitch] behind its shift, or the line itself in natural order
+constexpr __host__ __device__ int wfft_region(int E, int T)
+{
+    const WfftLayout l = wfft_layout(E, T);
+    const int lpw = T >= 32 ? 1 : 32 / T;
+    const int tile = E * l.pitch + l.shift * (lpw - 1);
+    return (tile > E * T ? tile : E * T) + 1;
+}
+
 template <int E, int T> struct WarpFFT {
     static_assert(T <= 32 || T == 64, "lanes per line");
     static_assert(E % T == 0 && E / T <= 8 && E % 2 == 0, "E/T stage-B transforms per lane");
@@ -134,21 +191,27 @@ template <int E, int T> struct WarpFFT {
     // one-per-line actions (TMA issue) and sums must skip them
     static constexpr int AL = T >= 32 ? 32 : LPW * T;
     static __device__ __forceinline__ bool is_shadow(int lane) { return lane >= AL; }
+    // the lane a shadow lane repeats: one of the SAME half-warp (8-byte shared-memory accesses are served per half-warp:
+    // a repeated address inside a half is a broadcast, the same address from the other half costs another wavefront)
+    static constexpr int SH0 = AL > 16 ? 16 : 0;
+    static __device__ __forceinline__ int real_lane(int lane) { return lane >= AL ? SH0 + (lane - AL) % (AL - SH0) : lane; }
     // lines a CTA of NW warps works on at a time
     static constexpr __host__ __device__ int lines_per_cta(int nw) { return WPL > 1 ? nw / WPL : nw * LPW; }
     // lane within the line / line within the CTA of this thread
     static __device__ __forceinline__ int lane_in_line(int warp, int lane)
     {
-        return WPL > 1 ? (warp % WPL) * 32 + lane : (lane >= AL ? lane - AL : lane) % T;
+        return WPL > 1 ? (warp % WPL) * 32 + lane : real_lane(lane) % T;
     }
-    static __device__ __forceinline__ int line_in_warp(int lane) { return WPL > 1 ? 0 : (lane >= AL ? lane - AL : lane) / T; }
+    static __device__ __forceinline__ int line_in_warp(int lane) { return WPL > 1 ? 0 : real_lane(lane) / T; }
     static __device__ __forceinline__ int line_in_cta(int warp, int lane) { return WPL > 1 ? warp / WPL : warp * LPW + line_in_warp(lane); }
     // all lanes of a line (bar: a named barrier id private to the line, used only when the line spans warps)
     static __device__ __forceinline__ void line_sync(int bar)
     {
         if constexpr (WPL > 1) named_barrier(bar, 32 * WPL); else __syncwarp();
     }
-    static constexpr int RS = N + E + 1;      // minimum slots per line region
+    static constexpr WfftLayout TL = wfft_layout(E, T);
+    static constexpr int TSH = TL.shift;                  // exchange tile (tuned layout): shift per line of the warp, pitch TL.pitch
+    static constexpr int RS = wfft_region(E, T);          // minimum slots per line region
     // smallest region stride >= RS with stride % 16 == m: makes accesses by (line-minor, slot-major)
     // thread groups of 16/m lines conflict free
     static constexpr __host__ __device__ int stride_mod16(int m) { return RS + ((m - RS % 16) + 16) % 16; }
@@ -162,19 +225,23 @@ template <int E, int T> struct WarpFFT {
     // Forward transform only: inverse transforms are taken as conj(fft(conj(.))) with the
     // conjugations folded into the neighbouring point-wise steps, so that every kernel
     // runs ONE butterfly body (instruction-cache footprint).
-    template <bool PRUNED, class TW>
-    static __device__ __forceinline__ void run(cx<float>* v, cx<float>* region, const TW& tw, int t,
-                                               bool pruned_now = true, int bar = 1)
+    // TUNED: the regions of the lines start on 128-byte boundaries (column kernel: TMA source) and the tile uses the
+    // searched pitch and per-line shift (lw: line of the warp this lane works on); otherwise the plain pitch T + 1
+    template <bool PRUNED, class TW, bool TUNED = false>
+    static __device__ __forceinline__ void run(cx<float>* v, cx<float>* region_base, const TW& tw, int t,
+                                               bool pruned_now = true, int bar = 1, int lw = 0)
     {
+        constexpr int TP = TUNED ? TL.pitch : T + 1;
+        cx<float>* region = region_base + (TUNED ? lw * TSH : 0);
         // first radix-2 level: skipped arithmetic when the upper half of the input is zero; the
         // remaining levels are one shared body
         LaneFFT<E>::template run_first<PRUNED>(v, pruned_now);
-        tw.apply_all(v, [&](int k1, cx<float> a) { region[k1 * (T + 1) + t] = a; });
+        tw.apply_all(v, [&](int k1, cx<float> a) { region[k1 * TP + t] = a; });
         line_sync(bar);
 #pragma unroll
         for (int m = 0; m < M; ++m) {
 #pragma unroll
-            for (int n2 = 0; n2 < T; ++n2) v[m * T + n2] = region[(t + T * m) * (T + 1) + n2];
+            for (int n2 = 0; n2 < T; ++n2) v[m * T + n2] = region[(t + T * m) * TP + n2];
         }
         line_sync(bar);
 #pragma unroll
@@ -416,7 +483,7 @@ __device__ void kfast_columns(const FastParams& fp, unsigned char* smem)
         }
 #pragma unroll 1
         for (int phase = 0; phase < 2; ++phase) {
-            W::template run<PRUNED0>(v, mine, tw, t, phase == 0, lbar);
+            W::template run<PRUNED0, decltype(tw), true>(v, mine, tw, t, phase == 0, lbar, lw);
             if (phase == 0) {
 #pragma unroll
                 for (int j = 0; j < E; ++j) mine[W::out_k(t, j)] = v[W::out_reg(j)];
@@ -509,8 +576,9 @@ __device__ void kfast_rows_inverse(const FastParams& fp, unsigned char* smem)
     float* red = reinterpret_cast<float*>(twsm + StageTw<E, T>::smem_entries());   // [NWARP][R][2] floats + doubles after
     double* redd = reinterpret_cast<double*>(red + NWARP * R * 2);
     const int warp = threadIdx.x >> 5;
-    const bool shadow = (int)threadIdx.x >= T * R;            // T * R not a multiple of 32: the surplus threads repeat the
-    const int tid = shadow ? threadIdx.x - T * R : threadIdx.x;   // first ones (identical loads / stores; sums skip them)
+    const bool shadow = (int)threadIdx.x >= T * R;            // T * R not a multiple of 32: the surplus threads repeat real
+    constexpr int LASTW = (T * R) / 32 * 32, LASTN = (T * R) % 32 ? (T * R) % 32 : 32;   // threads of their own warp (identical
+    const int tid = shadow ? LASTW + ((int)threadIdx.x - T * R) % LASTN : (int)threadIdx.x;   // loads / stores; sums skip them)
     const int r = tid % R, tq = tid / R;                      // stage A: t = tq; stage B: k1 = tq + T m
     StageTw<E, T> tw;
     tw.init(fp.twx, twsm, tq, threadIdx.x, NT);            // (the table copy strides over ALL threads, shadows included)
@@ -647,8 +715,9 @@ __device__ void kfast_rows_inverse_tma(const FastParams& fp, unsigned char* smem
     double* redd = reinterpret_cast<double*>(red + NWARP * R * 2);
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(redd + NWARP * R * 2);
     const int warp = threadIdx.x >> 5;
-    const bool shadow = (int)threadIdx.x >= T * R;            // T * R not a multiple of 32: the surplus threads repeat the
-    const int tid = shadow ? threadIdx.x - T * R : threadIdx.x;   // first ones (identical loads / stores; sums skip them)
+    const bool shadow = (int)threadIdx.x >= T * R;            // T * R not a multiple of 32: the surplus threads repeat real
+    constexpr int LASTW = (T * R) / 32 * 32, LASTN = (T * R) % 32 ? (T * R) % 32 : 32;   // threads of their own warp (identical
+    const int tid = shadow ? LASTW + ((int)threadIdx.x - T * R) % LASTN : (int)threadIdx.x;   // loads / stores; sums skip them)
     const int r = tid % R, tq = tid / R;                      // stage A: t = tq; stage B: k1 = tq + T m
     if (threadIdx.x == 0) mbar_init(bar, 1);
     StageTw<E, T> tw;
