@@ -11,6 +11,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <tuple>
 #include <type_traits>
 #include <vector>
@@ -807,6 +808,28 @@ extern "C" int fb_xcorr_batch_device_ex(const void* img0, const void* img1, int 
     return run_device(q, *ctx, img0, img1, n, dx, dy, conf, peak, mirror, (cudaStream_t)stream);
 }
 
+static std::atomic<long long> g_opt_copy_threads{6};
+
+// dst0 <- src0 (n0 bytes) and dst1 <- src1 (n1 bytes), cut into pieces for up to `copy_threads` host threads
+static void parallel_copy(void* dst0, const void* src0, size_t n0, void* dst1, const void* src1, size_t n1)
+{
+    const int want = (int)g_opt_copy_threads.load();
+    const size_t total = n0 + n1, piece_min = (size_t)4 << 20;
+    int nt = (int)(total / piece_min);
+    nt = nt < 1 ? 1 : (nt > want ? want : nt);
+    if (nt <= 1) { memcpy(dst0, src0, n0); memcpy(dst1, src1, n1); return; }
+    std::vector<std::thread> team;
+    auto part = [&](int k) {
+        // thread k takes the k-th slice of both arrays
+        const size_t a0 = n0 * k / nt, e0 = n0 * (k + 1) / nt, a1 = n1 * k / nt, e1 = n1 * (k + 1) / nt;
+        memcpy((char*)dst0 + a0, (const char*)src0 + a0, e0 - a0);
+        memcpy((char*)dst1 + a1, (const char*)src1 + a1, e1 - a1);
+    };
+    for (int k = 1; k < nt; ++k) team.emplace_back(part, k);
+    part(0);
+    for (auto& th : team) th.join();
+}
+
 extern "C" int fb_xcorr_batch_host(const void* img0, const void* img1, int n, int h0, int w0, int h1, int w1,
                                    int in_dtype, int fft_h, int fft_w, int flags,
                                    double* dx, double* dy, double* conf, double* peak, double* mirror,
@@ -882,8 +905,9 @@ extern "C" int fb_xcorr_batch_host(const void* img0, const void* img1, int n, in
             else CU(cudaEventSynchronize(c.ev_done[s]));      // also implies the slot's H2D finished
         }
         if (!pinned) {
-            memcpy(c.pin[s], src0, (size_t)nb * b0);
-            memcpy((char*)c.pin[s] + off1, src1, (size_t)nb * b1);
+            // pageable arrays (what FEABAS callers pass): staged through the pinned slot by several host threads -- one
+            // thread copies at ~10 GB/s, a fifth of what the link takes
+            parallel_copy(c.pin[s], src0, (size_t)nb * b0, (char*)c.pin[s] + off1, src1, (size_t)nb * b1);
             src0 = (const char*)c.pin[s];
             src1 = (const char*)c.pin[s] + off1;
         }
@@ -955,6 +979,7 @@ extern "C" int fb_set_option(const char* name, long long value)
     if (!strcmp(name, "profile")) { g_opt_profile = value ? 1 : 0; return FB_OK; }
     if (!strcmp(name, "fast_flags")) { g_opt_fast_flags = value; return FB_OK; }
     if (!strcmp(name, "warp_fused")) { g_opt_warp_fused = value ? 1 : 0; return FB_OK; }
+    if (!strcmp(name, "copy_threads")) { if (value < 1 || value > 64) return fail(FB_EINVAL, "copy_threads out of range"); g_opt_copy_threads = value; return FB_OK; }
     if (!strcmp(name, "host_chunk_bytes")) { if (value < 4096) return fail(FB_EINVAL, "host_chunk_bytes too small"); g_opt_host_chunk = value; return FB_OK; }
     return fail(FB_EINVAL, "unknown option %s", name);
 }

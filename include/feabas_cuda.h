@@ -204,6 +204,8 @@ int fb_xcorr_plan_info(int h0, int w0, int h1, int w1, int in_dtype, int fft_h, 
 
 /* Tuning knobs: "ws_bytes" (HBM workspace budget per stream context, default
  * 2 GiB), "host_chunk_bytes" (input bytes per host-path chunk, default 64 MiB),
+ * "copy_threads" (host threads that stage pageable input into the pinned slots, default 6),
+ * "warp_fused" (0/1: small grids on the warp-per-line fused kernel, default 1),
  * "profile" (0/1: time every kernel with CUDA events, see fb_profile_read).      */
 int fb_set_option(const char* name, long long value);
 
