@@ -21,6 +21,7 @@ UNITS = {
     # the register-resident fast path, one translation unit per group of line lengths (parallel build)
     'fb_fast_pow2.cu': FAST_DEPS, 'fb_fast_big.cu': FAST_DEPS, 'fb_fast_r3.cu': FAST_DEPS, 'fb_fast_r5.cu': FAST_DEPS, 'fb_fast_r5b.cu': FAST_DEPS,
     'fb_image.cu': ['fb_common.h', HEADER],
+    'fb_image_ext.cu': ['fb_common.h', HEADER],
     # the warp-fused kernel (whole pair on one SM, register transforms), one translation unit per group of grids
     'fb_wf_a.cu': WF_DEPS, 'fb_wf_b.cu': WF_DEPS, 'fb_wf_c.cu': WF_DEPS,
 }

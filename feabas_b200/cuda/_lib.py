@@ -40,8 +40,11 @@ SYMBOLS = {
     'fb_masked_dog_workspace': (_ll, [_i, _i, _i]),
     'fb_masked_dog': (_i, [_vp, _vp, _i, _i, _i, _i, _i, ctypes.c_double, ctypes.c_double, _i, _vp, _vp, _ll, _i, _vp]),
     'fb_masked_dog_sparse': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, ctypes.c_double, ctypes.c_double, _i, _vp, _vp, _ll, _i, _vp]),
+    'fb_masked_dog_f64_workspace': (_ll, [_i, _i, _i]),
+    'fb_masked_dog_f64': (_i, [_vp, _vp, _i, _i, _i, _i, ctypes.c_double, ctypes.c_double, _i, _vp, _vp, _ll, _i, _vp]),
     'fb_stack_minmax': (_i, [_vp, _i, _ll, _i, _vp, _i, _vp]),
     'fb_resize_area': (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp]),
+    'fb_resize_area_frac': (_i, [_vp, _i, _i, _i, _i, ctypes.c_double, ctypes.c_double, _vp, _i, _i, _i, _vp]),
     'fb_resize_nearest': (_i, [_vp, _i, _i, _i, ctypes.c_double, ctypes.c_double, _vp, _i, _i, _i, _vp]),
     'fb_crop_blocks': (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, ctypes.c_double, ctypes.c_double, ctypes.c_double, _vp, _vp, _vp, _vp, _i, _vp]),
     'fb_crop_blocks_multi': (_i, [_vp, _i, _vp, _i, _i, _i, ctypes.c_double, _vp, _i, _vp]),

@@ -90,10 +90,16 @@ def masked_dog_device(img, sigma, mask=None, signed=True, ptp=None, exact=False,
     h, w = shape[-2:]
     n = int(np.prod(shape[:-2])) if len(shape) > 2 else 1
     img = img.contiguous()
+    if img.dtype == torch.float64:
+        # common.py:363-364 converts only non-floating dtypes: a float64 stack stays float64 throughout
+        if mask_images is not None:
+            raise ValueError('mask_images is a float32 / uint8 feature')
+        return _masked_dog_f64(img, n, h, w, sigma, mask, signed, ptp, out)
     if img.dtype not in (torch.float32, torch.uint8):
-        # common.py:363-364: every non-floating dtype is converted to float32
+        # every non-floating dtype is converted to float32; float16 follows scipy, which filters it as float64 and
+        # hands back float16 -- no caller does that, refuse it rather than guess
         if img.dtype.is_floating_point:
-            raise NotImplementedError('masked_dog_filter on %s images is not implemented (float32 / integer)' % img.dtype)
+            raise TypeError('masked_dog_filter: %s images are not supported (float32 / float64 / integer)' % img.dtype)
         img = img.to(torch.float32)
     if out is None:
         out = torch.empty(shape, dtype=torch.float32, device=img.device)
@@ -122,6 +128,28 @@ def masked_dog_device(img, sigma, mask=None, signed=True, ptp=None, exact=False,
     return out
 
 
+def _masked_dog_f64(img, n, h, w, sigma, mask, signed, ptp, out):
+    """float64 branch of ``masked_dog_device`` (``fb_masked_dog_f64``): float64 in, float64 out."""
+    if out is None:
+        out = torch.empty(img.shape, dtype=torch.float64, device=img.device)
+    mask_n, mptr = 1, None
+    if mask is not None:
+        m = mask if mask.dtype == torch.uint8 else (mask != 0).to(torch.uint8)
+        if m.dim() > 2 and int(np.prod(m.shape[:-2])) > 1:
+            m = m.expand(img.shape).contiguous()
+            mask_n = n
+        else:
+            m = m.reshape(h, w).contiguous()
+        mptr = m.data_ptr()
+    L = _lib.lib()
+    wb = L.fb_masked_dog_f64_workspace(n, h, w)
+    work = torch.empty(wb, dtype=torch.uint8, device=img.device)
+    _lib.check(L.fb_masked_dog_f64(img.data_ptr(), mptr, n, h, w, mask_n, float(sigma), float('nan') if ptp is None else float(ptp),
+                                   0 if signed else _lib.FB_DOG_UNSIGNED, out.data_ptr(), work.data_ptr(), wb,
+                                   img.device.index, _stream(img)))
+    return out
+
+
 def masked_dog_filter(img, sigma, mask=None, signed=True, **kwargs):
     """Drop-in for ``feabas.common.masked_dog_filter`` (common.py:353-377).
 
@@ -147,22 +175,40 @@ def _round_half_even(v):
     return int(np.rint(v))
 
 
+_DBL_EPSILON = 2.220446049250313e-16
+
+
 def resize_area(img, factor, **kwargs):
-    """``cv2.resize(img, None, fx=factor, fy=factor, interpolation=cv2.INTER_AREA)`` for
-    ``factor = 1/k`` (k integer), ``img``: ``(..., H, W)`` uint8 (bit-exact) or float32."""
-    k = int(round(1.0 / factor))
-    if k < 1 or abs(1.0 / factor - k) > 1e-12:
-        raise NotImplementedError(f'INTER_AREA resize only for factors 1/k (got {factor})')
+    """``cv2.resize(img, None, fx=factor, fy=factor, interpolation=cv2.INTER_AREA)`` for any ``factor <= 1``
+    (matcher.py:254-256,321-322); ``img``: ``(..., H, W)`` uint8 or float32, bit-exact for both.  OpenCV has two
+    code paths and so does this: k x k cell means when ``1/factor`` is an integer to within DBL_EPSILON
+    (``fb_resize_area``), per-axis coverage tables otherwise (``fb_resize_area_frac``)."""
+    if not factor > 0:
+        raise ValueError(f'resize factor {factor}')
+    scale = 1.0 / float(factor)
+    if scale < 1:
+        # enlarging: OpenCV switches INTER_AREA to a bilinear variant; no FEABAS configuration asks for it
+        raise NotImplementedError(f'INTER_AREA resize only shrinks (got factor {factor})')
+    k = int(np.rint(scale))
+    fast = abs(scale - k) < _DBL_EPSILON
     on_gpu = is_cuda_tensor(img)
     t = to_device(img, kwargs.get('device', None))
-    if k == 1:
+    if fast and k == 1:
         return t.clone() if on_gpu else np.array(img, copy=True)
     shape = t.shape
     h, w = shape[-2:]
     n = int(np.prod(shape[:-2])) if len(shape) > 2 else 1
     oh, ow = _round_half_even(h * factor), _round_half_even(w * factor)   # cv2: saturate_cast<int>(size * fx)
+    if oh < 1 or ow < 1:
+        raise ValueError(f'resize of {h}x{w} by {factor} leaves no pixel')      # (cv2 raises as well)
+    if (oh, ow) == (h, w):
+        return t.clone() if on_gpu else np.array(img, copy=True)               # cv2::resize: equal sizes are a plain copy
     out = torch.empty(tuple(shape[:-2]) + (oh, ow), dtype=t.dtype, device=t.device)
-    _lib.check(_lib.lib().fb_resize_area(t.data_ptr(), n, h, w, _code(t), k, out.data_ptr(), oh, ow, t.device.index, _stream(t)))
+    if fast:
+        _lib.check(_lib.lib().fb_resize_area(t.data_ptr(), n, h, w, _code(t), k, out.data_ptr(), oh, ow, t.device.index, _stream(t)))
+    else:
+        _lib.check(_lib.lib().fb_resize_area_frac(t.data_ptr(), n, h, w, _code(t), scale, scale, out.data_ptr(), oh, ow,
+                                                  t.device.index, _stream(t)))
     return out if on_gpu else out.cpu().numpy()
 
 

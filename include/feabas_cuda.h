@@ -132,6 +132,14 @@ int fb_masked_dog_sparse(const void* img, const unsigned char* mask, const int* 
                          int mask_n, double sigma, double ptp, int flags, float* out, void* work, long long work_bytes,
                          int device, void* stream);
 
+/* The same for float64 images (feabas/common.py:363 converts only non-floating dtypes, a float64 stack stays
+ * float64 through scipy.ndimage and comes out float64): every operation in double in scipy's order, out:
+ * n x h x w doubles.  mask: NULL or mask_n (1 or n) images.  work: fb_masked_dog_f64_workspace(n, h, w) bytes. */
+long long fb_masked_dog_f64_workspace(int n, int h, int w);
+int fb_masked_dog_f64(const double* img, const unsigned char* mask, int n, int h, int w, int mask_n,
+                      double sigma, double ptp, int flags, double* out, void* work, long long work_bytes,
+                      int device, void* stream);
+
 /* {min, max} (float32) of each of n images of `elems` elements: np.ptp of blocks
  * (feabas/matcher.py:196,205) and of stacks (feabas/common.py:369).  minmax: n x 2 floats.      */
 int fb_stack_minmax(const void* stack, int n, long long elems, int in_dtype, float* minmax, int device, void* stream);
@@ -141,6 +149,14 @@ int fb_stack_minmax(const void* stack, int n, long long elems, int in_dtype, flo
  * oh, ow: the output size OpenCV picks, round-half-even(h / k), round-half-even(w / k).           */
 int fb_resize_area(const void* src, int n, int h, int w, int in_dtype, int k, void* dst, int oh, int ow,
                    int device, void* stream);
+
+/* The same call for ANY shrinking factor (coarse_downsample / fine_downsample are free parameters of
+ * stitching_matcher, feabas/matcher.py:233-234): OpenCV's general INTER_AREA path -- per-axis tables of source
+ * pixels and float32 coverage weights, float32 accumulation along x then y, round half to even for uint8
+ * (bit-exact for uint8 and float32).  inv_fx, inv_fy = 1 / fx, 1 / fy as doubles (>= 1); oh, ow as above.
+ * OpenCV takes the k x k path above only when |1/f - round(1/f)| < DBL_EPSILON on both axes.           */
+int fb_resize_area_frac(const void* src, int n, int h, int w, int in_dtype, double inv_fx, double inv_fy,
+                        void* dst, int oh, int ow, int device, void* stream);
 
 /* cv2.resize(..., interpolation=cv2.INTER_NEAREST) of uint8 masks (feabas/matcher.py:257-264):
  * dst(y, x) = src(min(floor(y * inv_fy), h - 1), min(floor(x * inv_fx), w - 1)).                */

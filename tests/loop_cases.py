@@ -94,6 +94,11 @@ def stitch_cases():
                                              kwargs=dict(sigma=2.5, coarse_downsample=0.5, fine_downsample=1, spacings=[0.1, 0.4], pad=True,
                                                          residue_mode='threshold', residue_len=1.5))
 
+    # factors that are not 1/k: OpenCV's general INTER_AREA path (coverage tables), odd output sizes, sigma * factor
+    cases['stitch_frac_downsample'] = dict(make=lambda: strips(29, (810, 275), jitter=7)[:2],
+                                           kwargs=dict(sigma=2.5, coarse_downsample=0.4, fine_downsample=0.8, pad=True, conf_thresh=0.33,
+                                                       residue_len=2))
+
     def masked():
         a, b, _ = strips(27)
         return a, b

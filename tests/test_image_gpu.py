@@ -67,7 +67,57 @@ def test_resize_area_vs_cv2(fc, k):
         m = rng.random(shape) > 0.5
         np.testing.assert_array_equal(fc.resize_mask(m, 1 / k), mo.resize_mask_oracle(m, 1 / k))
     with pytest.raises(NotImplementedError):
-        fc.resize_area(np.zeros((10, 10), np.uint8), 0.4)
+        fc.resize_area(np.zeros((10, 10), np.uint8), 1.5)      # enlarging: not INTER_AREA proper, no FEABAS caller
+
+
+@pytest.mark.parametrize('factor', [0.4, 0.3, 0.7, 0.9, 0.45, 0.15, 0.8, 1 / 2.5, 0.999])
+def test_resize_area_any_factor_vs_cv2(fc, factor):
+    """coarse_downsample / fine_downsample are free parameters (matcher.py:233-234): OpenCV's general INTER_AREA path,
+    bit-exact for uint8 AND float32 (same tables, same float32 operation order)."""
+    import torch
+    rng = np.random.default_rng(int(factor * 1000))
+    for shape in [(301, 517), (64, 64), (500, 333), (9, 7), (64, 700), (3, 200, 130)]:
+        u8 = rng.integers(0, 256, shape, dtype=np.uint8)
+        want = np.stack([mo.resize_area_oracle(x, factor) for x in u8.reshape((-1,) + shape[-2:])]).reshape(shape[:-2] + (-1,))
+        want = want.reshape(shape[:-2] + mo.resize_area_oracle(u8.reshape((-1,) + shape[-2:])[0], factor).shape)
+        got = fc.resize_area(u8, factor)
+        assert got.shape == want.shape and got.dtype == np.uint8
+        np.testing.assert_array_equal(got, want)
+        f32 = (rng.standard_normal(shape[-2:]) * 40 + 128).astype(np.float32)
+        np.testing.assert_array_equal(fc.resize_area(f32, factor), mo.resize_area_oracle(f32, factor))
+        m = rng.random(shape[-2:]) > 0.5
+        np.testing.assert_array_equal(fc.resize_mask(m, factor), mo.resize_mask_oracle(m, factor))
+    t = fc.resize_area(torch.from_numpy(u8[0]).cuda(), factor)
+    assert t.is_cuda and np.array_equal(t.cpu().numpy(), mo.resize_area_oracle(u8[0], factor))
+
+
+def test_dog_float64(fc):
+    """common.py:363 converts only non-floating dtypes: float64 images are filtered and returned in float64."""
+    import torch
+    rng = np.random.default_rng(5)
+    for shape, sigma in [((2, 90, 131), 2.5), ((70, 45), 6.0), ((1, 40, 300), 1.0), ((33, 29), 12.0)]:
+        img = rng.standard_normal(shape) * 30 + 120
+        mask = rng.random(shape) > 0.2
+        one = rng.random(shape[-2:]) > 0.3
+        for m in (None, mask, one):
+            for signed in (True, False):
+                want = mo.masked_dog_oracle(img, sigma, mask=m, signed=signed)
+                got = fc.masked_dog_filter(img, sigma, mask=m, signed=signed)
+                assert got.dtype == np.float64 and got.shape == want.shape
+                # every operation in double in scipy's order; exp() of the taps may differ in the last ulp
+                np.testing.assert_allclose(got, want, rtol=0, atol=1e-13 * np.ptp(img))
+        t = fc.masked_dog_filter(torch.from_numpy(img).cuda(), sigma, mask=torch.from_numpy(mask).cuda(), ptp=500.0)
+        assert t.is_cuda and t.dtype == torch.float64
+        np.testing.assert_allclose(t.cpu().numpy(), mo.masked_dog_oracle(img, sigma, mask=mask, ptp=500.0), rtol=0, atol=1e-13 * 500)
+    # float64 straight into xcorr_fft with sigma > 0 (matcher.py:54-58): complex128 pipeline
+    a = rng.standard_normal((2, 64, 64)) * 20 + 100
+    b = np.roll(a, (3, -2), axis=(1, 2))
+    from oracle import xcorr_oracle as xo
+    got = fc.xcorr_fft(a, b, sigma=2.0, subpixel=True)
+    want = xo.xcorr_oracle(mo.masked_dog_oracle(a, 2.0), mo.masked_dog_oracle(b, 2.0), subpixel=True)
+    np.testing.assert_allclose(got[0], want[0], atol=1e-6)
+    np.testing.assert_allclose(got[1], want[1], atol=1e-6)
+    np.testing.assert_allclose(got[2], want[2], rtol=1e-6)
 
 
 def _blocks(boxes, ainv, tinv):
