@@ -16,6 +16,10 @@
 namespace fb {
 
 constexpr int kNW1 = 8, kNW2 = 8;                    // warps per CTA of K1 / K2
+constexpr int kNW2S = 8;                            // warps per CTA of the solo column kernel (one CTA per SM)
+constexpr int kSoloRegs = 248;                       // registers per thread it may use: 65536 / (32 kNW2S), a multiple of 8
+// the solo column kernel exists for lines inside one warp with at most 32 points per lane
+template <int E, int T> constexpr __host__ __device__ bool kSoloOk() { return E <= 32 && T <= 32; }
 // rows per GT tile = lines per K3 CTA: 8 when 8 divides the line length (square grids: the row count), else 4;
 // 4 for the two-warp lines of 4096 (shared memory)
 template <int E, int T> constexpr int kR3() { return T > 32 || (E * T) % 8 ? 4 : 8; }
@@ -38,6 +42,7 @@ struct FastLaunch {
     bool pruned;           // K1 / K2
     bool mirror;           // K3
     int k3_variant;
+    bool k2_solo;          // K2: the one-line-per-column-pair kernel
     int grid, threads;
     size_t smem;
     cudaStream_t stream;

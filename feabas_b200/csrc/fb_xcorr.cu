@@ -439,6 +439,20 @@ static size_t fast_smem(int n, int nw)
 }
 
 static std::atomic<int> g_num_sms{0};
+static std::atomic<int> g_opt_k2_solo{0};      // option "k2_solo": column stage on the one-line-per-column-pair kernel
+
+// shared memory of the solo column kernel: two transpose regions per line + the stage-twiddle table
+static size_t fast_smem_solo(int n)
+{
+    int E, T; fast_et(n, E, T);
+    const int lines = fast_lines(T, kNW2S);
+    return ((size_t)lines * 2 * ((wfft_region(E, T) + 15) & ~15) + n) * sizeof(cx<float>);
+}
+static bool fast_k2_solo(const Problem& q)
+{
+    int E, T; fast_et(q.ny, E, T);
+    return g_opt_k2_solo && E && E <= 32 && T <= 32 && fast_smem_solo(q.ny) <= kMaxSmem;
+}
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -528,7 +542,7 @@ static int fast_stage(int stage, const Problem& q, StreamCtx& ctx, const FastPar
         const int grid = work < cap ? work : cap;
         const bool pruned = q.w0 <= q.nx / 2 && q.w1 <= q.nx / 2;
         ProfScope ps(ctx, st, SLOT_ROWS_FWD);
-        FastLaunch l{q.nx, in_dtype, pruned, false, 0, grid, 32 * kNW1, fast_smem(q.nx, kNW1), st};
+        FastLaunch l{q.nx, in_dtype, pruned, false, 0, false, grid, 32 * kNW1, fast_smem(q.nx, kNW1), st};
         if (!fast_dispatch(1, fp, l)) return fail(FB_ESIZE, "no fast-path row kernel for %d points", q.nx);
     } else if (stage == 2) {
         const int cpg = fast_lines(TY, kNW2) / 2;
@@ -537,7 +551,12 @@ static int fast_stage(int stage, const Problem& q, StreamCtx& ctx, const FastPar
         const int grid = work < cap ? work : cap;
         const bool pruned = q.h0 <= q.ny / 2 && q.h1 <= q.ny / 2;     // (rows >= h of the row spectra are zero)
         ProfScope ps(ctx, st, SLOT_COLUMNS);
-        FastLaunch l{q.ny, 0, pruned, false, 0, grid, 32 * kNW2, fast_smem(q.ny, kNW2), st};
+        FastLaunch l{q.ny, 0, pruned, false, 0, false, grid, 32 * kNW2, fast_smem(q.ny, kNW2), st};
+        if (fast_k2_solo(q)) {
+            const int cpg_s = fast_lines(TY, kNW2S);
+            const int work_s = cnt * ((g.kp + cpg_s - 1) / cpg_s);
+            l.k2_solo = true; l.grid = work_s < g_num_sms ? work_s : (int)g_num_sms; l.threads = 32 * kNW2S; l.smem = fast_smem_solo(q.ny);
+        }
         if (!fast_dispatch(2, fp, l)) return fail(FB_ESIZE, "no fast-path column kernel for %d points", q.ny);
     } else if (stage == 3) {
         // K3: TX * R threads own R lines (R <= rblk rows of a GT tile)
@@ -554,7 +573,7 @@ static int fast_stage(int stage, const Problem& q, StreamCtx& ctx, const FastPar
         const bool mir = q.conf_mode == CONF_MIRROR;
         const size_t sm3t = sm3 + 16;                                         // + mbarrier
         const int variant = (R == 4 && q.nx == 1024) ? (fp.rblk == 8 ? 3 : 2) : (tma3 ? 0 : 1);
-        FastLaunch l{q.nx, 0, false, mir, variant, grid, nt, variant == 0 ? sm3t : sm3, st};
+        FastLaunch l{q.nx, 0, false, mir, variant, false, grid, nt, variant == 0 ? sm3t : sm3, st};
         if (!fast_dispatch(3, fp, l)) return fail(FB_ESIZE, "no fast-path inverse row kernel for %d points", q.nx);
     } else {
         ProfScope ps(ctx, st, SLOT_FINALIZE);
@@ -574,9 +593,10 @@ static void fast_work(int stage, const Problem& q, int cnt, long long& work, int
         work = (long long)cnt * ((q.hp0 + TR - 1) / TR + (q.hp1 + TR - 1) / TR);
         cap = g_num_sms * (EX > 32 ? 1 : 16 / kNW1);
     } else if (stage == 2) {
-        const int cpg = fast_lines(TY, kNW2) / 2;
+        const bool solo = fast_k2_solo(q);
+        const int cpg = solo ? fast_lines(TY, kNW2S) : fast_lines(TY, kNW2) / 2;
         work = (long long)cnt * ((q.g.kp + cpg - 1) / cpg);
-        cap = g_num_sms * (EY > 32 ? 1 : 16 / kNW2);
+        cap = solo ? (int)g_num_sms : g_num_sms * (EY > 32 ? 1 : 16 / kNW2);
     } else {
         const int R = fast_rblk(q.nx, TX);
         work = (long long)cnt * (q.nrt / R);
@@ -978,6 +998,7 @@ extern "C" int fb_set_option(const char* name, long long value)
     if (!strcmp(name, "ws_bytes")) { if (value < (1 << 20)) return fail(FB_EINVAL, "ws_bytes too small"); g_opt_ws_bytes = value; return FB_OK; }
     if (!strcmp(name, "profile")) { g_opt_profile = value ? 1 : 0; return FB_OK; }
     if (!strcmp(name, "fast_flags")) { g_opt_fast_flags = value; return FB_OK; }
+    if (!strcmp(name, "k2_solo")) { g_opt_k2_solo = value ? 1 : 0; return FB_OK; }
     if (!strcmp(name, "warp_fused")) { g_opt_warp_fused = value ? 1 : 0; return FB_OK; }
     if (!strcmp(name, "copy_threads")) { if (value < 1 || value > 64) return fail(FB_EINVAL, "copy_threads out of range"); g_opt_copy_threads = value; return FB_OK; }
     if (!strcmp(name, "host_chunk_bytes")) { if (value < 4096) return fail(FB_EINVAL, "host_chunk_bytes too small"); g_opt_host_chunk = value; return FB_OK; }

@@ -55,13 +55,15 @@ template <int E> struct LaneTw {
 // The same twiddles read from a shared-memory copy of the table instead (paired rows, one LDS.128 per
 // two outputs, fetched a batch ahead of use).  Cheaper in FP32 work, dearer in LSU wavefronts; the
 // two variants measure within 1 % of each other on B200 (profiles/r1/sweeps.md), this one slightly ahead.
-template <int E, int T> struct SmemTw {
+// TBMAX: most table rows fetched per batch (two batches are in flight: 8 TBMAX registers)
+template <int E, int T, int TBMAX = 4> struct SmemTw {
     const float4* tw4;   // + t applied
     __device__ __forceinline__ void init(const cx<float>* smem_table, int t) { tw4 = reinterpret_cast<const float4*>(smem_table) + t; }
     // out(k1, value) stores the twiddled value of output k1
     template <typename F> __device__ __forceinline__ void apply_all(const cx<float>* v, F out) const
     {
-        constexpr int H = E / 2, TB = H % 4 == 0 ? 4 : (H % 3 == 0 ? 3 : (H % 5 == 0 ? 5 : 1)), NB = H / TB;
+        constexpr int H = E / 2, TB0 = H % 4 == 0 ? 4 : (H % 3 == 0 ? 3 : (H % 5 == 0 ? 5 : 1));
+        constexpr int TB = TB0 <= TBMAX ? TB0 : (H % 2 == 0 && TBMAX >= 2 ? 2 : 1), NB = H / TB;
         float4 wq[2][TB];
 #pragma unroll
         for (int i = 0; i < TB; ++i) wq[0][i] = tw4[i * T];
@@ -90,9 +92,9 @@ constexpr bool kLaneTwiddles = false;     // true: LaneTw (registers), false: Sm
 #define FB_LANE_TW_K2 0
 #endif
 // LANE: this kernel keeps the stage twiddles of a lane in registers (needs E % 8 == 0)
-template <int E, int T, bool LANE = kLaneTwiddles> struct StageTw {
+template <int E, int T, bool LANE = kLaneTwiddles, int TBMAX = 4> struct StageTw {
     LaneTw<E> lane;
-    SmemTw<E, T> sm;
+    SmemTw<E, T, TBMAX> sm;
     // table: global [E/2][T][2]; smem_table: room for E * T entries (unused with lane twiddles)
     __device__ __forceinline__ void init(const cx<float>* table, cx<float>* smem_table, int t, int tid, int nthr)
     {
@@ -550,6 +552,149 @@ __device__ void kfast_columns(const FastParams& fp, unsigned char* smem)
         if (leader) tma_store_wait_read();
         W::line_sync(lbar);
     }
+}
+
+// all but the `pending` most recent bulk stores of this thread have finished READING shared memory
+template <int PENDING> __device__ __forceinline__ void tma_store_wait_read_but()
+{
+    asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(PENDING) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2, one line per column PAIR ("solo"): the lanes of a line transform the F0 column, keep its spectrum in
+// registers, transform the F1 column, form conj(P) and conj(Q) in registers and transform both -- no spectrum
+// exchange through shared memory (a fifth of the column kernel's shared-memory wavefronts) and no barrier
+// between warps at all: every warp drifts through its load / butterfly / transpose phases on its own.  Costs
+// registers (two 2E-register images per lane: one CTA of NW warps per SM) and two transpose regions per line (the
+// TMA store of P drains from one while Q is transformed in the other).  The four transforms of a work item run
+// through ONE copy of the butterfly code (rolled loop); global loads are issued a whole transform ahead of use
+// into the register image that is idle at that point.  E <= 32, lines inside one warp.
+// ---------------------------------------------------------------------------------------------
+// the permutation j -> out_reg(j) as a list of cycles: order[i] = i-th element visited, start / last = first / last of its cycle
+template <int E, int T> struct PermCycles {
+    int order[E];
+    bool start[E], last[E];
+    constexpr __host__ __device__ PermCycles() : order{}, start{}, last{}
+    {
+        bool seen[E] = {};
+        int n = 0;
+        for (int j0 = 0; j0 < E; ++j0) {
+            if (seen[j0]) continue;
+            int j = j0;
+            bool first = true;
+            while (!seen[j]) {
+                seen[j] = true; order[n] = j; start[n] = first; last[n] = false; first = false; ++n;
+                j = WarpFFT<E, T>::out_reg(j);
+            }
+            last[n - 1] = true;
+        }
+    }
+};
+// v[j] <- conj(P)_j = F0 conj(F1), park[j] <- conj(Q)_j = conj(F0 F1) with F0 = park[out_reg(j)], F1 = v[out_reg(j)] (old values)
+template <int E, int T, int I = 0> struct SoloProducts {
+    static __device__ __forceinline__ void run(cx<float>* v, cx<float>* park, cx<float>& a0, cx<float>& b0)
+    {
+        constexpr PermCycles<E, T> pc{};
+        constexpr int j = pc.order[I], src = WarpFFT<E, T>::out_reg(j);
+        constexpr bool st = pc.start[I], la = pc.last[I];
+        if constexpr (st) { a0 = park[j]; b0 = v[j]; }                 // the cycle's first element is overwritten first: keep it
+        const cx<float> a = la ? a0 : park[src], b = la ? b0 : v[src];
+        v[j] = cmulc(a, b);
+        park[j] = mk<float>(a.x * b.x - a.y * b.y, -(a.x * b.y) - a.y * b.x);
+        if constexpr (I + 1 < E) SoloProducts<E, T, I + 1>::run(v, park, a0, b0);
+    }
+};
+
+template <int E, int T, int NW, bool PRUNED0>
+__device__ void kfast_columns_solo(const FastParams& fp, unsigned char* smem)
+{
+    using W = WarpFFT<E, T>;
+    static_assert(W::WPL == 1 && E <= 32, "solo column kernel: a line inside one warp, 2 x 2E registers per lane");
+    constexpr int N = W::N, LPW = W::LPW, RS = (W::RS + 15) & ~15, NT = 32 * NW;
+    constexpr int CPG = NW * LPW;                           // columns per CTA and work item
+    const XcParams& p = fp.x;
+    cx<float>* regions = reinterpret_cast<cx<float>*>(smem);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int t = W::lane_in_line(warp, lane), lw = W::line_in_warp(lane);
+    const bool leader = t == 0 && !W::is_shadow(lane);     // one thread per line
+    StageTw<E, T, false, 2> tw;                             // (short twiddle batches: registers are what this kernel is short of)
+    tw.init(fp.twy, regions + NW * LPW * 2 * RS, t, tid, NT);
+    const bool mirror = p.conf_mode == CONF_MIRROR;
+    const int kp = p.kp, groups = (kp + CPG - 1) / CPG, total = p.n * groups;
+    cx<float>* regA = regions + ((warp * LPW + lw) * 2) * RS;
+    cx<float>* regB = regA + RS;
+    const int hp0 = fp.hp0, hp1 = fp.hp1;
+    cx<float> v[E], park[E];
+    // column `col` of pair `pair` of F0 / F1 -> dst (zero rows pruned)
+    auto load_col = [&](cx<float>* dst, const cx<float>* FT, int hp, int pair, int col) {
+        const cx<float>* src = FT + ((size_t)pair * kp + (col < kp ? col : 0)) * hp;
+#pragma unroll
+        for (int n1 = 0; n1 < E; ++n1) {
+            const int y = n1 * T + t;
+            cx<float> a = mk<float>(0.f, 0.f);
+            if ((!PRUNED0 || n1 < E / 2) && y < hp) a = ldg(src + y);
+            dst[n1] = a;
+        }
+    };
+    if ((int)blockIdx.x < total) {
+        const int pair = blockIdx.x / groups, grp = blockIdx.x - pair * groups;
+        load_col(park, fp.FT0, hp0, pair, grp * CPG + warp * LPW + lw);
+    }
+    for (int work = blockIdx.x; work < total; work += gridDim.x) {
+        const int pair = work / groups, grp = work - pair * groups;
+        const int col = grp * CPG + warp * LPW + lw;
+        const bool live = col < kp;
+        const int nw_ = work + gridDim.x;
+        if (lane == 0 && warp == 0 && !(fp.flags & 2) && nw_ + (int)gridDim.x < total) {      // the work item after the next -> L2
+            const int w2 = nw_ + gridDim.x;
+            const int np = w2 / groups, ng = w2 - np * groups;
+            int nc = kp - ng * CPG; nc = nc > CPG ? CPG : nc;
+            prefetch_l2_bulk(fp.FT0 + ((size_t)np * kp + (size_t)ng * CPG) * hp0, (unsigned)(nc * hp0 * 8));
+            prefetch_l2_bulk(fp.FT1 + ((size_t)np * kp + (size_t)ng * CPG) * hp1, (unsigned)(nc * hp1 * 8));
+        }
+#pragma unroll
+        for (int j = 0; j < E; ++j) v[j] = park[j];        // the F0 column (loaded during the previous item's last transform)
+        load_col(park, fp.FT1, hp1, pair, col);             // the F1 column arrives under the first transform
+#pragma unroll 1
+        for (int pass = 0; pass < 4; ++pass) {
+            cx<float>* reg = pass == 3 ? regB : regA;
+            if (pass == 0 || pass == 3) {                   // the store that last drained from this region has read it
+                if (leader) tma_store_wait_read_but<1>();
+                __syncwarp();
+            }
+            W::template run<PRUNED0, decltype(tw), true>(v, reg, tw, t, pass < 2, 1, lw);
+            if (pass == 0) {
+#pragma unroll
+                for (int j = 0; j < E; ++j) { const cx<float> x = v[j]; v[j] = park[j]; park[j] = x; }
+            } else if (pass == 1) {
+                // output k = t + T j of lane t is input element n1 = j of the next transform: a register permutation.
+                // unscaled: 1 / (ny nx) is applied once per pair by the finalize kernel (XcParams::out_scale)
+                // (in place, cycle by cycle of the permutation: the register images sit in fixed registers across the rolled loop)
+                cx<float> a0, b0;
+                SoloProducts<E, T>::run(v, park, a0, b0);
+            } else {
+                // natural y order into the region, one bulk tensor store scatters the column into its ny / rblk tiles
+#pragma unroll
+                for (int j = 0; j < E; ++j) reg[W::out_k(t, j)] = v[W::out_reg(j)];
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (leader && live) tma_store_4d(&fp.gt_map, reg, 0, col, pass - 2, pair * fp.gt_tiles);
+                if (pass == 2) {
+                    if (!mirror) { pass = 3; }              // one surface only: skip the Q transform (park is dead)
+                    else {
+#pragma unroll
+                        for (int j = 0; j < E; ++j) v[j] = park[j];
+                    }
+                    if (nw_ < total) {                      // next item's F0 column arrives under the last transform
+                        const int np = nw_ / groups, ng = nw_ - np * groups;
+                        load_col(park, fp.FT0, hp0, np, ng * CPG + warp * LPW + lw);
+                    }
+                }
+            }
+        }
+    }
+    if (leader) tma_store_wait_read();                      // shared memory must outlive the last store's read
+    __syncwarp();
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -81,6 +81,12 @@ def lib():
             fn.restype = res
             fn.argtypes = args
         _lib = handle
+        # FEABAS_CUDA_OPTIONS="name=value,...": fb_set_option switches for a whole run (experiments, comparison runs)
+        for item in filter(None, os.environ.get('FEABAS_CUDA_OPTIONS', '').split(',')):
+            name, _, value = item.partition('=')
+            rc = handle.fb_set_option(name.strip().encode(), int(value))
+            if rc != 0:
+                raise FeabasCudaError(f'FEABAS_CUDA_OPTIONS: {item!r}: {handle.fb_last_error().decode()}')
     return _lib
 
 
