@@ -341,10 +341,10 @@ def bench_blocks(args, wl, rank, world, local, warmup):
     batch_rank = batch * len(secs_dev)
 
     def step():
-        out = None
-        for l0, l1 in loaders:
-            out = fc.bboxes_mesh_renderer_matcher(m0, m1, l0, l1, boxes, boxes, **kw)
-        return out
+        if strong:       # the job list of this rank through the pipelined entry point (next pair enqueued before this one is read back)
+            return fc.bboxes_mesh_renderer_matcher_many(((m0, m1, l0, l1, boxes, boxes) for l0, l1 in loaders), **kw)[-1]
+        l0, l1 = loaders[0]
+        return fc.bboxes_mesh_renderer_matcher(m0, m1, l0, l1, boxes, boxes, **kw)
 
     def barrier():
         torch.cuda.synchronize()
@@ -396,8 +396,12 @@ def bench_blocks(args, wl, rank, world, local, warmup):
         def e_step():
             # the call a user makes: host images in, matches out (upload of both sections inside); with a list of pairs the
             # match lists of all ranks are gathered on the host (shard.gather_concat)
-            outs = [fc.bboxes_mesh_renderer_matcher(m0, m1, fc.ArrayLoader(ah, device=local), fc.ArrayLoader(bh, device=local), boxes, boxes, **kw)
-                    for ah, bh in host]
+            if strong:
+                outs = fc.bboxes_mesh_renderer_matcher_many(((m0, m1, fc.ArrayLoader(ah, device=local), fc.ArrayLoader(bh, device=local), boxes, boxes)
+                                                             for ah, bh in host), **kw)
+            else:
+                outs = [fc.bboxes_mesh_renderer_matcher(m0, m1, fc.ArrayLoader(ah, device=local), fc.ArrayLoader(bh, device=local), boxes, boxes, **kw)
+                        for ah, bh in host]
             if strong:
                 cat = [np.concatenate([o[i] for o in outs], axis=0) if outs else None for i in range(3)]
                 return shard.gather_concat(tuple(cat))
@@ -422,8 +426,10 @@ def bench_blocks(args, wl, rank, world, local, warmup):
             dt = float(t.item())
         e2e = {'value': units * e_steps / dt, 'unit': 'matches/s',
                'h2d_bytes_per_step': int(allsum(float(sum(x.numel() + y.numel() for x, y in host)))), 'd2h_bytes_per_step': int(5 * 8 * units), 'steps': e_steps,
-               'api': 'feabas_b200.cuda.bboxes_mesh_renderer_matcher(ArrayLoader(pinned uint8 host sections)) -> fb_crop_blocks + fb_masked_dog + fb_xcorr_batch_device'
-                      + (' per section pair of this rank, + shard.gather_concat of the match lists' if strong else '')}
+               'api': ('feabas_b200.cuda.bboxes_mesh_renderer_matcher_many(jobs of ArrayLoader(pinned uint8 host sections))' if strong else
+                       'feabas_b200.cuda.bboxes_mesh_renderer_matcher(ArrayLoader(pinned uint8 host sections))')
+                      + ' -> fb_crop_blocks + fb_masked_dog + fb_xcorr_batch_device'
+                      + (' per section pair of this rank (two pairs in flight), + shard.gather_concat of the match lists' if strong else '')}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

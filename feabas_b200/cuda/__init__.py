@@ -5,14 +5,14 @@ from .xcorr import fft_shape, next_fast_len, xcorr_fft, xcorr_fft_device
 from .blocks import (bbox_centers, bbox_sizes, distributor_cartesian_bbox, divide_bbox, intersect_bbox, z_order)
 from .image import masked_dog_filter, resize_area, resize_mask, crop_blocks
 from .surrogate import AffineMesh, AffineSLM, ArrayLoader
-from .matcher import (bboxes_mesh_renderer_matcher, global_translation_matcher, iterative_xcorr_matcher_w_mesh,
+from .matcher import (bboxes_mesh_renderer_matcher, bboxes_mesh_renderer_matcher_many, global_translation_matcher, iterative_xcorr_matcher_w_mesh,
                       section_matcher, section_matcher_many, set_mesh_factory, stitching_matcher, stitching_matcher_many)
 from . import _lib, matchio
 
 __all__ = ['xcorr_fft', 'xcorr_fft_device', 'fft_shape', 'next_fast_len',
            'global_translation_matcher', 'stitching_matcher', 'stitching_matcher_many', 'section_matcher', 'section_matcher_many',
            'iterative_xcorr_matcher_w_mesh',
-           'bboxes_mesh_renderer_matcher', 'distributor_cartesian_bbox', 'divide_bbox', 'intersect_bbox', 'z_order',
+           'bboxes_mesh_renderer_matcher', 'bboxes_mesh_renderer_matcher_many', 'distributor_cartesian_bbox', 'divide_bbox', 'intersect_bbox', 'z_order',
            'bbox_centers', 'bbox_sizes', 'masked_dog_filter', 'resize_area', 'resize_mask', 'crop_blocks',
            'AffineMesh', 'AffineSLM', 'ArrayLoader', 'set_mesh_factory', 'install', 'Match',
            'FFT_CONF_NONE', 'FFT_CONF_STD', 'FFT_CONF_MIRROR']

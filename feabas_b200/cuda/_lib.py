@@ -9,7 +9,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), 'csrc', 'libfeabas_cuda.so')
+# FEABAS_CUDA_LIB: another build of the same library (kernel-variant comparison runs)
+LIB_PATH = os.environ.get('FEABAS_CUDA_LIB') or os.path.join(os.path.dirname(_HERE), 'csrc', 'libfeabas_cuda.so')
 
 FB_F32, FB_U8, FB_F64 = 0, 1, 2
 FB_FLAG_PAD = 0x1

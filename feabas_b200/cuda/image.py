@@ -48,6 +48,14 @@ def to_device(x, device=None, dtype=None):
     return t.contiguous()
 
 
+def upload_small(arr, device):
+    """Small host array (block rows, index lists; a few KB) -> CUDA tensor on the current stream, straight from pageable
+    memory: the driver embeds such copies in the command stream, so they do not queue up on the copy engine behind
+    the whole-section uploads of ``ArrayLoader`` (staging them through page-locked memory was measured: the same GPU
+    idle gaps, and 18 % less end-to-end throughput on the config-4 block pass, because a pinned copy is a DMA)."""
+    return torch.from_numpy(np.ascontiguousarray(arr)).to(device, non_blocking=True)
+
+
 _UPLOAD_STREAMS = {}
 
 
@@ -246,7 +254,7 @@ def crop_blocks_masked(img, blocks, block_shape, origin=None, fillval=0, cover=N
     blk_host = None
     if not is_cuda_tensor(blocks):
         blk_host = np.ascontiguousarray(blocks, dtype=np.float64).reshape(-1, 10)
-        blocks = torch.from_numpy(blk_host).to(img.device, non_blocking=True)
+        blocks = upload_small(blk_host, img.device)
     n = blocks.shape[0]
     if out is None:
         out = torch.empty((n, bh, bw), dtype=img.dtype, device=img.device)
@@ -275,14 +283,14 @@ def crop_blocks_masked(img, blocks, block_shape, origin=None, fillval=0, cover=N
             part = np.nonzero(~whole)[0].astype(np.int32)
             slot = np.full(n, -1, dtype=np.int32)
             slot[part] = np.arange(part.size, dtype=np.int32)
-            both = torch.from_numpy(np.concatenate((slot, part))).to(img.device, non_blocking=True)
+            both = upload_small(np.concatenate((slot, part)), img.device)
             slots, mask_images = both[:n], both[n:]
             mask = torch.empty((part.size, bh, bw), dtype=torch.uint8, device=img.device)
             fptr = slots.data_ptr()
         else:
             mask = torch.empty((n, bh, bw), dtype=torch.uint8, device=img.device)
             if n and whole.any():
-                slots = torch.from_numpy(np.where(whole, -1, np.arange(n)).astype(np.int32)).to(img.device, non_blocking=True)
+                slots = upload_small(np.where(whole, -1, np.arange(n)).astype(np.int32), img.device)
                 fptr = slots.data_ptr()
         mptr = mask.data_ptr()
     if n:
@@ -291,7 +299,7 @@ def crop_blocks_masked(img, blocks, block_shape, origin=None, fillval=0, cover=N
                                              float(origin[0]), float(origin[1]), float(fillval), out.data_ptr(),
                                              cptr, fptr, mptr, img.device.index, _stream(img)))
     if not compact and mask is not None and whole is not None and whole.any():
-        mask[torch.from_numpy(np.nonzero(whole)[0]).to(img.device)] = 1          # (whole blocks: the kernel wrote no mask)
+        mask[upload_small(np.nonzero(whole)[0], img.device)] = 1          # (whole blocks: the kernel wrote no mask)
     if compact:
         return out, mask, mask_images, any_covered
     return out, mask
@@ -387,7 +395,7 @@ def crop_blocks_multi(parts, block_shape, fillval=0):
     out = torch.empty((n, bh, bw), dtype=img0.dtype, device=img0.device)
     if n:
         packed = np.concatenate((rows.view(np.uint8).reshape(-1), src.view(np.uint8).reshape(-1)))    # one upload
-        dev_buf = torch.from_numpy(packed).to(img0.device, non_blocking=True)
+        dev_buf = upload_small(packed, img0.device)
         rows_ptr = dev_buf.data_ptr()
         _lib.check(_lib.lib().fb_crop_blocks_multi(rows_ptr + rows.nbytes, _code(img0), rows_ptr, n, bh, bw, float(fillval),
                                                   out.data_ptr(), img0.device.index, _stream(img0)))

@@ -118,7 +118,7 @@ def _translation_retry(a, b, tx, ty, conf, conf_mode, divide_factor):
     if keep.size == 0:
         return tx, ty, conf
     if keep.size < flat.size:
-        sel = torch.from_numpy(keep).to(s0.device)
+        sel = _img.upload_small(keep, s0.device)
         s0, s1 = s0.index_select(0, sel).contiguous(), s1.index_select(0, sel).contiguous()
     res = xcorr_fft_device(s0, s1, conf_mode=conf_mode, pad=True).cpu().numpy()
     off_x = ((win1[:, 1] - win1[:, 0]) - (win0[:, 1] - win0[:, 0])) / 2 + win1[:, 0] - win0[:, 0]
@@ -228,22 +228,27 @@ def bboxes_mesh_renderer_matcher(mesh0, mesh1, image_loader0, image_loader1, bbo
     ``pad`` (True), ``subpixel`` (False), ``mask_range`` (None); ``render_mode`` / ``geodesic_mask`` /
     ``affine_approx_tol`` / ``render_weight_threshold`` are accepted and only meaningful for reference meshes.
     """
+    if not (hasattr(mesh0, 'render_map') and hasattr(mesh1, 'render_map')):
+        return _reference_block_pass(mesh0, mesh1, image_loader0, image_loader1, bboxes0, bboxes1, **kwargs)
+    return _bboxes_collect(_bboxes_enqueue(mesh0, mesh1, image_loader0, image_loader1, bboxes0, bboxes1, **kwargs))
+
+
+def _bboxes_enqueue(mesh0, mesh1, image_loader0, image_loader1, bboxes0, bboxes1, **kwargs):
+    """Device half of ``bboxes_mesh_renderer_matcher``: every batch rendered and cross-correlated, nothing read back.
+    Returns what ``_bboxes_collect`` needs."""
     batch_size = kwargs.get('batch_size', None)
     sigma = kwargs.get('sigma', 0.0)
     conf_mode = kwargs.get('conf_mode', FFT_CONF_MIRROR)
     pad = kwargs.get('pad', True)
     subpixel = kwargs.get('subpixel', False)
     mask_range = kwargs.get('mask_range', None)
-    empty = (np.empty((0, 2)), np.empty((0, 2)), np.empty(0))
-    if not (hasattr(mesh0, 'render_map') and hasattr(mesh1, 'render_map')):
-        return _reference_block_pass(mesh0, mesh1, image_loader0, image_loader1, bboxes0, bboxes1, **kwargs)
+    pending = []
     if bboxes0 is None or len(bboxes0) == 0:
-        return empty
+        return pending, None, None, conf_mode
     loader0 = _as_loader(image_loader0, kwargs.get('device', None))
     loader1 = _as_loader(image_loader1, loader0.tensor.device.index)
     bboxes0, bboxes1 = np.asarray(bboxes0), np.asarray(bboxes1)
     edges = _blk.split_batches(bboxes0, bboxes1, batch_size)
-    pending = []
     for lo, hi in zip(edges[:-1], edges[1:]):
         if hi <= lo:
             continue
@@ -253,17 +258,55 @@ def bboxes_mesh_renderer_matcher(mesh0, mesh1, image_loader0, image_loader1, bbo
         stack1 = _render_stack(mesh1, loader1, bboxes1[lo:hi], sigma, mask_range=mask_range)
         if stack1 is None:
             continue
-        pending.append((lo, hi, xcorr_fft_device(stack0, stack1, conf_mode=conf_mode, pad=pad, subpixel=subpixel)))
+        res = xcorr_fft_device(stack0, stack1, conf_mode=conf_mode, pad=pad, subpixel=subpixel)
+        # the read-back is enqueued NOW, right behind this batch (page-locked landing buffer + event): a copy issued at
+        # collection time would queue up behind whatever was enqueued in between (the next jobs of the _many entry point)
+        landed = torch.empty(res.shape, dtype=res.dtype, pin_memory=True)
+        landed.copy_(res, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(torch.cuda.current_stream(res.device))
+        pending.append((lo, hi, landed, done))
+    return pending, bboxes0, bboxes1, conf_mode
+
+
+def _bboxes_collect(enqueued):
+    """Host half: wait for each batch's read-back, block displacements -> matched points (matcher.py:840-849)."""
+    pending, bboxes0, bboxes1, conf_mode = enqueued
     if not pending:
-        return empty
+        return np.empty((0, 2)), np.empty((0, 2)), np.empty(0)
     xy0, xy1, conf = [], [], []
-    for lo, hi, res in pending:                           # one synchronising read per batch, after all were enqueued
-        res = res.cpu().numpy()
+    for lo, hi, landed, done in pending:
+        done.synchronize()
+        res = landed.numpy()
         p0, p1 = _blk.block_points(bboxes0[lo:hi], bboxes1[lo:hi], res[0], res[1])
         xy0.append(p0)
         xy1.append(p1)
         conf.append(res[2].astype(np.float64 if conf_mode == 1 else np.float32))
     return np.concatenate(xy0, axis=0), np.concatenate(xy1, axis=0), np.concatenate(conf, axis=0)
+
+
+def bboxes_mesh_renderer_matcher_many(jobs, depth=2, **kwargs):
+    """``bboxes_mesh_renderer_matcher`` over MANY independent section pairs (the aligner's job list, feabas/aligner.py:
+    one pair per job; ``align_main.py`` fans them out to worker processes) with the device kept busy: the block passes
+    of up to ``depth`` jobs are enqueued before the results of the oldest one are read back, so uploads, renders and
+    correlations of the next pair run under the host's share of the previous one.  ``jobs``: iterable of
+    ``(mesh0, mesh1, image_loader0, image_loader1, bboxes0, bboxes1)`` -- consumed lazily, a generator may build the
+    loaders (and start their uploads) on demand.  Returns the list of ``(xy0, xy1, conf)``, identical to one call per job."""
+    from collections import deque
+    queue, results = deque(), []
+    for job in jobs:
+        mesh0, mesh1 = job[0], job[1]
+        if not (hasattr(mesh0, 'render_map') and hasattr(mesh1, 'render_map')):
+            while queue:
+                results.append(_bboxes_collect(queue.popleft()))
+            results.append(_reference_block_pass(*job, **kwargs))
+            continue
+        queue.append(_bboxes_enqueue(*job, **kwargs))
+        while len(queue) > max(int(depth), 0):
+            results.append(_bboxes_collect(queue.popleft()))
+    while queue:
+        results.append(_bboxes_collect(queue.popleft()))
+    return results
 
 
 _MERGE_BYTES = 1 << 30          # blocks of one merged launch: at most this many bytes per stack

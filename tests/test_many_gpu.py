@@ -104,6 +104,31 @@ def test_section_matcher_many_equals_one_call_per_pair(fc):
     assert many[0][0].shape[0] > 100
 
 
+def test_bboxes_matcher_many_equals_one_call_per_pair(fc):
+    """The pipelined job-list entry point (two pairs in flight) returns what one call per pair returns, bit for bit,
+    from device tensors and from pinned host images (lazy job generator: uploads start while the previous pair runs)."""
+    import torch
+    pairs = [lc.section_pair(seed, size=size, shift=shift) for seed, size, shift in ((61, 520, (6.0, -4.0)), (62, 520, (-3.0, 8.0)), (63, 390, (2.0, 2.0)))]
+    kw = dict(sigma=3.5, batch_size=9, pad=True, subpixel=True)
+
+    def job(k, pinned):
+        a, b = pairs[k]
+        h, w = a.shape
+        if pinned:
+            a, b = torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory()
+        boxes = np.array([(x, y, x + 130, y + 130) for y in range(0, h - 129, 130) for x in range(0, w - 129, 130)], dtype=np.float64)
+        return (fc.AffineMesh.from_bbox((0, 0, w, h), cartesian=True, uid=0.0), fc.AffineMesh.from_bbox((0, 0, w, h), cartesian=True, uid=1.0),
+                fc.ArrayLoader(a), fc.ArrayLoader(b), boxes, boxes)
+    want = [fc.bboxes_mesh_renderer_matcher(*job(k, False), **kw) for k in range(3)]
+    for pinned in (False, True):
+        for depth in (0, 1, 2, 5):
+            many = fc.bboxes_mesh_renderer_matcher_many((job(k, pinned) for k in range(3)), depth=depth, **kw)
+            assert len(many) == 3
+            for got, ref in zip(many, want):
+                _same(got, ref)
+    assert want[0][0].shape[0] == 16 and fc.bboxes_mesh_renderer_matcher_many([], **kw) == []
+
+
 def test_host_threads_on_two_gpus_overlap(fc):
     """fb_xcorr_batch_host holds only its own (device, stream) context: two host threads feeding two GPUs run
     concurrently (round 1 serialised them on a global mutex)."""
