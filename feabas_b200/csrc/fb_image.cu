@@ -318,6 +318,7 @@ __global__ void __launch_bounds__(kNT) fbk_gauss2d_reg(const __grid_constant__ G
     // entirely beyond one end of it, where mode='nearest' repeats the end pixel): a quarter of the load instructions and of
     // the exposed latency of the scalar loop below (ncu, round 2: long_scoreboard was half of all stall samples).
     const bool vec = (p.w & 3) == 0 && (reinterpret_cast<size_t>(base) & 15) == 0 && (p.src_stride & 3) == 0;
+    bool masked_any = false;                               // MODE_MASK: this thread loaded a masked (zero) mask pixel
     if (vec) {
         typedef typename Vec4<TS>::type V4;
         constexpr int GW = IN / 4, TOT = IN * GW, UN = 3;
@@ -344,7 +345,10 @@ __global__ void __launch_bounds__(kNT) fbk_gauss2d_reg(const __grid_constant__ G
                 const int yy = i / GW, g = i - yy * GW;
                 if (i < TOT) {
                     float4 f;
-                    if (MODE == MODE_MASK) { f.x = v[u].x ? 0.f : span; f.y = v[u].y ? 0.f : span; f.z = v[u].z ? 0.f : span; f.w = v[u].w ? 0.f : span; }
+                    if (MODE == MODE_MASK) {
+                        f.x = v[u].x ? 0.f : span; f.y = v[u].y ? 0.f : span; f.z = v[u].z ? 0.f : span; f.w = v[u].w ? 0.f : span;
+                        masked_any = masked_any || !(v[u].x && v[u].y && v[u].z && v[u].w);
+                    }
                     else { f.x = (float)v[u].x; f.y = (float)v[u].y; f.z = (float)v[u].z; f.w = (float)v[u].w; }
                     *reinterpret_cast<float4*>(s_in + yy * PITCH + 4 * g) = f;
                 }
@@ -366,11 +370,20 @@ __global__ void __launch_bounds__(kNT) fbk_gauss2d_reg(const __grid_constant__ G
             for (int u = 0; u < UN; ++u) {
                 const int i = i0 + u * kNT;
                 const int yy = i / IN, xx = i - yy * IN;
-                if (i < TOT) s_in[yy * PITCH + xx] = MODE == MODE_MASK ? (v[u] ? 0.f : span) : (float)v[u];
+                if (i < TOT) {
+                    s_in[yy * PITCH + xx] = MODE == MODE_MASK ? (v[u] ? 0.f : span) : (float)v[u];
+                    if (MODE == MODE_MASK) masked_any = masked_any || !v[u];
+                }
             }
         }
     }
-    __syncthreads();
+    if (MODE == MODE_MASK) {
+        // a tile (with its halo) without a masked pixel contributes a zero term: |x| - 0 keeps x bit for bit.  Blocks that
+        // hang over the border of the mesh are masked along one edge only, most of their tiles stop here.
+        if (!__syncthreads_or(masked_any)) return;
+    } else {
+        __syncthreads();
+    }
     // row pass: item = (row yy, strip of 8 outputs); consecutive threads take consecutive rows (pitch = 4 mod 32: the
     // 128-bit loads of 8 consecutive rows fall into different banks)
     for (int i = tid; i < IN * (kFT / kFP); i += kNT) {

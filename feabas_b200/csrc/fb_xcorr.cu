@@ -153,7 +153,7 @@ static std::map<std::tuple<int, int, int>, DevTables> g_tables;      // (device,
 static std::map<std::pair<int, void*>, StreamCtx> g_ctx;              // (device, stream the work runs on)
 static std::map<int, bool> g_attr_done;
 static void* const kOwnStreamKey = reinterpret_cast<void*>(~(uintptr_t)0);   // context of the host path's private stream
-static std::atomic<long long> g_opt_ws_bytes{2LL << 30};
+static std::atomic<long long> g_opt_ws_bytes{8LL << 30};
 static std::atomic<long long> g_opt_host_chunk{64LL << 20};
 static std::atomic<long long> g_opt_profile{0};
 static std::atomic<long long> g_opt_fused_threads{0};      // experiment switch: threads per CTA of the fused kernel (0: 512 above 100 KB, else 256)
@@ -759,7 +759,15 @@ static int run_device(const Problem& q, StreamCtx& ctx, const void* img0, const 
         size_t need = (size_t)chunk * q.ws_per_pair;
         if (need > ctx.ws_bytes) {
             if (ctx.ws) { CU(cudaStreamSynchronize(st)); CU(cudaFree(ctx.ws)); ctx.ws = nullptr; ctx.ws_bytes = 0; ctx.gt_maps.clear(); }
-            if (cudaMalloc(&ctx.ws, need) != cudaSuccess) { cudaGetLastError(); return fail(FB_ENOMEM, "workspace of %zu bytes", need); }
+            // the budget is a ceiling, not a reservation: when the device cannot give that much (worker processes
+            // sharing one GPU), work in smaller chunks instead of failing
+            while (cudaMalloc(&ctx.ws, need) != cudaSuccess) {
+                cudaGetLastError();
+                ctx.ws = nullptr;
+                if (chunk == 1) return fail(FB_ENOMEM, "workspace of %zu bytes", need);
+                chunk = (chunk + 1) / 2;
+                need = (size_t)chunk * q.ws_per_pair;
+            }
             ctx.ws_bytes = need;
         }
     } else if (chunk > 65535 * 16) {

@@ -218,10 +218,11 @@ int fb_next_fast_len(int target);
 int fb_xcorr_plan_info(int h0, int w0, int h1, int w1, int in_dtype, int fft_h, int fft_w, int flags,
                        long long* info8);
 
-/* Tuning knobs: "ws_bytes" (HBM workspace budget per stream context, default
- * 2 GiB), "host_chunk_bytes" (input bytes per host-path chunk, default 64 MiB),
+/* Tuning knobs: "ws_bytes" (ceiling of the HBM workspace per stream context, default 8 GiB: 650 pairs of 512^2
+ * blocks at FFT 1024^2; allocated as needed, halved when the device cannot give it), "host_chunk_bytes" (input bytes per host-path chunk, default 64 MiB),
  * "copy_threads" (host threads that stage pageable input into the pinned slots, default 6),
  * "warp_fused" (0/1: small grids on the warp-per-line fused kernel, default 1),
+ * "k2_solo" (0/1: experiment, column stage with one warp per column pair -- measured slower, default 0),
  * "profile" (0/1: time every kernel with CUDA events, see fb_profile_read).      */
 int fb_set_option(const char* name, long long value);
 
