@@ -366,7 +366,7 @@ def bench_blocks(args, wl, rank, world, local, warmup):
     assert n_ok >= 0.99 * batch, f'only {n_ok}/{batch} blocks recovered the offset {shift}: {d[:4]}'
     run_info['ground_truth_recovered'] = n_ok / batch
     units = allsum(float(batch_rank))                           # block pairs per step, all ranks
-    L.profile_read(local, stream, reset=True) if L.launch_count() else None
+    L.profile_read(local, 'all', reset=True) if L.launch_count() else None
     L.set_option('profile', 1)
     mon, mon_path = clocks_monitor_start(local) if rank == 0 else (None, None)
     launches0 = L.launch_count()
@@ -381,7 +381,7 @@ def bench_blocks(args, wl, rank, world, local, warmup):
     launches = L.launch_count() - launches0
     clocks = clocks_monitor_stop(mon, mon_path) if rank == 0 else None
     L.set_option('profile', 0)
-    prof = L.profile_read(local, stream, reset=True)
+    prof = L.profile_read(local, 'all', reset=True)
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -1015,31 +1015,39 @@ extern "C" int fb_set_option(const char* name, long long value)
 
 extern "C" int fb_profile_read(int device, void* stream, double* ms5, long long* launches5, int reset)
 {
-    StreamCtx* cp = nullptr;
+    std::vector<StreamCtx*> todo;
+    const bool all = stream == (void*)(intptr_t)-1;        // FB_ALL_STREAMS: every context of the device, summed
     {
         std::lock_guard<std::mutex> lk(g_mu);
-        auto it = g_ctx.find(std::make_pair(device, stream));
-        if (it == g_ctx.end()) it = g_ctx.find(std::make_pair(device, stream ? stream : kOwnStreamKey));
-        if (it == g_ctx.end()) return fail(FB_EINVAL, "no context for device %d / stream %p", device, stream);
-        cp = &it->second;
+        if (all) {
+            for (auto& kv : g_ctx) if (kv.first.first == device) todo.push_back(&kv.second);
+        } else {
+            auto it = g_ctx.find(std::make_pair(device, stream));
+            if (it == g_ctx.end()) it = g_ctx.find(std::make_pair(device, stream ? stream : kOwnStreamKey));
+            if (it == g_ctx.end()) return fail(FB_EINVAL, "no context for device %d / stream %p", device, stream);
+            todo.push_back(&it->second);
+        }
     }
-    StreamCtx& c = *cp;
-    std::lock_guard<std::mutex> lk(c.mu);
+    for (int i = 0; i < 5; ++i) { if (ms5) ms5[i] = 0; if (launches5) launches5[i] = 0; }
     CU(cudaSetDevice(device));
-    for (auto& t : c.prof_pending) {
-        float ms = 0.f;
-        CU(cudaEventSynchronize(std::get<2>(t)));
-        CU(cudaEventElapsedTime(&ms, std::get<1>(t), std::get<2>(t)));
-        c.prof_ms[std::get<0>(t)] += ms;
-        c.prof_n[std::get<0>(t)] += 1;
-        c.prof_free.push_back(std::get<1>(t));
-        c.prof_free.push_back(std::get<2>(t));
-    }
-    c.prof_pending.clear();
-    for (int i = 0; i < 5; ++i) {
-        if (ms5) ms5[i] = c.prof_ms[i];
-        if (launches5) launches5[i] = c.prof_n[i];
-        if (reset) { c.prof_ms[i] = 0; c.prof_n[i] = 0; }
+    for (StreamCtx* cp : todo) {
+        StreamCtx& c = *cp;
+        std::lock_guard<std::mutex> lk(c.mu);
+        for (auto& t : c.prof_pending) {
+            float ms = 0.f;
+            CU(cudaEventSynchronize(std::get<2>(t)));
+            CU(cudaEventElapsedTime(&ms, std::get<1>(t), std::get<2>(t)));
+            c.prof_ms[std::get<0>(t)] += ms;
+            c.prof_n[std::get<0>(t)] += 1;
+            c.prof_free.push_back(std::get<1>(t));
+            c.prof_free.push_back(std::get<2>(t));
+        }
+        c.prof_pending.clear();
+        for (int i = 0; i < 5; ++i) {
+            if (ms5) ms5[i] += c.prof_ms[i];
+            if (launches5) launches5[i] += c.prof_n[i];
+            if (reset) { c.prof_ms[i] = 0; c.prof_n[i] = 0; }
+        }
     }
     return FB_OK;
 }

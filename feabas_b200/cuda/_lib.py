@@ -117,7 +117,10 @@ KERNEL_SLOTS = ('rows_forward', 'columns', 'rows_inverse', 'finalize', 'fused')
 
 
 def profile_read(device, stream, reset=True):
-    """{kernel: (total_ms, launches)} measured with CUDA events while option 'profile' is on."""
+    """{kernel: (total_ms, launches)} measured with CUDA events while option 'profile' is on; ``stream='all'``: summed
+    over every stream context of the device (FB_ALL_STREAMS)."""
+    if stream == 'all':
+        stream = ctypes.c_void_p(-1)
     ms = (ctypes.c_double * 5)()
     cnt = (_ll * 5)()
     check(lib().fb_profile_read(int(device), stream, ms, cnt, int(reset)))

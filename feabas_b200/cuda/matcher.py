@@ -285,15 +285,29 @@ def _bboxes_collect(enqueued):
     return np.concatenate(xy0, axis=0), np.concatenate(xy1, axis=0), np.concatenate(conf, axis=0)
 
 
-def bboxes_mesh_renderer_matcher_many(jobs, depth=2, **kwargs):
+_JOB_STREAMS = {}
+
+
+def _job_streams(device, count):
+    """``count`` side streams per device for the job-list entry point (created once)."""
+    have = _JOB_STREAMS.setdefault(device.index, [])
+    while len(have) < count:
+        have.append(torch.cuda.Stream(device=device))
+    return have[:count]
+
+
+def bboxes_mesh_renderer_matcher_many(jobs, depth=2, streams=2, **kwargs):
     """``bboxes_mesh_renderer_matcher`` over MANY independent section pairs (the aligner's job list, feabas/aligner.py:
     one pair per job; ``align_main.py`` fans them out to worker processes) with the device kept busy: the block passes
     of up to ``depth`` jobs are enqueued before the results of the oldest one are read back, so uploads, renders and
-    correlations of the next pair run under the host's share of the previous one.  ``jobs``: iterable of
+    correlations of the next pair run under the host's share of the previous one.  With ``streams`` > 1 consecutive
+    jobs alternate between that many CUDA streams, so the image kernels of one pair (issue bound) and the FFT kernels
+    of another (FP32 / shared-memory / HBM bound) share the SMs.  ``jobs``: iterable of
     ``(mesh0, mesh1, image_loader0, image_loader1, bboxes0, bboxes1)`` -- consumed lazily, a generator may build the
     loaders (and start their uploads) on demand.  Returns the list of ``(xy0, xy1, conf)``, identical to one call per job."""
     from collections import deque
     queue, results = deque(), []
+    side, home, count = None, None, 0
     for job in jobs:
         mesh0, mesh1 = job[0], job[1]
         if not (hasattr(mesh0, 'render_map') and hasattr(mesh1, 'render_map')):
@@ -301,11 +315,27 @@ def bboxes_mesh_renderer_matcher_many(jobs, depth=2, **kwargs):
                 results.append(_bboxes_collect(queue.popleft()))
             results.append(_reference_block_pass(*job, **kwargs))
             continue
-        queue.append(_bboxes_enqueue(*job, **kwargs))
+        if streams > 1:
+            if side is None:
+                # (the device without touching .tensor: a pending upload must be waited for -- and its memory recorded --
+                # on the stream that consumes it, not on the caller's)
+                dev = _as_loader(job[2], kwargs.get('device', None))._tensor.device
+                home = torch.cuda.current_stream(dev)
+                side = _job_streams(dev, int(streams))
+                for st in side:
+                    st.wait_stream(home)                  # whatever produced the inputs was ordered on the caller's stream
+            with torch.cuda.stream(side[count % len(side)]):
+                queue.append(_bboxes_enqueue(*job, **kwargs))
+            count += 1
+        else:
+            queue.append(_bboxes_enqueue(*job, **kwargs))
         while len(queue) > max(int(depth), 0):
             results.append(_bboxes_collect(queue.popleft()))
     while queue:
         results.append(_bboxes_collect(queue.popleft()))
+    if side is not None:
+        for st in side:
+            home.wait_stream(st)                          # later work on the caller's stream sees the side streams drained
     return results
 
 

@@ -229,7 +229,9 @@ int fb_set_option(const char* name, long long value);
 /* Per-kernel device time, measured with CUDA events on the launching stream while
  * option "profile" is 1.  Slots: 0 rows-forward, 1 columns, 2 rows-inverse,
  * 3 finalize, 4 fused.  ms5 / launches5: arrays of 5 (accumulated since the
- * last reset).  Synchronises the pending events of that (device, stream).     */
+ * last reset).  Synchronises the pending events of that (device, stream);
+ * stream == FB_ALL_STREAMS: the sum over every stream context of the device.  */
+#define FB_ALL_STREAMS ((void*)(-1))
 int fb_profile_read(int device, void* stream, double* ms5, long long* launches5, int reset);
 
 /* Number of kernels this library has launched in this process.              */

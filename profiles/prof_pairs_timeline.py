@@ -11,6 +11,7 @@ import bench
 import feabas_b200.cuda as fc
 
 n_pairs = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+n_streams = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 size, h, w, sigma = 8192, 512, 512, 3.5
 dev = torch.device('cuda', 0)
 secs = [bench.make_section_pair(size, 300 + k, dev, (7, -5)) for k in range(n_pairs)]
@@ -22,7 +23,7 @@ kw = dict(sigma=sigma, batch_size=len(boxes), pad=True, subpixel=True)
 
 
 def step():
-    return fc.bboxes_mesh_renderer_matcher_many(((m0, m1, l0, l1, boxes, boxes) for l0, l1 in loaders), **kw)
+    return fc.bboxes_mesh_renderer_matcher_many(((m0, m1, l0, l1, boxes, boxes) for l0, l1 in loaders), streams=n_streams, **kw)
 
 
 for _ in range(2):

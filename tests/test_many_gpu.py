@@ -121,8 +121,8 @@ def test_bboxes_matcher_many_equals_one_call_per_pair(fc):
                 fc.ArrayLoader(a), fc.ArrayLoader(b), boxes, boxes)
     want = [fc.bboxes_mesh_renderer_matcher(*job(k, False), **kw) for k in range(3)]
     for pinned in (False, True):
-        for depth in (0, 1, 2, 5):
-            many = fc.bboxes_mesh_renderer_matcher_many((job(k, pinned) for k in range(3)), depth=depth, **kw)
+        for depth, streams in ((0, 1), (1, 1), (2, 2), (5, 3), (2, 1)):
+            many = fc.bboxes_mesh_renderer_matcher_many((job(k, pinned) for k in range(3)), depth=depth, streams=streams, **kw)
             assert len(many) == 3
             for got, ref in zip(many, want):
                 _same(got, ref)
