@@ -12,6 +12,9 @@ MESH_GEAR_FIXED = 0
 MESH_GEAR_MOVING = 1
 MESH_GEAR_STAGING = 2
 
+# feabas/constant.py:18-21 -- MeshRenderer.crop modes
+RENDER_FULL = 3
+
 # feabas/constant.py:27-31
 ANNEAL_CONNECTED_RIGID = 2
 ANNEAL_COPY_EXACT = 4

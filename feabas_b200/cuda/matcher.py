@@ -21,7 +21,7 @@ from . import image as _img
 from . import _lib
 from .constant import (ANNEAL_CONNECTED_RIGID as _ANNEAL_CONNECTED_RIGID, ANNEAL_COPY_EXACT as _ANNEAL_COPY_EXACT,
                        DEFAULT_AVG_DEFORM, DEFAULT_RESOLUTION, DEFAULT_THICKNESS, FFT_CONF_MIRROR, MESH_GEAR_FIXED,
-                       MESH_GEAR_INITIAL, MESH_GEAR_MOVING, Match)
+                       MESH_GEAR_INITIAL, MESH_GEAR_MOVING, RENDER_FULL, Match)
 from .surrogate import AffineMesh, AffineSLM, ArrayLoader
 from .xcorr import fft_shape, xcorr_fft, xcorr_fft_device
 
@@ -199,6 +199,12 @@ def _render_stack(mesh, loader, bboxes, sigma, ptp_hint=None, mask_range=None):
             scale = mesh.resolution / loader.resolution
             x_lo, y_lo, x_hi, y_hi = ((v + 0.5) * scale - 0.5 for v in (x_lo, y_lo, x_hi, y_hi))
         cover = (x_lo - loader.x0, y_lo - loader.y0, x_hi - loader.x0, y_hi - loader.y0)
+    return _render_rows(loader, rows, shape, sigma, cover, ptp_hint, mask_range)
+
+
+def _render_rows(loader, rows, shape, sigma, cover=None, ptp_hint=None, mask_range=None):
+    """``fb_crop_blocks`` rows -> stack (band-passed when ``sigma`` > 0).  ``cover``: rectangle of the source the mesh
+    covers (loader pixel frame), or None when every block is known to be rendered whole."""
     if sigma <= 0:
         return _img.crop_blocks_masked(loader.tensor, rows, shape, fillval=loader.default_fillval, cover=None)[0]
     if mask_range is not None:
@@ -421,19 +427,162 @@ def _itemsize(dtype):
 
 
 def _reference_block_pass(mesh0, mesh1, image_loader0, image_loader1, bboxes0, bboxes1, **kwargs):
-    """Reference ``Mesh`` objects: blocks are rendered by the reference's own ``MeshRenderer`` on the host
-    (piecewise-linear fields, shapely masks: SURVEY section 2 row 9, not part of this package) and matched by the
-    CUDA ``xcorr_fft``.  Needs FEABAS installed."""
+    """Reference ``Mesh`` objects (FEABAS installed): the reference's own ``MeshRenderer`` is built for both sections
+    (feabas/matcher.py:792-829) and handed to ``bboxes_renderer_matcher``."""
     try:
         import feabas.matcher as ref
+        import feabas.renderer as ref_renderer
     except Exception as exc:            # pragma: no cover - FEABAS is not installed in the build container
         raise TypeError('meshes without render_map() need the FEABAS package for rendering') from exc
-    saved = ref.xcorr_fft               # pragma: no cover
-    ref.xcorr_fft = xcorr_fft           # pragma: no cover
-    try:                                # pragma: no cover
-        return ref.bboxes_mesh_renderer_matcher(mesh0, mesh1, image_loader0, image_loader1, bboxes0, bboxes1, **kwargs)
-    finally:                            # pragma: no cover
-        ref.xcorr_fft = saved
+    if isinstance(mesh0, dict):         # pragma: no cover
+        mesh0 = ref.Mesh(**mesh0)
+    elif isinstance(mesh0, str):        # pragma: no cover
+        mesh0 = ref.Mesh.from_h5(mesh0)
+    if isinstance(mesh1, dict):         # pragma: no cover
+        mesh1 = ref.Mesh(**mesh1)
+    elif isinstance(mesh1, str):        # pragma: no cover
+        mesh1 = ref.Mesh.from_h5(mesh1)
+    if isinstance(image_loader0, (str, dict)):      # pragma: no cover
+        image_loader0 = ref.dal.get_loader_from_json(image_loader0)
+    if isinstance(image_loader1, (str, dict)):      # pragma: no cover
+        image_loader1 = ref.dal.get_loader_from_json(image_loader1)
+    make = dict(geodesic_mask=kwargs.get('geodesic_mask', False), render_weight_threshold=kwargs.get('render_weight_threshold', 0),
+                affine_approx_tol=kwargs.get('affine_approx_tol', 0.0))
+    render0 = ref.MeshRenderer.from_mesh(mesh0, image_loader=image_loader0, **make)
+    render1 = ref.MeshRenderer.from_mesh(mesh1, image_loader=image_loader1, **make)
+    if render0 is None or render1 is None:
+        return np.empty((0, 2)), np.empty((0, 2)), np.empty(0)
+    return bboxes_renderer_matcher(render0, render1, image_loader0, image_loader1, bboxes0, bboxes1,
+                                   renderer_module=ref_renderer, **kwargs)
+
+
+def renderer_block_rows(render, bboxes, log_sigma, loader_resolution, renderer_module):
+    """``fb_crop_blocks`` rows (source coordinates in the loader's global pixel frame) for the blocks ``bboxes`` of a
+    REFERENCE ``MeshRenderer`` -- or None when the batch cannot go through the affine gather.
+
+    ``MeshRenderer.crop_field`` (feabas/renderer.py:497-512) first tries an affine map per block: the global fit when its
+    residue is below the tolerance, else a fit over the triangles that touch the block (``bbox_affine_tform``,
+    renderer.py:395-416); only when that misses the tolerance too does it interpolate the piecewise-linear field.  The
+    matcher asks for this with ``affine_approximated_render=True`` (the default, feabas/matcher.py:507,586-603: 0.1 px at
+    the finest level, max(1, 2 % of the spacing) above).  This function follows exactly those decisions, block by block,
+    and evaluates the covered-region rule of ``crop_field_affine`` (renderer.py:436-449) with the reference module's own
+    geometry calls; a block that is only partly covered, a geodesic mask, or a block whose fit misses the tolerance
+    makes the whole batch fall back to the reference's host renderer (the band-pass sees the batch as one array,
+    feabas/common.py:369, so a batch is not split)."""
+    approx = getattr(render, '_affine_approximator', None)
+    tol = float(getattr(render, '_affine_approx_tol', 0) or 0)
+    if approx is None or not tol > 0 or getattr(render, '_geodesic_mask', False):
+        return None
+    offset = np.tile(np.asarray(render._offset, dtype=np.float64).ravel(), 2)
+    covered = getattr(render, '_covered_region', None)
+    b = np.asarray(bboxes, dtype=np.float64).reshape(-1, 4)
+    rows = np.empty((b.shape[0], 10), dtype=np.float64)
+    shape = None
+    for i in range(b.shape[0]):
+        bbox0 = b[i] - offset
+        if approx['global_residue'] < tol:
+            full = np.asarray(approx['global_affine'], dtype=np.float64)
+            a, t = full[:2, :2], full[-1, :2]
+        else:                                           # pragma: no cover - needs shapely's STRtree
+            a, t, res = render.bbox_affine_tform(bbox0, offsetting=False)
+            if a is None or not res < tol:
+                return None
+        wd, ht = round(bbox0[2] - bbox0[0]), round(bbox0[3] - bbox0[1])
+        if shape is None:
+            shape = (int(ht), int(wd))
+        elif shape != (int(ht), int(wd)):
+            return None
+        if log_sigma > 0 and covered is not None:       # precise_mask=log_sigma>0
+            box0 = renderer_module.shpgeo.box(*(bbox0 - 0.5))
+            box1 = renderer_module.shapely.affinity.affine_transform(box0, np.concatenate((a.T, t), axis=None))
+            if not (box1.area - covered.intersection(box1).area) < 1:
+                return None
+        rows[i] = (bbox0[0], bbox0[1], (bbox0[2] - bbox0[0]) / wd, (bbox0[3] - bbox0[1]) / ht,
+                   a[0, 0], a[1, 0], t[0], a[0, 1], a[1, 1], t[1])
+    if loader_resolution != render.resolution:          # crop_multiple, renderer.py:621-624 (pixel centres kept)
+        scale = render.resolution / loader_resolution
+        rows[:, [4, 5, 7, 8]] *= scale
+        rows[:, [6, 9]] = (rows[:, [6, 9]] + 0.5) * scale - 0.5
+    return rows, shape
+
+
+def _rows_footprint(rows, shape):
+    """Integer bounding box (xmin, ymin, xmax, ymax) of the source pixels the rows can touch, with OpenCV's margin."""
+    bh, bw = shape
+    xe = np.stack((rows[:, 0], rows[:, 0] + (bw - 1) * rows[:, 2]), axis=-1)[:, :, None]
+    ye = np.stack((rows[:, 1], rows[:, 1] + (bh - 1) * rows[:, 3]), axis=-1)[:, None, :]
+    xs = xe * rows[:, 4, None, None] + ye * rows[:, 5, None, None] + rows[:, 6, None, None]
+    ys = xe * rows[:, 7, None, None] + ye * rows[:, 8, None, None] + rows[:, 9, None, None]
+    return (int(np.floor(xs.min())) - 6, int(np.floor(ys.min())) - 6, int(np.ceil(xs.max())) + 7, int(np.ceil(ys.max())) + 7)
+
+
+def _pixels_for_rows(image_loader, rows, shape, device=None):
+    """An ``ArrayLoader`` that holds every source pixel the rows touch: the whole image of an in-RAM loader (uploaded
+    once and cached on it), else the region the batch needs, cut with the loader's own ``crop`` (tiles read and
+    assembled by FEABAS's IO layer, feabas/dal.py) and uploaded."""
+    if isinstance(image_loader, ArrayLoader) or hasattr(image_loader, '_img'):
+        return _as_loader(image_loader, device)
+    region = _rows_footprint(rows, shape)
+    img = image_loader.crop(region, return_empty=True)
+    return ArrayLoader(np.ascontiguousarray(img), fillval=image_loader.default_fillval, resolution=image_loader.resolution,
+                       x0=region[0], y0=region[1], device=device)
+
+
+def bboxes_renderer_matcher(render0, render1, image_loader0, image_loader1, bboxes0, bboxes1, renderer_module=None, **kwargs):
+    """The block pass of ``bboxes_mesh_renderer_matcher`` (feabas/matcher.py:830-861) over two REFERENCE ``MeshRenderer``
+    objects.  Batches whose blocks are affine within the renderer's tolerance and fully covered (``renderer_block_rows``)
+    are cut from the section on the device (``fb_crop_blocks``), band-passed and correlated there; any other batch is
+    rendered by the renderer's own ``crop_multiple`` on the host and correlated by the CUDA ``xcorr_fft``."""
+    if renderer_module is None:
+        import feabas.renderer as renderer_module       # pragma: no cover - needs FEABAS
+    batch_size = kwargs.get('batch_size', None)
+    sigma = kwargs.get('sigma', 0.0)
+    conf_mode = kwargs.get('conf_mode', FFT_CONF_MIRROR)
+    pad = kwargs.get('pad', True)
+    subpixel = kwargs.get('subpixel', False)
+    mask_range = kwargs.get('mask_range', None)
+    render_mode = kwargs.get('render_mode', RENDER_FULL)
+    empty = (np.empty((0, 2)), np.empty((0, 2)), np.empty(0))
+    if bboxes0 is None or len(bboxes0) == 0:
+        return empty
+    bboxes0, bboxes1 = np.asarray(bboxes0), np.asarray(bboxes1)
+    edges = _blk.split_batches(bboxes0, bboxes1, batch_size)
+    conf_dtype = np.float64 if conf_mode == 1 else np.float32
+    xy0, xy1, conf = [], [], []
+    for lo, hi in zip(edges[:-1], edges[1:]):
+        if hi <= lo:
+            continue
+        b0, b1 = bboxes0[lo:hi], bboxes1[lo:hi]
+        on_device = render_mode == RENDER_FULL          # (RENDER_CONTIGEOUS / LOCAL_* modes: the reference's own code)
+        r0 = renderer_block_rows(render0, b0, sigma, image_loader0.resolution, renderer_module) if on_device else None
+        r1 = renderer_block_rows(render1, b1, sigma, image_loader1.resolution, renderer_module) if on_device and r0 is not None else None
+        if r0 is not None and r1 is not None:
+            pix0 = _pixels_for_rows(image_loader0, *r0, device=kwargs.get('device', None))
+            pix1 = _pixels_for_rows(image_loader1, *r1, device=pix0.tensor.device.index)
+            rows0, rows1 = r0[0].copy(), r1[0].copy()
+            rows0[:, 6] -= pix0.x0; rows0[:, 9] -= pix0.y0
+            rows1[:, 6] -= pix1.x0; rows1[:, 9] -= pix1.y0
+            stack0 = _render_rows(pix0, rows0, r0[1], sigma, None, None, mask_range)
+            stack1 = None if stack0 is None else _render_rows(pix1, rows1, r1[1], sigma, None, None, mask_range)
+            if stack0 is None or stack1 is None:
+                continue
+            res = xcorr_fft_device(stack0, stack1, conf_mode=conf_mode, pad=pad, subpixel=subpixel).cpu().numpy()
+            dx, dy, cf = res[0], res[1], res[2].astype(conf_dtype)
+        else:
+            stack0 = render0.crop_multiple(b0, mode=render_mode, log_sigma=sigma, remap_interp=1, mask_range=mask_range)   # 1 = cv2.INTER_LINEAR
+            if stack0 is None:
+                continue
+            stack1 = render1.crop_multiple(b1, mode=render_mode, log_sigma=sigma, remap_interp=1, mask_range=mask_range)
+            if stack1 is None:
+                continue
+            dx, dy, cf = xcorr_fft(stack0, stack1, conf_mode=conf_mode, pad=pad, subpixel=subpixel)
+        p0, p1 = _blk.block_points(b0, b1, dx, dy)
+        xy0.append(p0)
+        xy1.append(p1)
+        conf.append(cf)
+    if not xy0:
+        return empty
+    return np.concatenate(xy0, axis=0), np.concatenate(xy1, axis=0), np.concatenate(conf, axis=0)
 
 
 # --------------------------------------------------------------------------------------------

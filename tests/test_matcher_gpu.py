@@ -3,6 +3,7 @@ iterative loop, stitching_matcher) against golden vectors of the unmodified refe
 import numpy as np
 import pytest
 
+import loop_cases as lc
 from feabas_b200 import synth
 from oracle import matcher_oracle as mo
 
@@ -129,3 +130,83 @@ def test_section_matcher_surrogate(fc):
     assert xy0.shape == xy1.shape and xy0.shape[0] > 50 and wt.shape[0] == xy0.shape[0]
     d = np.median(xy1 - xy0, axis=0)
     np.testing.assert_allclose(d, [8, -6], atol=0.3)
+
+
+class _DuckRenderer:
+    """The attributes of ``feabas.renderer.MeshRenderer`` that ``renderer_block_rows`` reads (renderer.py:36-48), filled
+    in for an affine mesh the way the reference's ``from_mesh`` does (:90-109), and a ``crop_multiple`` that renders on
+    the host through the oracle (what the reference's own method does for such a mesh)."""
+
+    def __init__(self, mesh, img, tol=0.1, origin=(0, 0)):
+        from oracle import convex
+        ainv, tinv = mesh.render_map()
+        self._affine_approximator = {'global_affine': np.concatenate((ainv, tinv.reshape(1, 2)), axis=0), 'global_residue': 0.0}
+        self._affine_approx_tol = tol
+        self._offset = np.zeros((1, 2))
+        self._geodesic_mask = False
+        self.resolution = mesh.resolution
+        x0, y0, x1, y1 = mesh.bounds
+        self._cover = (x0 + 0.5, y0 + 0.5, x1 - 0.5, y1 - 0.5)
+        self._covered_region = convex.box(*self._cover)
+        self._mesh, self._img, self._origin = mesh, img, origin
+        self.host_batches = 0
+
+    def crop_multiple(self, bboxes, **kwargs):
+        self.host_batches += 1
+        sigma = kwargs.get('log_sigma', 0)
+        ainv, tinv = self._mesh.render_map()
+        cover = None if not sigma > 0 else tuple(np.array(self._cover) - np.tile(self._origin, 2))
+        stack, mask = mo.render_blocks_oracle(self._img, bboxes, ainv, tinv, fillval=0, origin_xy=self._origin, cover=cover)
+        if not mask.any():
+            return None
+        return mo.masked_dog_oracle(stack, sigma, mask=mask) if sigma > 0 else stack
+
+
+class _RegionLoader:
+    """A loader without an in-RAM image attribute (FEABAS's tile-backed loaders): only ``crop`` gives pixels."""
+
+    def __init__(self, img, origin=(0, 0), resolution=4.0):
+        self.img, self.origin, self.resolution, self.default_fillval, self.dtype = img, origin, resolution, 0, img.dtype
+        self.crops = 0
+
+    def crop(self, bbox, return_empty=False, **kwargs):
+        self.crops += 1
+        x0, y0 = self.origin
+        return mo.crop_with_fill(self.img, (bbox[0] - x0, bbox[1] - y0, bbox[2] - x0, bbox[3] - y0), self.default_fillval)
+
+
+def test_bboxes_renderer_matcher_device_and_host_batches(fc):
+    """Reference-style renderers: batches that are affine within tolerance and fully covered are cut on the device (same
+    numbers as the AffineMesh path, bit for bit), a batch with a block hanging over the mesh border goes through the
+    renderer's own ``crop_multiple`` on the host and still meets the gates."""
+    import types
+    from oracle import convex
+    from feabas_b200.cuda import matcher as pm
+    mod = types.SimpleNamespace(shpgeo=types.SimpleNamespace(box=convex.box),
+                                shapely=types.SimpleNamespace(affinity=types.SimpleNamespace(affine_transform=convex.affine_transform)))
+    img0, img1 = lc.section_pair(71, size=520, angle=0.006, scale=1.003, shift=(5.0, -3.0))
+    h, w = img0.shape
+    m0 = fc.AffineMesh.from_bbox((0, 0, w, h), cartesian=True, uid=0.0)
+    m1 = fc.AffineMesh.from_bbox((0, 0, w, h), cartesian=True, uid=1.0)
+    ang = 0.006
+    m1.set_map(np.array([[np.cos(ang), np.sin(ang)], [-np.sin(ang), np.cos(ang)]]) * 1.003, np.array([-4.0, 2.5]))
+    inner = np.array([(x, y, x + 128, y + 128) for y in (40, 190, 340) for x in (40, 190, 340)], dtype=np.float64)
+    for sigma in (0.0, 2.5):
+        kw = dict(sigma=sigma, batch_size=9, pad=True, subpixel=True)
+        want = fc.bboxes_mesh_renderer_matcher(m0, m1, fc.ArrayLoader(img0), fc.ArrayLoader(img1), inner, inner, **kw)
+        r0, r1 = _DuckRenderer(m0, img0), _DuckRenderer(m1, img1)
+        ld0, ld1 = _RegionLoader(img0), _RegionLoader(img1)
+        got = pm.bboxes_renderer_matcher(r0, r1, ld0, ld1, inner, inner, renderer_module=mod, **kw)
+        assert r0.host_batches == 0 and r1.host_batches == 0 and ld0.crops == 1 and ld1.crops == 1
+        for a, b in zip(got, want):
+            np.testing.assert_array_equal(a, b)
+    # a block over the border with the band-pass on: host batch
+    border = np.concatenate((inner[:4], np.array([(430, 430, 558, 558)], dtype=np.float64)), axis=0)
+    kw = dict(sigma=2.5, batch_size=9, pad=True, subpixel=True)
+    want = fc.bboxes_mesh_renderer_matcher(m0, m1, fc.ArrayLoader(img0), fc.ArrayLoader(img1), border, border, **kw)
+    r0, r1 = _DuckRenderer(m0, img0), _DuckRenderer(m1, img1)
+    got = pm.bboxes_renderer_matcher(r0, r1, _RegionLoader(img0), _RegionLoader(img1), border, border, renderer_module=mod, **kw)
+    assert r0.host_batches == 1 and r1.host_batches == 1
+    np.testing.assert_allclose(got[0], want[0], atol=0.02)
+    np.testing.assert_allclose(got[1], want[1], atol=0.02)
+    np.testing.assert_allclose(got[2], want[2], rtol=1e-4, atol=1e-6)

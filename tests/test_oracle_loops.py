@@ -101,3 +101,57 @@ def test_reference_live_rerun_matches_committed_trace(golden_stitch):
     np.testing.assert_array_equal(xy0, rec['xy0'])
     np.testing.assert_array_equal(wt, rec['weight'])
     assert strain == float(rec['strain'])
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason='reference sources not present (GPU box)')
+def test_renderer_block_rows_follow_the_reference_renderer():
+    """``renderer_block_rows`` reads a REFERENCE ``MeshRenderer`` (the unmodified class; its constructor is the affine
+    stand-in's) the way ``crop_field`` does: the rows it builds are the field ``crop_field_affine`` returns, pixel for
+    pixel, blocks that hang over the covered region by a square pixel or more send the batch to the host renderer, and a
+    loader at another resolution rescales the map as ``crop_multiple`` does."""
+    import types
+    from oracle.ref_harness import Harness
+    from feabas_b200.cuda import matcher as pm
+    h = Harness()
+    rng = np.random.default_rng(2)
+    with h:
+        mesh = h.AffineMesh.from_bbox((0, 0, 640, 480), cartesian=True, uid=1.0, resolution=4.0)
+        ang = 0.013
+        mesh.set_map(np.array([[np.cos(ang), np.sin(ang)], [-np.sin(ang), np.cos(ang)]]) * 1.004, np.array([5.3, -7.1]))
+        img = rng.integers(0, 256, (480, 640), dtype=np.uint8)
+        for res_loader in (4.0, 8.0):
+            loader = h.stream_loader(img, resolution=res_loader)
+            render = h.renderer_cls.from_mesh(mesh, image_loader=loader, affine_approx_tol=0.1)
+            inner = np.array([(100, 80, 228, 208), (300, 200, 428, 328), (60, 300, 188, 428)], dtype=np.float64)
+            for sigma in (0.0, 2.5):
+                got = pm.renderer_block_rows(render, inner, sigma, loader.resolution, h.renderer)
+                assert got is not None
+                rows, shape = got
+                assert shape == (128, 128)
+                for k, bbox in enumerate(inner):
+                    xf, yf, mask = render.crop_field(bbox, log_sigma=sigma)
+                    if loader.resolution != render.resolution:
+                        sc = render.resolution / loader.resolution
+                        xf, yf = (xf + 0.5) * sc - 0.5, (yf + 0.5) * sc - 0.5
+                    assert mask.all()
+                    cols, rws = np.meshgrid(np.arange(128), np.arange(128))
+                    xx, yy = rows[k, 0] + cols * rows[k, 2], rows[k, 1] + rws * rows[k, 3]
+                    mine_x = xx * rows[k, 4] + yy * rows[k, 5] + rows[k, 6]
+                    mine_y = xx * rows[k, 7] + yy * rows[k, 8] + rows[k, 9]
+                    if loader.resolution == render.resolution:          # the same float64 operations in the same order
+                        np.testing.assert_array_equal(mine_x, xf)
+                        np.testing.assert_array_equal(mine_y, yf)
+                    else:                                               # the rescale is folded into the map
+                        np.testing.assert_allclose(mine_x, xf, rtol=0, atol=1e-9)
+                        np.testing.assert_allclose(mine_y, yf, rtol=0, atol=1e-9)
+            # a block that sticks out of the mesh: whole when rendered without the band-pass, host renderer with it
+            border = np.array([(100, 80, 228, 208), (560, 380, 688, 508)], dtype=np.float64)
+            assert pm.renderer_block_rows(render, border, 0.0, loader.resolution, h.renderer) is not None
+            assert pm.renderer_block_rows(render, border, 2.5, loader.resolution, h.renderer) is None
+            # ... and mixed block sizes, a zero tolerance or a geodesic mask are not affine-gather batches
+            assert pm.renderer_block_rows(render, np.array([(0, 0, 64, 64), (0, 0, 128, 64)], dtype=np.float64), 0.0, loader.resolution, h.renderer) is None
+            plain = h.renderer_cls.from_mesh(mesh, image_loader=loader, affine_approx_tol=0.1)
+            plain._affine_approx_tol = 0
+            assert pm.renderer_block_rows(plain, inner, 0.0, loader.resolution, h.renderer) is None
+            geo = types.SimpleNamespace(_affine_approximator=render._affine_approximator, _affine_approx_tol=0.1, _geodesic_mask=True)
+            assert pm.renderer_block_rows(geo, inner, 0.0, loader.resolution, h.renderer) is None
