@@ -351,13 +351,15 @@ __device__ void kwf_pair(const WfParams& wp, unsigned char* smem)
 #pragma unroll
             for (int n1 = 0; n1 < EY; ++n1) {
                 const int y = n1 * TY + ty;
-                v[n1] = y < H0 ? mk<float>(S[(size_t)y * SP + c], S[PLANE + (size_t)y * SP + c]) : mk<float>(0.f, 0.f);
+                // (idle slots of the last round transform zeros: reading the column another slot is rewriting in place would be
+                // a -- harmless, the result is dropped -- data race)
+                v[n1] = (live && y < H0) ? mk<float>(S[(size_t)y * SP + c], S[PLANE + (size_t)y * SP + c]) : mk<float>(0.f, 0.f);
             }
             LY::run(v, u0, regy, twy, ty);
 #pragma unroll
             for (int n1 = 0; n1 < EY; ++n1) {
                 const int y = n1 * TY + ty;
-                v[n1] = y < H1 ? mk<float>(S[(size_t)y * SP + KP + c], S[PLANE + (size_t)y * SP + KP + c]) : mk<float>(0.f, 0.f);
+                v[n1] = (live && y < H1) ? mk<float>(S[(size_t)y * SP + KP + c], S[PLANE + (size_t)y * SP + KP + c]) : mk<float>(0.f, 0.f);
             }
             LY::run(v, u1, regy, twy, ty);
             // second transforms straight from the register layout of the first (LineFFT::run_rev): no exchange in between
