@@ -91,11 +91,12 @@ __global__ void __launch_bounds__(512) fbk_fused(const __grid_constant__ XcParam
 // inverse transform; the column stage is linear, so the mean is taken over its per-channel outputs
 template <typename T>
 __global__ void __launch_bounds__(256) fbk_channel_mean(const cx<T>* __restrict__ g, cx<T>* __restrict__ out, int nchan,
-                                                         size_t elems, size_t total)
+                                                         size_t elems, size_t total, int pitch, int kp)
 {
     const T inv = T(1) / T(nchan);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const size_t pair = i / elems, e = i - pair * elems;
+        if ((int)(e % (size_t)pitch) >= kp) continue;      // row padding: never written, never read downstream
         const cx<T>* src = g + (pair * nchan) * elems + e;
         cx<T> a = src[0];
         for (int c = 1; c < nchan; ++c) a = a + src[(size_t)c * elems];
@@ -723,7 +724,7 @@ static int launch_chunk(const Problem& q, StreamCtx& ctx, const void* img0, cons
         cx<T>* gout = reinterpret_cast<cx<T>*>(w + f0 + f1 + gg);
         const size_t total = (size_t)nb * gpair;
         const int grid = (int)((total + 255) / 256 < 65535 ? (total + 255) / 256 : 65535);
-        fbk_channel_mean<T><<<grid, 256, 0, st>>>(reinterpret_cast<const cx<T>*>(p.G), gout, C, gpair, total);
+        fbk_channel_mean<T><<<grid, 256, 0, st>>>(reinterpret_cast<const cx<T>*>(p.G), gout, C, gpair, total, g.fpitch, g.kp);
         p.G = gout;
         g_launches += 1;
     }
