@@ -1050,7 +1050,7 @@ def clocks_monitor_stop(sampler, _path=None):
     return sampler.stop()
 
 
-def h2d_ceiling(dev, world, dist, mib=256, reps=4):
+def h2d_ceiling(dev, world, dist, mib=256, reps=8):
     """What the host -> device path of this box delivers with ALL ranks copying at once: one pinned buffer and one
     cudaMemcpyAsync stream per rank, started together; GB/s summed over ranks (max-over-ranks time).  The end-to-end
     numbers are bound by this, not by a kernel."""
@@ -1059,18 +1059,21 @@ def h2d_ceiling(dev, world, dist, mib=256, reps=4):
     dst = torch.empty(mib << 20, dtype=torch.uint8, device=dev)
     dst.copy_(buf, non_blocking=True)
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(reps):
-        dst.copy_(buf, non_blocking=True)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([dt], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
-    return world * reps * (mib << 20) / dt / 1e9
+    best = 0.0
+    for _ in range(3):                                   # best of three trials (the first ones still fault pages in on some boxes)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            dst.copy_(buf, non_blocking=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        best = max(best, world * reps * (mib << 20) / dt / 1e9)
+    return best
 
 
 def measured_traffic(workload, kernel):

@@ -45,8 +45,8 @@ def divide_bbox(bbox, **kwargs):
     count_x = max(np.ceil(width / size_x), least_x)
     step_y = int(np.ceil(height / count_y))
     step_x = int(np.ceil(width / count_x))
-    starts_x = np.linspace(x_lo, x_hi - step_x, num=int(count_x), endpoint=True)
-    starts_y = np.linspace(y_lo, y_hi - step_y, num=int(count_y), endpoint=True)
+    starts_x = _linspace(x_lo, x_hi - step_x, int(count_x))
+    starts_y = _linspace(y_lo, y_hi - step_y, int(count_y))
     if shrink_factor != 1:
         small_x, small_y = step_x * shrink_factor, step_y * shrink_factor
         starts_x = starts_x + (step_x - small_x) / 2
@@ -55,9 +55,24 @@ def divide_bbox(bbox, **kwargs):
     if round_output:
         starts_x = np.round(starts_x).astype(np.int32)
         starts_y = np.round(starts_y).astype(np.int32)
-    grid_x, grid_y = np.meshgrid(starts_x, starts_y)
-    grid_x, grid_y = grid_x.ravel(), grid_y.ravel()
+    grid_x, grid_y = np.tile(starts_x, starts_y.size), np.repeat(starts_y, starts_x.size)      # meshgrid(...).ravel()
     return grid_x, grid_y, grid_x + step_x, grid_y + step_y
+
+
+def _linspace(start, stop, num):
+    """``np.linspace(start, stop, num, endpoint=True)`` (float64) without its argument handling -- the same operations in
+    the same order: ``arange(num) * step + start`` with ``step = (stop - start) / (num - 1)``, the last sample set to
+    ``stop``; the block grid is built thousands of times per section."""
+    start, stop = float(start), float(stop)
+    if num == 1:
+        return np.array([start])
+    delta = stop - start
+    step = delta / (num - 1)
+    y = np.arange(num, dtype=np.float64)
+    y = y * step if step != 0 else y / (num - 1) * delta
+    y += start
+    y[-1] = stop
+    return y
 
 
 def intersect_bbox(bbox0, bbox1):
@@ -72,6 +87,14 @@ def z_order(indices, base=2):
     grid = np.asarray(indices)
     ndim = grid.shape[-1]
     grid = grid - grid.min(axis=0)
+    if base == 2 and ndim == 2 and grid.size and float(grid.max()) < 2 ** 31 and np.all(grid == np.floor(grid)):
+        # the digit loop below for the usual case, as bit interleaving on integers: the same integer score
+        # (digit d of axis a lands on bit 2 d + a), hence the same stable order
+        g = grid.astype(np.int64)
+        for shift, maskbits in ((16, 0x0000FFFF0000FFFF), (8, 0x00FF00FF00FF00FF), (4, 0x0F0F0F0F0F0F0F0F),
+                                (2, 0x3333333333333333), (1, 0x5555555555555555)):
+            g = (g | (g << shift)) & maskbits
+        return np.argsort(g[:, 0] + 2 * g[:, 1], kind='stable')
     key = np.zeros_like(grid)
     digit = 0
     while np.any(grid > 0):
@@ -104,7 +127,10 @@ def distributor_cartesian_bbox(mesh0, mesh1, spacing, **kwargs):
     if not valid:
         return None, None
     boxes0 = np.stack(divide_bbox(common_box, block_size=spacing, min_num_blocks=min_num_blocks, shrink_factor=shrink0), axis=-1)
-    boxes1 = np.stack(divide_bbox(common_box, block_size=spacing, min_num_blocks=min_num_blocks, shrink_factor=shrink1), axis=-1)
+    if shrink1 == shrink0:                               # (the usual call: one grid for both sides)
+        boxes1 = boxes0.copy()
+    else:
+        boxes1 = np.stack(divide_bbox(common_box, block_size=spacing, min_num_blocks=min_num_blocks, shrink_factor=shrink1), axis=-1)
     if zorder:
         col = np.round((boxes0[:, 0] - boxes0[:, 0].min()) / spacing)
         row = np.round((boxes0[:, 1] - boxes0[:, 1].min()) / spacing)
@@ -117,6 +143,12 @@ def split_batches(bboxes0, bboxes1, batch_size=None):
     """Index edges of the xcorr batches: a new batch starts wherever the (rounded) block size of
     either side changes, and runs longer than ``batch_size`` are cut into near-equal pieces."""
     count = bboxes0.shape[0]
+    if count and (batch_size is None or batch_size >= count):
+        # the usual call: one grid of equal blocks, no batch limit -- the general code below returns [0, count] for it
+        s0 = np.round(bboxes0[:, 2:4] - bboxes0[:, 0:2])
+        s1 = np.round(bboxes1[:, 2:4] - bboxes1[:, 0:2])
+        if (s0 == s0[0]).all() and (s1 == s1[0]).all() and (s0[0] > 0).all() and (s1[0] > 0).all():
+            return np.array([0, count])
     size0 = np.round(bbox_sizes(bboxes0))
     size1 = np.round(bbox_sizes(bboxes1))
     change = np.any(np.diff(size0, axis=0), axis=-1) | np.any(np.diff(size1, axis=0), axis=-1)

@@ -380,18 +380,23 @@ def crop_blocks_multi(parts, block_shape, fillval=0):
     dtype and a device.  Returns the stack ``sum(K) x bh x bw``, parts in order."""
     bh, bw = int(block_shape[0]), int(block_shape[1])
     img0 = parts[0][0]
-    rows = np.concatenate([np.ascontiguousarray(b, dtype=np.float64).reshape(-1, 10) for _, b in parts], axis=0)
+    row_list = [np.ascontiguousarray(b, dtype=np.float64).reshape(-1, 10) for _, b in parts]
+    counts = np.array([r.shape[0] for r in row_list], dtype=np.int64)
+    rows = np.concatenate(row_list, axis=0)
     n = rows.shape[0]
     src = np.empty(n, dtype=_SRC_DTYPE)
-    at = 0
-    for img, b in parts:
-        k = np.asarray(b).reshape(-1, 10).shape[0]
+    for img, _ in parts:
         if img.dtype != img0.dtype or img.device != img0.device or img.dim() != 2 or not img.is_contiguous():
             raise ValueError('crop_blocks_multi: the source images must be contiguous 2-D tensors of one dtype on one device')
-        ox, oy = batch_origin(b, bh, bw)
-        src['img'][at:at + k], src['ih'][at:at + k], src['iw'][at:at + k] = img.data_ptr(), img.shape[0], img.shape[1]
-        src['ox'][at:at + k], src['oy'][at:at + k] = ox, oy
-        at += k
+    if n:
+        live = counts > 0
+        starts = (np.cumsum(counts) - counts)[live]
+        ox, oy = batch_origins(rows, bh, bw, starts)                      # one origin per part, all parts at once
+        reps = counts[live]
+        src['img'] = np.repeat(np.array([img.data_ptr() for (img, _), ok in zip(parts, live) if ok], dtype=np.uint64), reps)
+        src['ih'] = np.repeat(np.array([img.shape[0] for (img, _), ok in zip(parts, live) if ok], dtype=np.int32), reps)
+        src['iw'] = np.repeat(np.array([img.shape[1] for (img, _), ok in zip(parts, live) if ok], dtype=np.int32), reps)
+        src['ox'], src['oy'] = np.repeat(ox, reps), np.repeat(oy, reps)
     out = torch.empty((n, bh, bw), dtype=img0.dtype, device=img0.device)
     if n:
         packed = np.concatenate((rows.view(np.uint8).reshape(-1), src.view(np.uint8).reshape(-1)))    # one upload
@@ -407,16 +412,29 @@ def crop_blocks(img, blocks, block_shape, origin=None, fillval=0, out=None):
     return crop_blocks_masked(img, blocks, block_shape, origin=origin, fillval=fillval, out=out)[0]
 
 
+def _block_field_minima(b, bh, bw):
+    """Per block: minimum of the (affine) coordinate field over the block -- it sits at a corner."""
+    xe = np.stack((b[:, 0], b[:, 0] + (bw - 1) * b[:, 2]), axis=-1)[:, :, None]     # N x 2 x 1
+    ye = np.stack((b[:, 1], b[:, 1] + (bh - 1) * b[:, 3]), axis=-1)[:, None, :]     # N x 1 x 2
+    xs = xe * b[:, 4, None, None] + ye * b[:, 5, None, None] + b[:, 6, None, None]
+    ys = xe * b[:, 7, None, None] + ye * b[:, 8, None, None] + b[:, 9, None, None]
+    return xs.reshape(b.shape[0], -1).min(axis=1), ys.reshape(b.shape[0], -1).min(axis=1)
+
+
+def batch_origins(rows, bh, bw, starts):
+    """``batch_origin`` of many batches at once: ``rows`` holds the batches one after the other, batch k starts at row
+    ``starts[k]`` (increasing, first 0).  Returns two float64 arrays (x, y), one entry per batch."""
+    x_min, y_min = _block_field_minima(np.asarray(rows, dtype=np.float64).reshape(-1, 10), bh, bw)
+    starts = np.asarray(starts, dtype=np.int64)
+    return np.floor(np.minimum.reduceat(x_min, starts)) - 4, np.floor(np.minimum.reduceat(y_min, starts)) - 4
+
+
 def batch_origin(blocks, bh, bw, partial=None, cover=None):
     """floor(min of the batch's coordinate field) - 4 per axis (common.py:300-304): the field is affine, so
     its extrema sit at block corners.  ``partial`` (bool per block) marks blocks of which only the pixels inside
     ``cover`` are rendered: their contribution to the minimum cannot lie below the cover's lower edge."""
     b = np.asarray(blocks, dtype=np.float64).reshape(-1, 10)
-    xe = np.stack((b[:, 0], b[:, 0] + (bw - 1) * b[:, 2]), axis=-1)[:, :, None]     # N x 2 x 1
-    ye = np.stack((b[:, 1], b[:, 1] + (bh - 1) * b[:, 3]), axis=-1)[:, None, :]     # N x 1 x 2
-    xs = xe * b[:, 4, None, None] + ye * b[:, 5, None, None] + b[:, 6, None, None]
-    ys = xe * b[:, 7, None, None] + ye * b[:, 8, None, None] + b[:, 9, None, None]
-    x_min, y_min = xs.reshape(b.shape[0], -1).min(axis=1), ys.reshape(b.shape[0], -1).min(axis=1)
+    x_min, y_min = _block_field_minima(b, bh, bw)
     if partial is not None and cover is not None and np.any(partial):
         x_min = np.where(partial, np.maximum(x_min, cover[0]), x_min)
         y_min = np.where(partial, np.maximum(y_min, cover[1]), y_min)
