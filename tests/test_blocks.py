@@ -71,6 +71,33 @@ def test_random_against_oracle():
         _same(p[0], q[0]), _same(p[1], q[1])
 
 
+def test_fast_paths_of_the_block_grid_are_the_reference_arithmetic():
+    """The block grid is built thousands of times per section: ``_linspace`` is ``np.linspace`` operation for operation,
+    ``divide_bbox`` / ``z_order`` on float-valued boxes (what the matcher passes: mesh bounding boxes after a translation)
+    equal the oracle bit for bit, ``split_batches``' shortcut equals its general code."""
+    rng = np.random.default_rng(0)
+    for it in range(3000):
+        a, b = rng.uniform(-1e4, 1e4, 2)
+        if it % 50 == 0:
+            b = a
+        n = int(rng.integers(1, 60))
+        _same(bk._linspace(a, b, n), np.linspace(a, b, num=n, endpoint=True))
+    for it in range(1500):
+        x0, y0 = rng.uniform(-500, 500, 2) if it % 2 else rng.integers(-500, 500, 2)
+        w, h = rng.uniform(30, 4000, 2) if it % 3 else rng.integers(30, 4000, 2)
+        box = (x0, y0, x0 + w, y0 + h)
+        kw = dict(block_size=float(rng.uniform(20, 900)), min_num_blocks=int(rng.integers(1, 4)), shrink_factor=float(rng.choice([1, 0.7, 0.5])),
+                  round_output=bool(it % 4))
+        _same(np.stack(bk.divide_bbox(box, **kw)), np.stack(mo.divide_bbox_oracle(box, **kw)))
+        g = rng.integers(0, int(rng.integers(1, 70)), (int(rng.integers(1, 400)), 2)).astype(np.float64)
+        _same(bk.z_order(g), mo.z_order_oracle(g))
+    _same(bk.z_order(np.array([[0.5, 1.0], [2.0, 0.0], [1.0, 1.0]])), mo.z_order_oracle(np.array([[0.5, 1.0], [2.0, 0.0], [1.0, 1.0]])))   # general loop
+    boxes = np.stack(mo.divide_bbox_oracle((3.2, -7.9, 3003.2, 392.1), block_size=75, min_num_blocks=2), -1)
+    _same(bk.split_batches(boxes, boxes, None), np.array([0, boxes.shape[0]]))
+    _same(bk.split_batches(boxes, boxes, 10 ** 6), np.array([0, boxes.shape[0]]))
+    assert bk.split_batches(boxes, boxes, 7).size > 2
+
+
 def test_auto_spacings_and_division():
     # SURVEY 8(d): 3000 x 500 strips -> [75, 750] (float fuzz kept), 400 x 500 -> [75]
     for s0, s1 in [((3000, 500), (3000, 500)), ((400, 4000), (400, 4000)), ((400, 500), (400, 500)), ((90, 70), (80, 75))]:

@@ -42,6 +42,20 @@ def test_batch_origin_matches_the_field_minimum():
     assert ox == np.floor(min(xs)) - 4 and oy == np.floor(min(ys)) - 4
 
 
+def test_batch_origins_of_many_batches_equal_one_call_per_batch():
+    """``crop_blocks_multi`` takes the source-crop origins of all its parts in one vectorised pass."""
+    rng = np.random.default_rng(1)
+    for _ in range(100):
+        counts = rng.integers(1, 40, int(rng.integers(1, 6)))
+        rows = rng.uniform(-50, 50, (counts.sum(), 10))
+        rows[:, 2:4] = rng.uniform(0.5, 1.5, (counts.sum(), 2))
+        rows[:, [4, 8]] = 1 + rng.normal(0, 0.01, (counts.sum(), 2))
+        starts = np.cumsum(counts) - counts
+        ox, oy = _img.batch_origins(rows, 64, 48, starts)
+        for j, (lo, c) in enumerate(zip(starts, counts)):
+            assert _img.batch_origin(rows[lo:lo + c], 64, 48) == (ox[j], oy[j])
+
+
 def test_montage_overlaps_of_the_stitch_workload():
     wl = dict(bench.WORKLOADS['stitch2x3'], tile=(300, 400), margin=10)
     strips = bench.make_overlap_strips(wl, seed=1)
