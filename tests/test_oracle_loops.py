@@ -155,3 +155,18 @@ def test_renderer_block_rows_follow_the_reference_renderer():
             assert pm.renderer_block_rows(plain, inner, 0.0, loader.resolution, h.renderer) is None
             geo = types.SimpleNamespace(_affine_approximator=render._affine_approximator, _affine_approx_tol=0.1, _geodesic_mask=True)
             assert pm.renderer_block_rows(geo, inner, 0.0, loader.resolution, h.renderer) is None
+        # a renderer with an offset (MeshRenderer keeps vertex coordinates relative to it, renderer.py:57,86): crop_field
+        # subtracts it from the block before anything else, and so do the rows
+        from oracle import convex
+        approx = dict(render._affine_approximator)
+        shifted = h.renderer_cls([None], offset=np.array([[37.0, -21.0]]), resolution=4.0, affine_approximator=approx,
+                                 affine_approx_tol=0.1, covered_region=convex.box(0.0, 0.0, 639.0, 479.0))
+        boxes = inner + np.tile([37.0, -21.0], 2)
+        rows, shape = pm.renderer_block_rows(shifted, boxes, 2.5, 4.0, h.renderer)
+        for k, bbox in enumerate(boxes):
+            xf, yf, mask = shifted.crop_field(bbox, log_sigma=2.5)
+            cols, rws = np.meshgrid(np.arange(128), np.arange(128))
+            xx, yy = rows[k, 0] + cols * rows[k, 2], rows[k, 1] + rws * rows[k, 3]
+            np.testing.assert_array_equal(xx * rows[k, 4] + yy * rows[k, 5] + rows[k, 6], xf)
+            np.testing.assert_array_equal(xx * rows[k, 7] + yy * rows[k, 8] + rows[k, 9], yf)
+            assert mask.all()
