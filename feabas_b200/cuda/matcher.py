@@ -483,7 +483,7 @@ def renderer_block_rows(render, bboxes, log_sigma, loader_resolution, renderer_m
         if approx['global_residue'] < tol:
             full = np.asarray(approx['global_affine'], dtype=np.float64)
             a, t = full[:2, :2], full[-1, :2]
-        else:                                           # pragma: no cover - needs shapely's STRtree
+        else:
             a, t, res = render.bbox_affine_tform(bbox0, offsetting=False)
             if a is None or not res < tol:
                 return None

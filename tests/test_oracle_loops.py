@@ -170,3 +170,62 @@ def test_renderer_block_rows_follow_the_reference_renderer():
             np.testing.assert_array_equal(xx * rows[k, 4] + yy * rows[k, 5] + rows[k, 6], xf)
             np.testing.assert_array_equal(xx * rows[k, 7] + yy * rows[k, 8] + rows[k, 9], yf)
             assert mask.all()
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason='reference sources not present (GPU box)')
+def test_renderer_block_rows_per_block_fit_branch():
+    """An ELASTIC mesh: the global affine fit misses the tolerance, so ``crop_field`` fits an affine map per block over the
+    triangles that touch it (the reference's own ``bbox_affine_tform`` + ``spatial.fit_affine``, renderer.py:395-416; the
+    STRtree is replaced by a brute-force intersection query).  ``renderer_block_rows`` must take the same branch and
+    reproduce the reference's field bit for bit where the local fit is within tolerance, and give the batch up where
+    it is not."""
+    from oracle import convex
+    from oracle.ref_harness import Harness
+    from feabas_b200.cuda import matcher as pm
+    h = Harness()
+    # regular triangulation of a 640 x 480 section, vertices every 80 px; moving = initial + a smooth bend
+    gx, gy = np.meshgrid(np.arange(0, 641, 80.0) - 0.5, np.arange(0, 481, 80.0) - 0.5)
+    v_init = np.stack((gx.ravel(), gy.ravel()), axis=-1)
+    nxv = gx.shape[1]
+    tris = []
+    for r in range(gx.shape[0] - 1):
+        for c in range(nxv - 1):
+            i = r * nxv + c
+            tris += [(i, i + 1, i + nxv), (i + 1, i + nxv + 1, i + nxv)]
+    tris = np.array(tris)
+    bend = 4e-6 * np.stack(((v_init[:, 1] - 240) ** 2, (v_init[:, 0] - 320) ** 2), axis=-1)     # ~0.3 px over the section, locally affine
+    v_mov = v_init * 1.002 + np.array([4.0, -3.0]) + bend
+
+    class Tree:                                            # shapely.STRtree.query(geom, predicate='intersects')
+        def __init__(self, polys):
+            self.polys = polys
+
+        def query(self, geom, predicate=None):
+            assert predicate == 'intersects'
+            return np.array([k for k, p in enumerate(self.polys) if p.intersection(geom).area > 0], dtype=np.int64)
+
+    with h:
+        spatial = __import__('feabas.spatial', fromlist=['fit_affine'])
+        full = spatial.fit_affine(v_init, v_mov)                       # global fit, renderer.py:97-102 (moving -> image)
+        resid = np.max(np.sum((v_init - (v_mov @ full[:2, :2] + full[-1, :2])) ** 2, axis=-1)) ** 0.5
+        assert resid > 0.12                                            # ... misses a 0.1 px tolerance
+        tree = Tree([convex.ConvexPoly(v_mov[t]) for t in tris])
+        approx = {'global_affine': full, 'global_residue': resid, 'vertices': (tree, tris, v_mov, v_init)}
+        render = h.renderer_cls([None], offset=np.zeros((1, 2)), resolution=4.0, affine_approximator=approx,
+                                affine_approx_tol=0.1, covered_region=convex.box(0.0, 0.0, 639.0, 479.0))
+        boxes = np.array([(100, 80, 164, 144), (300, 200, 364, 264), (420, 330, 484, 394)], dtype=np.float64)
+        got = pm.renderer_block_rows(render, boxes, 2.5, 4.0, h.renderer)
+        assert got is not None
+        rows, shape = got
+        assert shape == (64, 64) and np.ptp(rows[:, 4]) > 0            # one affine map PER BLOCK, not the global one
+        for k, bbox in enumerate(boxes):
+            xf, yf, mask = render.crop_field(bbox, log_sigma=2.5)      # the reference takes its bbox_affine_tform branch
+            cols, rws = np.meshgrid(np.arange(64), np.arange(64))
+            xx, yy = rows[k, 0] + cols * rows[k, 2], rows[k, 1] + rws * rows[k, 3]
+            np.testing.assert_array_equal(xx * rows[k, 4] + yy * rows[k, 5] + rows[k, 6], xf)
+            np.testing.assert_array_equal(xx * rows[k, 7] + yy * rows[k, 8] + rows[k, 9], yf)
+            assert mask.all()
+        # a tolerance the local fits cannot meet: the batch is the host renderer's
+        tight = h.renderer_cls([None], offset=np.zeros((1, 2)), resolution=4.0, affine_approximator=approx,
+                               affine_approx_tol=1e-6, covered_region=convex.box(0.0, 0.0, 639.0, 479.0))
+        assert pm.renderer_block_rows(tight, boxes, 0.0, 4.0, h.renderer) is None
