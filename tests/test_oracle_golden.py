@@ -112,3 +112,23 @@ def test_reference_direct_when_present():
         o = xo.xcorr_oracle(a, b, **kw)
         for x, y in zip(r, o):
             _same(x, y)
+
+
+def test_reference_direct_dog_dtypes():
+    """The oracle's band-pass is the live reference's for every dtype branch of common.py:363 (uint8 -> float32, float32,
+    float64 kept), with and without masks, signed and unsigned.  (The float64 branch is what ``fb_masked_dog_f64`` is
+    compared with on the GPU.)"""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip('reference tree not present (GPU box)')
+    matcher, common, const = ref_loader.load()
+    rng = np.random.default_rng(17)
+    for dtype in (np.uint8, np.float32, np.float64):
+        img = (rng.random((2, 61, 83)) * 255).astype(dtype)
+        mask = rng.random((2, 61, 83)) > 0.15
+        for m in (None, mask):
+            for signed in (True, False):
+                want = common.masked_dog_filter(img, 2.5, mask=m, signed=signed)
+                got = mo.masked_dog_oracle(img, 2.5, mask=m, signed=signed)
+                assert got.dtype == want.dtype == (np.float64 if dtype == np.float64 else np.float32)
+                np.testing.assert_array_equal(got, want)
