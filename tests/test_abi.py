@@ -76,3 +76,30 @@ def test_no_cpu_fallback(lib):
     with pytest.raises(lib.FeabasCudaError, match='no CUDA device'):
         xcorr_fft(a, a)
     assert lib.launch_count() == 0
+
+
+def test_image_entry_points_reject_bad_arguments_and_have_no_cpu_fallback(lib):
+    """Argument errors are reported before anything touches a device (FB_EINVAL / FB_ESIZE with a message); with valid
+    arguments and no GPU every image entry point answers FB_ECUDA "no CUDA device": none computes on the host."""
+    import torch
+    L = lib.lib()
+    buf = np.zeros(64 * 64, np.float64)
+    ptr = buf.ctypes.data
+    assert L.fb_resize_area_frac(ptr, 1, 64, 64, lib.FB_U8, 0.5, 2.5, ptr, 26, 128, 0, None) == -1        # 1/fx < 1: enlarging
+    assert b'shrinks' in L.fb_last_error()
+    assert L.fb_resize_area_frac(ptr, 1, 64, 64, lib.FB_F64, 2.5, 2.5, ptr, 26, 26, 0, None) == -1        # dtype
+    assert L.fb_resize_area_frac(ptr, 1, 64, 64, lib.FB_U8, 2.5, 2.5, ptr, 40, 26, 0, None) == -1         # output too large
+    assert L.fb_masked_dog_f64(ptr, None, 1, 64, 64, 1, 2.5, float('nan'), 0, ptr, ptr, 16, 0, None) == -1   # workspace too small
+    assert b'workspace' in L.fb_last_error()
+    need = L.fb_masked_dog_f64_workspace(1, 64, 64)
+    assert need >= 2 * 64 * 64 * 8
+    assert L.fb_masked_dog_f64(ptr, None, 1, 64, 64, 1, 100.0, float('nan'), 0, ptr, ptr, need, 0, None) == -2   # sigma: radius too large
+    assert L.fb_masked_dog_f64(ptr, ptr, 3, 64, 64, 2, 2.5, float('nan'), 0, ptr, ptr, L.fb_masked_dog_f64_workspace(3, 64, 64), 0, None) == -1
+    assert b'mask_n' in L.fb_last_error()
+    assert L.fb_profile_read(0, ctypes.c_void_p(-1), None, None, 0) in (0, -3)      # FB_ALL_STREAMS: no context yet is not an error
+    if not torch.cuda.is_available():
+        assert L.fb_resize_area_frac(ptr, 1, 64, 64, lib.FB_U8, 2.5, 2.5, ptr, 26, 26, 0, None) == -3
+        assert b'no CUDA device' in L.fb_last_error()
+        assert L.fb_masked_dog_f64(ptr, None, 1, 64, 64, 1, 2.5, float('nan'), 0, ptr, ptr, need, 0, None) == -3
+        assert b'no CUDA device' in L.fb_last_error()
+        assert lib.launch_count() == 0
